@@ -1,0 +1,496 @@
+"""Host side of the B200 barcode / UMI path, mirroring the reference's interfaces for this path.
+
+Names follow the reference (paths under lib/rust/ of the reference checkout):
+  Whitelist            barcode/src/whitelist.rs:452-525        Plain / Trans
+  Posterior            barcode/src/corrector.rs:93-109          the correction strategy's two parameters
+  BarcodeCorrector     barcode/src/corrector.rs:15-71           batch form of correct_barcode
+  ChemistryDef         cr_types/src/chemistry/mod.rs:718-751    only the read layout the path needs
+  FeatureReference     cr_types/src/reference/feature_reference.rs  genes + tethered feature barcodes
+  GemWell              the three hot stages over one GEM well:
+     .make_shard()          cr_lib/src/stages/make_shard.rs          exact match + priors
+     .barcode_correction()  cr_lib/src/stages/barcode_correction.rs  Hamming-1 posterior correction
+     .align_and_count()     cr_lib/src/stages/align_and_count.rs     UMI correction / dedup / counts
+     .count_matrix()        cr_h5/src/count_matrix.rs:382-448        CSC arrays, barcode index
+Everything computes on the GPU through libcrgpu.so (include/crgpu.h); there is no CPU path here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import NO_FEATURE, NO_RANK, LibraryDef, ReadBatch, check, ptr
+
+F64_MAX = 1.7976931348623157e308
+
+# BarcodeSegmentState, barcode/src/lib.rs:270-283
+NOT_CHECKED, VALID_BEFORE_CORRECTION, VALID_AFTER_CORRECTION, INVALID = 0, 1, 2, 3
+# per-read flags (DupInfo, tx_annotation/src/mark_dups.rs:61-72)
+F_UMI_VALID, F_HAS_DUPINFO, F_UMI_CORRECTED, F_LOW_SUPPORT, F_UMI_COUNT = 1, 2, 4, 8, 16
+
+_BASES = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def ascii_matrix(seqs, L: Optional[int] = None) -> np.ndarray:
+    """list of str/bytes of equal length, or an (n, L) uint8 array -> (n, L) uint8 ASCII matrix."""
+    if isinstance(seqs, np.ndarray):
+        a = np.ascontiguousarray(seqs, dtype=np.uint8)
+        if a.ndim == 1 and L:
+            a = a.reshape(-1, L)
+        return a
+    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    if L is None:
+        L = len(bs[0]) if bs else 0
+    if any(len(b) != L for b in bs):
+        raise ValueError("sequences must all have the same length")
+    return np.frombuffer(b"".join(bs), dtype=np.uint8).reshape(len(bs), L).copy()
+
+
+def unpack_2bit(packed: np.ndarray, L: int) -> np.ndarray:
+    """2-bit packed sequences (first base most significant) -> (n, L) ASCII."""
+    p = np.asarray(packed).astype(np.uint64)
+    out = np.empty((p.shape[0], L), dtype=np.uint8)
+    for i in range(L):
+        out[:, i] = _BASES[((p >> np.uint64(2 * (L - 1 - i))) & np.uint64(3)).astype(np.int64)]
+    return out
+
+
+@dataclass
+class Whitelist:
+    """Whitelist::Plain (translated is None) or Whitelist::Trans (raw -> translated)."""
+    seqs: np.ndarray
+    translated: Optional[np.ndarray] = None
+
+    @staticmethod
+    def plain(seqs) -> "Whitelist":
+        return Whitelist(ascii_matrix(seqs))
+
+    @staticmethod
+    def trans(raw, translated) -> "Whitelist":
+        r, t = ascii_matrix(raw), ascii_matrix(translated)
+        if r.shape != t.shape:
+            raise ValueError("raw and translated whitelists differ in shape")
+        return Whitelist(r, t)
+
+    @staticmethod
+    def from_txt(path: str) -> "Whitelist":
+        """A whitelist .txt[.gz]: one sequence per line, or `raw translated` pairs
+        (WhitelistSource::iter, barcode/src/whitelist.rs:255-281)."""
+        import gzip
+
+        op = gzip.open if path.endswith(".gz") else open
+        raw, tr = [], []
+        with op(path, "rt") as f:
+            for line in f:
+                parts = line.split()
+                if not parts:
+                    continue
+                raw.append(parts[0])
+                if len(parts) > 1:
+                    tr.append(parts[1])
+        if tr and len(tr) != len(raw):
+            raise ValueError("not a translation whitelist: some lines have one column")
+        return Whitelist.trans(raw, tr) if tr else Whitelist.plain(raw)
+
+    @property
+    def length(self) -> int:
+        return int(self.seqs.shape[1])
+
+
+@dataclass
+class Posterior:
+    """Posterior { max_expected_barcode_errors, bc_confidence_threshold } with the reference defaults."""
+    max_expected_barcode_errors: float = F64_MAX
+    bc_confidence_threshold: float = 0.975
+
+
+@dataclass
+class ChemistryDef:
+    """Read layout of a chemistry (lib/python/cellranger/chemistry_defs.json)."""
+    name: str
+    bc_offset: int = 0
+    bc_length: int = 16
+    umi_offset: int = 16
+    umi_length: int = 12
+
+    @staticmethod
+    def SC3Pv2() -> "ChemistryDef":
+        return ChemistryDef("SC3Pv2", 0, 16, 16, 10)
+
+    @staticmethod
+    def SC3Pv3() -> "ChemistryDef":
+        return ChemistryDef("SC3Pv3", 0, 16, 16, 12)
+
+
+_PATTERN_RE = re.compile(r"^(?:5[Pp]?[-_]?|\^)?([ACGTN]*)\(BC\)([ACGTN]*)(?:[-_]?3[Pp]?|\$)?$")
+
+
+def tethered_offset(pattern: str) -> int:
+    """Offset of the (BC) capture of a 5'-tethered pattern such as `5PNNNNNNNNNN(BC)` or `^(BC)`
+    (FeatureExtractor::compile_pattern, cr_types/src/reference/feature_extraction.rs:306-342).
+    Only wildcard (N) bases may precede the capture; anything else is outside this path."""
+    m = _PATTERN_RE.match(pattern)
+    if not m or not (pattern.startswith("5") or pattern.startswith("^")):
+        raise ValueError(f"unsupported feature pattern {pattern!r}: need a 5'-tethered pattern with one (BC)")
+    pre, post = m.group(1), m.group(2)
+    if set(pre) - {"N"} or post:
+        raise ValueError(f"unsupported feature pattern {pattern!r}: only N wildcards before (BC) are supported")
+    return len(pre)
+
+
+@dataclass
+class FeatureReference:
+    """Genes (indices 0..n_genes-1) followed by feature-barcode features."""
+    n_genes: int
+    fb_ids: list = field(default_factory=list)
+    fb_seqs: list = field(default_factory=list)       # str, equal length per feature type
+    fb_types: list = field(default_factory=list)      # feature-type id (>= 1) per feature barcode
+    fb_patterns: list = field(default_factory=list)   # pattern string per feature barcode
+
+    @property
+    def n_features(self) -> int:
+        return self.n_genes + len(self.fb_seqs)
+
+    def add_feature_barcode(self, fid: str, seq: str, feature_type: int, pattern: str = "5PNNNNNNNNNN(BC)") -> int:
+        if feature_type < 1:
+            raise ValueError("feature_type 0 is reserved for genes")
+        self.fb_ids.append(fid)
+        self.fb_seqs.append(seq)
+        self.fb_types.append(feature_type)
+        self.fb_patterns.append(pattern)
+        return self.n_features - 1
+
+
+@dataclass
+class CountMatrix:
+    """Feature x barcode matrix in CSC, as write_matrix_h5_helper lays it out
+    (cr_h5/src/count_matrix.rs:382-448): data i32, indices = feature index, indptr i64 per barcode."""
+    barcodes: np.ndarray       # (n_barcodes, L) ASCII, sorted
+    barcode_rank: np.ndarray   # uint32 content rank of each column
+    indptr: np.ndarray         # int64[n_barcodes + 1]
+    indices: np.ndarray        # uint32[nnz]
+    data: np.ndarray           # int32[nnz]
+    n_features: int
+
+    @property
+    def shape(self):
+        return (self.n_features, self.barcodes.shape[0])
+
+    def barcode_strings(self, gem_group: int = 1):
+        return [f"{bytes(b).decode()}-{gem_group}" for b in self.barcodes]
+
+    def mtx_lines(self):
+        """`feature barcode count` triplets, 1-based, in file order
+        (MtxWriter::write_matrix_mtx, cr_lib/src/stages/write_matrix_market.rs:81-120)."""
+        cols = np.repeat(np.arange(self.barcodes.shape[0], dtype=np.int64), np.diff(self.indptr))
+        return [f"{int(f) + 1} {int(c) + 1} {int(v)}" for f, c, v in zip(self.indices, cols, self.data)]
+
+
+class GemWell:
+    """One GEM well on one GPU: whitelist tables, library types, read batches and the three stages."""
+
+    def __init__(self, device: int = 0, posterior: Optional[Posterior] = None, filter_umis: bool = True):
+        self.L = _lib.load()
+        self._ctx = C.c_void_p()
+        check(self.L.crgpu_ctx_create(int(device), C.byref(self._ctx)), "crgpu_ctx_create")
+        self.device = device
+        self.posterior = posterior or Posterior()
+        check(self.L.crgpu_set_params(self._ctx, C.c_double(self.posterior.bc_confidence_threshold),
+                                      C.c_double(self.posterior.max_expected_barcode_errors), int(filter_umis)))
+        self._keep = []
+        self._whitelists = []
+        self._libs = []
+        self._batches = []
+        self.bc_length = None
+        self.umi_length = None
+        self.feature_reference: Optional[FeatureReference] = None
+
+    # ---- lifecycle ----
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self.L.crgpu_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def ctx(self):
+        return self._ctx
+
+    # ---- setup ----
+    def add_whitelist(self, wl: Whitelist) -> int:
+        out = C.c_int(-1)
+        check(self.L.crgpu_whitelist_add(self._ctx, ptr(wl.seqs), C.c_uint64(wl.seqs.shape[0]), wl.length,
+                                         ptr(wl.translated), C.byref(out)), "crgpu_whitelist_add")
+        self._whitelists.append(wl)
+        self.bc_length = wl.length
+        return out.value
+
+    def add_library(self, whitelist: int, chemistry: ChemistryDef, umi_correction: bool = True,
+                    feature_type: int = 0, fb_offset: int = 0, fb_length: int = 0) -> int:
+        """A library type. feature_type 0 = Gene Expression (features come with the reads);
+        otherwise a feature-barcode library whose features carry that feature_type."""
+        d = LibraryDef(whitelist, chemistry.bc_offset, chemistry.bc_length, chemistry.umi_offset,
+                       chemistry.umi_length, int(umi_correction), int(feature_type != 0), feature_type,
+                       fb_offset, fb_length)
+        out = C.c_int(-1)
+        check(self.L.crgpu_library_add(self._ctx, C.byref(d), C.byref(out)), "crgpu_library_add")
+        self._libs.append(d)
+        self.umi_length = chemistry.umi_length
+        return out.value
+
+    def set_feature_reference(self, fr: FeatureReference):
+        ft = np.zeros(fr.n_features, dtype=np.int32)
+        stride = max([len(s) for s in fr.fb_seqs], default=1)
+        seqs = np.full((fr.n_features, stride), ord("A"), dtype=np.uint8)
+        for i, (s, t) in enumerate(zip(fr.fb_seqs, fr.fb_types)):
+            ft[fr.n_genes + i] = t
+            seqs[fr.n_genes + i, :len(s)] = np.frombuffer(s.encode(), dtype=np.uint8)
+        check(self.L.crgpu_features_set(self._ctx, fr.n_features, ptr(ft), ptr(seqs), stride), "crgpu_features_set")
+        self.feature_reference = fr
+
+    def add_reads(self, library: int, r1_seq, r1_qual, feature=None, r2_seq=None, r2_qual=None) -> int:
+        """Host arrays: r1_seq/r1_qual (n, r1_len) uint8, feature uint32[n] (GEX) or r2_* (feature barcode)."""
+        r1_seq = np.ascontiguousarray(r1_seq, dtype=np.uint8)
+        r1_qual = np.ascontiguousarray(r1_qual, dtype=np.uint8)
+        if r1_seq.ndim != 2 or r1_seq.shape != r1_qual.shape:
+            raise ValueError("r1_seq and r1_qual must be (n, r1_len) arrays of the same shape")
+        n, r1_len = r1_seq.shape
+        rb = ReadBatch()
+        rb.n, rb.r1_len = n, r1_len
+        rb.r1_seq, rb.r1_qual = r1_seq.ctypes.data, r1_qual.ctypes.data
+        keep = [r1_seq, r1_qual]
+        if feature is not None:
+            feature = np.ascontiguousarray(feature, dtype=np.uint32)
+            if feature.shape != (n,):
+                raise ValueError("feature must have one entry per read")
+            rb.feature = feature.ctypes.data
+            keep.append(feature)
+        if r2_seq is not None:
+            r2_seq = np.ascontiguousarray(r2_seq, dtype=np.uint8)
+            r2_qual = np.ascontiguousarray(r2_qual, dtype=np.uint8)
+            rb.r2_len = r2_seq.shape[1]
+            rb.r2_seq, rb.r2_qual = r2_seq.ctypes.data, r2_qual.ctypes.data
+            keep += [r2_seq, r2_qual]
+        rb.on_device = 0
+        out = C.c_int(-1)
+        check(self.L.crgpu_reads_add(self._ctx, library, C.byref(rb), C.byref(out)), "crgpu_reads_add")
+        self._keep.append(keep)
+        self._batches.append((library, n))
+        return out.value
+
+    def add_reads_device(self, library: int, n: int, r1_len: int, r1_seq: int, r1_qual: int, feature: int = 0,
+                         r2_len: int = 0, r2_seq: int = 0, r2_qual: int = 0) -> int:
+        """Device pointers (ints), borrowed until clear_reads()."""
+        rb = ReadBatch()
+        rb.n, rb.r1_len, rb.r1_seq, rb.r1_qual = n, r1_len, r1_seq, r1_qual
+        rb.feature = feature or None
+        rb.r2_len, rb.r2_seq, rb.r2_qual = r2_len, r2_seq or None, r2_qual or None
+        rb.on_device = 1
+        out = C.c_int(-1)
+        check(self.L.crgpu_reads_add(self._ctx, library, C.byref(rb), C.byref(out)), "crgpu_reads_add")
+        self._batches.append((library, n))
+        return out.value
+
+    def clear_reads(self):
+        check(self.L.crgpu_reads_clear(self._ctx))
+        self._keep.clear()
+        self._batches.clear()
+
+    # ---- stages ----
+    def make_shard(self):
+        check(self.L.crgpu_pass1(self._ctx), "crgpu_pass1")
+
+    def barcode_correction(self):
+        check(self.L.crgpu_pass2(self._ctx), "crgpu_pass2")
+
+    def align_and_count(self, annotate_reads: bool = False):
+        check(self.L.crgpu_count(self._ctx), "crgpu_count")
+        if annotate_reads:
+            check(self.L.crgpu_annotate_reads(self._ctx), "crgpu_annotate_reads")
+
+    def run(self, annotate_reads: bool = False):
+        self.make_shard()
+        self.barcode_correction()
+        self.align_and_count(annotate_reads)
+
+    def sync(self):
+        check(self.L.crgpu_sync(self._ctx), "crgpu_sync")
+
+    # ---- cross-chunk state ----
+    def n_content(self) -> int:
+        n = C.c_uint64()
+        check(self.L.crgpu_whitelist_size(self._ctx, C.byref(n), None))
+        return int(n.value)
+
+    def set_prior(self, library: int, counts):
+        c = np.ascontiguousarray(counts, dtype=np.uint32)
+        check(self.L.crgpu_prior_set(self._ctx, library, ptr(c), C.c_uint64(c.shape[0])), "crgpu_prior_set")
+
+    def prior(self, library: int) -> np.ndarray:
+        return self._counts(library, 0)
+
+    def corrected_counts(self, library: int) -> np.ndarray:
+        return self._counts(library, 1)
+
+    def _counts(self, library, which):
+        out = np.zeros(self.n_content(), dtype=np.uint32)
+        check(self.L.crgpu_bc_counts_get(self._ctx, library, which, ptr(out), C.c_uint64(out.shape[0])))
+        return out
+
+    def fb_exact_counts(self) -> np.ndarray:
+        n = self.feature_reference.n_features if self.feature_reference else 0
+        out = np.zeros(n, dtype=np.int64)
+        check(self.L.crgpu_fb_counts_get(self._ctx, ptr(out), n))
+        return out
+
+    def prior_dev(self, library: int):
+        p, n = C.c_void_p(), C.c_uint64()
+        check(self.L.crgpu_prior_dev(self._ctx, library, C.byref(p), C.byref(n)))
+        return p.value, int(n.value)
+
+    def valid_counts_dev(self, library: int):
+        p, n = C.c_void_p(), C.c_uint64()
+        check(self.L.crgpu_valid_counts_dev(self._ctx, library, C.byref(p), C.byref(n)))
+        return p.value, int(n.value)
+
+    def fb_counts_dev(self):
+        p, n = C.c_void_p(), C.c_int32()
+        check(self.L.crgpu_fb_counts_dev(self._ctx, C.byref(p), C.byref(n)))
+        return p.value, int(n.value)
+
+    def keys_dev(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        check(self.L.crgpu_keys_dev(self._ctx, C.byref(p), C.byref(n)), "crgpu_keys_dev")
+        return p.value, int(n.value)
+
+    def keys_partition(self, bounds) -> np.ndarray:
+        b = np.ascontiguousarray(bounds, dtype=np.uint32)
+        out = np.zeros(b.shape[0] - 1, dtype=np.uint64)
+        check(self.L.crgpu_keys_partition(self._ctx, b.shape[0] - 1, ptr(b), ptr(out)), "crgpu_keys_partition")
+        return out
+
+    def keys_set(self, dev_ptr: int, n: int):
+        check(self.L.crgpu_keys_set(self._ctx, C.c_void_p(dev_ptr), C.c_uint64(n)), "crgpu_keys_set")
+
+    def set_owned_range(self, lo: int, hi: int):
+        check(self.L.crgpu_set_owned_range(self._ctx, C.c_uint32(lo), C.c_uint32(hi)))
+
+    def key_layout(self) -> dict:
+        v = [C.c_int32() for _ in range(4)]
+        check(self.L.crgpu_key_layout(self._ctx, *[C.byref(x) for x in v]))
+        return dict(rank_shift=v[0].value, feature_shift=v[1].value, lib_shift=v[2].value, umi_bits=v[3].value)
+
+    def stream(self) -> int:
+        p = C.c_void_p()
+        check(self.L.crgpu_stream(self._ctx, C.byref(p)))
+        return p.value or 0
+
+    # ---- results ----
+    def stats(self) -> dict:
+        out = (C.c_uint64 * 16)()
+        check(self.L.crgpu_stats(self._ctx, out))
+        return {k: int(v) for k, v in zip(_lib.STAT_NAMES, out) if not k.startswith("_")}
+
+    def phase_times(self) -> dict:
+        ms = (C.c_float * 32)()
+        n = C.c_int32()
+        names = C.c_char_p()
+        check(self.L.crgpu_phase_times(self._ctx, ms, 32, C.byref(n), C.byref(names)))
+        raw = C.string_at(names, 4096) if n.value else b""
+        parts = raw.split(b"\0")[: n.value]
+        return {p.decode(): float(ms[i]) for i, p in enumerate(parts)}
+
+    def barcode_seqs(self, ranks) -> np.ndarray:
+        r = np.ascontiguousarray(ranks, dtype=np.uint32)
+        out = np.zeros((r.shape[0], self.bc_length), dtype=np.uint8)
+        check(self.L.crgpu_barcode_seqs(self._ctx, ptr(r), C.c_uint64(r.shape[0]), ptr(out)))
+        return out
+
+    def reads(self, batch: int = 0) -> dict:
+        """Per-read results of one batch: bc_rank, bc_state, umi (2-bit), flags, feature."""
+        n = self._batches[batch][1]
+        bc_rank = np.zeros(n, dtype=np.uint32)
+        state = np.zeros(n, dtype=np.uint8)
+        umi = np.zeros(n, dtype=np.uint32)
+        flags = np.zeros(n, dtype=np.uint8)
+        feature = np.zeros(n, dtype=np.uint32)
+        check(self.L.crgpu_reads_get(self._ctx, batch, ptr(bc_rank), ptr(state), ptr(umi), ptr(flags), ptr(feature)),
+              "crgpu_reads_get")
+        return dict(bc_rank=bc_rank, state=state, umi=umi, flags=flags, feature=feature)
+
+    def count_matrix(self) -> CountMatrix:
+        nb, nnz, nf = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(self.L.crgpu_matrix_dims(self._ctx, C.byref(nb), C.byref(nnz), C.byref(nf)), "crgpu_matrix_dims")
+        rank = np.zeros(nb.value, dtype=np.uint32)
+        indptr = np.zeros(nb.value + 1, dtype=np.int64)
+        indices = np.zeros(nnz.value, dtype=np.uint32)
+        data = np.zeros(nnz.value, dtype=np.int32)
+        check(self.L.crgpu_matrix_get(self._ctx, ptr(rank), ptr(indptr), ptr(indices), ptr(data)), "crgpu_matrix_get")
+        return CountMatrix(self.barcode_seqs(rank), rank, indptr, indices, data, int(nf.value))
+
+    def molecules(self) -> np.ndarray:
+        """UmiCount rows: (barcode column, library, feature, umi 2-bit, read_count)."""
+        n = C.c_uint64()
+        check(self.L.crgpu_molecules_count(self._ctx, C.byref(n)))
+        out = np.zeros((n.value, 5), dtype=np.uint32)
+        check(self.L.crgpu_molecules_get(self._ctx, ptr(out)), "crgpu_molecules_get")
+        return out
+
+
+class BarcodeCorrector:
+    """BarcodeCorrector::new(whitelist, bc_counts, strategy) — barcode/src/corrector.rs:15-71 — in batch
+    form: correct_barcodes() takes many invalid (or unchecked) segments at once."""
+
+    def __init__(self, whitelist: Whitelist, bc_counts: Optional[dict] = None,
+                 strategy: Optional[Posterior] = None, device: int = 0):
+        self.gw = GemWell(device=device, posterior=strategy or Posterior())
+        wl = self.gw.add_whitelist(whitelist)
+        self.lib = self.gw.add_library(wl, ChemistryDef("segment", 0, whitelist.length, 0, 0))
+        self.L = whitelist.length
+        content = whitelist.translated if whitelist.translated is not None else whitelist.seqs
+        self._content_sorted = np.unique(content, axis=0)
+        if bc_counts:
+            self.set_counts(bc_counts)
+
+    def set_counts(self, bc_counts: dict):
+        """bc_counts: {content sequence: count} (SimpleHistogram<BcSegSeq>)."""
+        index = {bytes(s): i for i, s in enumerate(self._content_sorted)}
+        prior = np.zeros(len(index), dtype=np.uint32)
+        for k, v in bc_counts.items():
+            kb = k.encode() if isinstance(k, str) else bytes(k)
+            if kb in index:
+                prior[index[kb]] = v
+        self.gw.set_prior(self.lib, prior)
+
+    def correct_barcodes(self, seqs, quals=None):
+        """Returns (corrected ASCII (n, L), state uint8[n]); rows of reads left Invalid keep the input."""
+        s = ascii_matrix(seqs, self.L)
+        q = None if quals is None else ascii_matrix(quals, self.L)
+        n = s.shape[0]
+        rank = np.zeros(n, dtype=np.uint32)
+        state = np.zeros(n, dtype=np.uint8)
+        check(self.gw.L.crgpu_correct_barcodes(self.gw.ctx, self.lib, ptr(s), ptr(q), C.c_uint64(n), ptr(rank),
+                                               ptr(state)), "crgpu_correct_barcodes")
+        out = s.copy()
+        ok = rank != NO_RANK
+        if ok.any():
+            out[ok] = self.gw.barcode_seqs(rank[ok])
+        return out, state
+
+    def close(self):
+        self.gw.close()

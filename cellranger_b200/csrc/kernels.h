@@ -1,0 +1,152 @@
+// kernels.h — host-callable launchers of the libcrgpu kernels (internal).
+#pragma once
+#include "common.cuh"
+
+struct Pass1Args {
+  uint64_t n;
+  int r1_len;
+  const uint8_t* seq;
+  const uint8_t* qual;
+  const uint32_t* feature;  // nullptr: features are resolved later (feature-barcode library)
+  int bc_off, bc_len, umi_off, umi_len;
+  DevWhitelist wl;
+  uint32_t* prior;  // [n_content]; nullptr = do not count
+  uint32_t* bc_out;
+  uint32_t* umi_out;
+  unsigned long long* keys;
+  unsigned long long* counters;  // [0] keys written so far, [1] invalid entries of this batch
+  uint32_t* inv_idx;
+  uint32_t* inv_bc;
+  uint32_t* inv_nmask;
+  uint4* inv_qual;
+  KeyLayout kl;
+  uint32_t lib;
+  int emit_keys;
+  int have_qual;  // 0: qualities absent (crgpu_correct_barcodes with qual == NULL)
+};
+
+struct Pass2Args {
+  uint64_t n_invalid;
+  const uint32_t* inv_idx;
+  const uint32_t* inv_bc;
+  const uint32_t* inv_nmask;
+  const uint4* inv_qual;
+  DevWhitelist wl;
+  const uint32_t* prior;
+  uint32_t* corrected;  // [n_content] counts of corrected reads; may be nullptr
+  uint32_t* bc_out;
+  const uint32_t* umi_out;
+  const uint32_t* feature;  // nullptr when keys are emitted later
+  unsigned long long* keys;
+  unsigned long long* counters;  // [0] keys
+  KeyLayout kl;
+  uint32_t lib;
+  int emit_keys;
+  int have_qual;
+  double threshold;
+  double max_expected_errors;
+  int check_expected_errors;
+};
+
+struct FbArgs {
+  uint64_t n;
+  int r2_len, fb_off, fb_len;
+  const uint8_t* r2_seq;
+  const uint8_t* r2_qual;
+  const uint32_t* fb_keys;   // sorted packed feature sequences of this library [n_fb]
+  const uint32_t* fb_index;  // feature index of each [n_fb]
+  int n_fb;
+  unsigned long long* exact_counts;  // [n_features] (pass 1) or nullptr
+  const double* feat_dist;           // [n_features] (pass 2) or nullptr
+  uint32_t* feature_out;             // [n] resolved feature (pass 2)
+  double threshold;
+};
+
+struct EmitArgs {
+  uint64_t n;
+  const uint32_t* bc_out;
+  const uint32_t* umi_out;
+  const uint32_t* feature;
+  unsigned long long* keys;
+  unsigned long long* counters;
+  KeyLayout kl;
+  uint32_t lib;
+};
+
+void upload_prob_luts(const double* bc_lut256, const double* fb_lut64, cudaStream_t st);
+int launch_pass1(const Pass1Args& a, int n_sms, cudaStream_t st);  // returns #kernel launches
+int launch_pass2(const Pass2Args& a, cudaStream_t st);
+int launch_fb(const FbArgs& a, cudaStream_t st);
+int launch_emit_keys(const EmitArgs& a, cudaStream_t st);
+int launch_valid_counts(const uint32_t* prior, const uint32_t* corrected, uint32_t* out, uint64_t n, cudaStream_t st);
+
+// ---- sort (sort.cu) ----
+// sorts n 64-bit keys on bits [0, end_bit); result in *out (one of the two buffers)
+int sort_keys(unsigned long long* keys, unsigned long long* alt, uint64_t n, int end_bit, void* temp,
+              size_t temp_bytes, unsigned long long** out, cudaStream_t st);
+size_t sort_temp_bytes(uint64_t n);
+
+// ---- dedup / count (dedup_kernels.cu) ----
+struct DedupBuffers {
+  // inputs
+  const unsigned long long* sorted;  // [n_keys]
+  uint64_t n_keys;
+  KeyLayout kl;
+  uint32_t umi_correction_mask;  // bit lib set: UMI correction enabled for that library
+  int filter_umis;
+  // work / outputs (device)
+  unsigned long long* dkeys;  // [cap] distinct keys
+  uint32_t* c0;               // [cap] raw read counts
+  uint32_t* best;             // [cap] index of the correction target (self if uncorrected)
+  unsigned long long* inc;    // [cap] incoming: count << 40 | reads
+  uint8_t* low;               // [cap] low-support flag
+  unsigned long long* key2;   // [cap] (rank, lib, umi, feature) order for the low-support grouping
+  unsigned long long* key2_alt;
+  unsigned long long* lb_desc;  // look-back descriptors
+  uint32_t* tickets;            // atomic tickets (several)
+  unsigned long long* scalars;  // device scalars: [0] n_distinct [1] nnz [2] n_molecules [3] corrected keys [4] low keys
+  void* sort_temp;
+  size_t sort_temp_bytes;
+  // matrix entries
+  uint32_t* ent_rank;     // [cap]
+  uint32_t* ent_feature;  // [cap]
+  uint32_t* ent_count;    // [cap]
+  // molecules: read count (c2) of each; their keys end up in key2
+  uint32_t* mol;  // [cap]
+  uint64_t cap;
+};
+int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st);
+struct MatrixArgs {
+  const uint32_t* valid_counts[CRGPU_MAX_LIBS];
+  int n_libs;
+  uint32_t n_content;
+  uint32_t own_lo, own_hi;
+  uint32_t* col_of_rank;   // [n_content+1] exclusive scan of seen flags
+  uint32_t* barcode_rank;  // [n_barcodes]
+  long long* indptr;       // [n_barcodes+1]
+};
+int run_matrix(DedupBuffers& b, MatrixArgs& m, uint64_t nnz, uint64_t n_mol, uint64_t* n_barcodes_host,
+               cudaStream_t st);
+
+struct AnnotateArgs {
+  uint64_t n;
+  const uint32_t* bc_out;
+  const uint32_t* umi_out;  // raw packed UMI words
+  uint32_t* umi_proc;       // out: processed (corrected) UMI words
+  const uint32_t* feature;
+  uint8_t* flags_out;
+  uint32_t lib;
+  uint64_t read_base;  // global index of read 0 of this batch
+};
+int run_molecule_rows(DedupBuffers& b, const uint32_t* col_of_rank, uint64_t n_mol, uint32_t* out5, cudaStream_t st);
+int run_annotate_prepare(DedupBuffers& b, uint64_t n_distinct, uint32_t* min_read, uint32_t* rep_raw, cudaStream_t st);
+int run_annotate_min(DedupBuffers& b, uint64_t n_distinct, const AnnotateArgs& a, uint32_t* min_read, cudaStream_t st);
+int run_annotate_final(DedupBuffers& b, uint64_t n_distinct, const AnnotateArgs& a, const uint32_t* min_read,
+                       const uint32_t* rep_raw, unsigned long long* read_stats, cudaStream_t st);
+
+// ---- synth (synth.cu) ----
+struct crgpu_synth_params;
+int launch_synth(const crgpu_synth_params* p, const uint32_t* d_wl, const uint32_t* d_cell_rank,
+                 const uint32_t* d_cell_cdf, const uint32_t* d_n_mol, const uint32_t* d_gene_cdf,
+                 const uint32_t* d_fb_cdf, const uint32_t* d_fb_packed, uint64_t start, uint64_t n, uint8_t* r1_seq,
+                 uint8_t* r1_qual, uint32_t* feature, uint8_t* r2_seq, uint8_t* r2_qual, cudaStream_t st);

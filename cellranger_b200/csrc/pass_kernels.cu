@@ -1,0 +1,638 @@
+// pass_kernels.cu — pass 1 (pack + exact whitelist match + priors) and pass 2 (Hamming-1 posterior
+// correction) of the barcode path, plus the feature-barcode kernels. sm_100a.
+//
+// Reference semantics restated here (never copied): lib/rust/cr_types/src/rna_read.rs:285-368
+// (barcode / UMI extraction), lib/rust/barcode/src/whitelist.rs:494-516 (check_and_update),
+// lib/rust/cr_lib/src/make_shard_metrics.rs:171-188 (priors), lib/rust/umi/src/info.rs:20-74 (UMI
+// validity), lib/rust/barcode/src/corrector.rs:111-171 (posterior),
+// lib/rust/cr_types/src/reference/feature_extraction.rs:34-117,447-471 (feature barcodes).
+#include "kernels.h"
+
+__constant__ double c_bc_prob[256];  // probability(q) = pow(10, -(q-33)/10), filled by host libm
+__constant__ double c_fb_prob[64];   // pow(10, -qv/10), qv = 0..33
+
+void upload_prob_luts(const double* bc_lut256, const double* fb_lut64, cudaStream_t st) {
+  cudaMemcpyToSymbolAsync(c_bc_prob, bc_lut256, 256 * sizeof(double), 0, cudaMemcpyHostToDevice, st);
+  cudaMemcpyToSymbolAsync(c_fb_prob, fb_lut64, 64 * sizeof(double), 0, cudaMemcpyHostToDevice, st);
+}
+
+// ---------------------------------------------------------------------------
+// mbarrier / bulk-copy (TMA, 1-D) wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// per-read logic shared by the staged and the generic kernel
+// ---------------------------------------------------------------------------
+struct ReadResult {
+  uint32_t bc_word;   // state | rank
+  uint32_t umi_word;  // flags | packed
+  bool emit_key;
+  unsigned long long key;
+  bool invalid;
+};
+
+__device__ __forceinline__ unsigned long long make_key(const KeyLayout& kl, uint32_t rank, uint32_t feature,
+                                                       uint32_t lib, uint32_t umi) {
+  return ((unsigned long long)rank << kl.rank_shift) | ((unsigned long long)feature << kl.feature_shift) |
+         ((unsigned long long)lib << kl.lib_shift) | (unsigned long long)umi;
+}
+
+__device__ __forceinline__ void classify_read(const Pass1Args& a, uint32_t bc, uint32_t nmask, uint32_t umi,
+                                              bool umi_has_n, bool umi_lowq, uint32_t feature, ReadResult* r) {
+  // UmiInfo::new: valid = !(has_n || is_homopolymer || low_min_qual)
+  uint32_t rep = 0x55555555u & mask_bits(2 * a.umi_len);
+  bool homopolymer = umi == (umi & 3u) * rep;
+  bool umi_valid = !(umi_has_n || homopolymer || umi_lowq) && a.umi_len > 0;
+  r->umi_word = (umi & UMI_SEQ_MASK) | (umi_valid ? UMI_VALID_BIT : 0u) | (umi_has_n ? UMI_HASN_BIT : 0u);
+  int idx = nmask ? -1 : wl_find(a.wl, bc);
+  r->emit_key = false;
+  r->key = 0ull;
+  if (idx >= 0) {
+    uint32_t rank = wl_rank_of(a.wl, idx);
+    if (a.prior) atomicAdd(a.prior + rank, 1u);
+    r->bc_word = (ST_VALID_BEFORE << BC_STATE_SHIFT) | rank;
+    r->invalid = false;
+    if (a.emit_keys && umi_valid && feature != NO_FEATURE) {
+      r->emit_key = true;
+      r->key = make_key(a.kl, rank, feature, a.lib, umi);
+    }
+  } else {
+    r->bc_word = (ST_INVALID << BC_STATE_SHIFT) | BC_RANK_MASK;
+    r->invalid = true;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Pass 1, staged: persistent CTAs, tiles of THREADS*RPT reads brought into shared memory by 1-D bulk
+// copies (TMA) behind a STAGES-deep mbarrier ring, so HBM sees only full-line coalesced requests.
+// Layout assumed: barcode = R1[0:16], UMI = R1[16:16+UMI_LEN], R1_LEN >= 16+UMI_LEN.
+// ---------------------------------------------------------------------------
+template <int R1_LEN>
+__device__ __forceinline__ void load_record(const uint8_t* base, int j, uint32_t (&w)[(R1_LEN + 3) / 4]) {
+  constexpr int NW = (R1_LEN + 3) / 4;
+  if constexpr (R1_LEN % 4 == 0) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(base + (size_t)j * R1_LEN);
+#pragma unroll
+    for (int i = 0; i < NW; i++) w[i] = p[i];
+  } else {
+    uint32_t o = (uint32_t)j * R1_LEN;
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(base + (o & ~3u));
+    uint32_t sh = (o & 3u) * 8u;
+    uint32_t x[NW + 1];
+#pragma unroll
+    for (int i = 0; i <= NW; i++) x[i] = p[i];
+#pragma unroll
+    for (int i = 0; i < NW; i++) w[i] = __funnelshift_r(x[i], x[i + 1], sh);
+  }
+}
+
+template <int R1_LEN, int UMI_LEN, int THREADS, int RPT, int STAGES>
+__global__ void __launch_bounds__(THREADS) pass1_staged_kernel(const Pass1Args a) {
+  constexpr int TILE = THREADS * RPT;
+  constexpr int SEQ_BYTES = TILE * R1_LEN;
+  constexpr int REC_PAD = 16;  // the unaligned record loader reads one word past a record
+  constexpr int STAGE_BYTES = 2 * (SEQ_BYTES + REC_PAD) + TILE * 4;
+  constexpr int NW = (R1_LEN + 3) / 4;
+  static_assert(SEQ_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t mbar[STAGES];
+  __shared__ uint32_t scan_a[THREADS / 32 + 1], scan_b[THREADS / 32 + 1];
+  __shared__ unsigned long long base_bcast;
+
+  const int tid = threadIdx.x;
+  const uint64_t n_tiles = (a.n + TILE - 1) / TILE;
+  const bool have_feat = a.feature != nullptr;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) mbar_init(&mbar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto stage_seq = [&](int s) { return smem + (size_t)s * STAGE_BYTES; };
+  auto stage_qual = [&](int s) { return smem + (size_t)s * STAGE_BYTES + SEQ_BYTES + REC_PAD; };
+  auto stage_feat = [&](int s) {
+    return reinterpret_cast<uint32_t*>(smem + (size_t)s * STAGE_BYTES + 2 * (SEQ_BYTES + REC_PAD));
+  };
+  // thread 0: start the copies of a FULL tile into stage s
+  auto issue = [&](uint64_t tile, int s) {
+    uint64_t first = tile * TILE;
+    if (first + TILE <= a.n) {
+      uint32_t bytes = 2 * SEQ_BYTES + (have_feat ? TILE * 4 : 0);
+      mbar_expect_tx(&mbar[s], bytes);
+      bulk_g2s(stage_seq(s), a.seq + first * R1_LEN, SEQ_BYTES, &mbar[s]);
+      bulk_g2s(stage_qual(s), a.qual + first * R1_LEN, SEQ_BYTES, &mbar[s]);
+      if (have_feat) bulk_g2s(stage_feat(s), a.feature + first, TILE * 4, &mbar[s]);
+    }
+  };
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) {
+      uint64_t tile = blockIdx.x + (uint64_t)s * gridDim.x;
+      if (tile < n_tiles) issue(tile, s);
+    }
+  }
+
+  uint32_t it = 0;
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+    const int s = it % STAGES;
+    const uint32_t parity = (it / STAGES) & 1u;
+    const uint64_t first = tile * TILE;
+    const int cnt = (int)((a.n - first) < (uint64_t)TILE ? (a.n - first) : (uint64_t)TILE);
+    if (cnt == TILE) {
+      mbar_wait(&mbar[s], parity);
+    } else {
+      // the partial last tile: plain cooperative loads
+      const uint8_t* gs = a.seq + first * R1_LEN;
+      const uint8_t* gq = a.qual + first * R1_LEN;
+      uint8_t* ss = stage_seq(s);
+      uint8_t* sq = stage_qual(s);
+      for (int b = tid; b < cnt * R1_LEN; b += THREADS) {
+        ss[b] = gs[b];
+        sq[b] = gq[b];
+      }
+      if (have_feat)
+        for (int b = tid; b < cnt; b += THREADS) stage_feat(s)[b] = a.feature[first + b];
+      __syncthreads();
+    }
+
+    ReadResult res[RPT];
+    uint32_t nmask_r[RPT], bc_r[RPT];
+    uint4 bcq_r[RPT];
+    uint32_t n_key = 0, n_inv = 0;
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
+      const int j = tid + k * THREADS;
+      res[k].emit_key = false;
+      res[k].invalid = false;
+      if (j < cnt) {
+        uint32_t ws[NW], wq[NW];
+        load_record<R1_LEN>(stage_seq(s), j, ws);
+        load_record<R1_LEN>(stage_qual(s), j, wq);
+        uint32_t bad0, bad1, bad2, bad3;
+        uint32_t bc = (pack4(ws[0], &bad0) << 24) | (pack4(ws[1], &bad1) << 16) | (pack4(ws[2], &bad2) << 8) |
+                      pack4(ws[3], &bad3);
+        uint32_t nmask = 0;
+        if (bad0 | bad1 | bad2 | bad3) {
+          // bit `pos` for every non-ACGT base (rare path)
+          uint32_t bb[4] = {bad0, bad1, bad2, bad3};
+#pragma unroll
+          for (int wd = 0; wd < 4; wd++)
+#pragma unroll
+            for (int by = 0; by < 4; by++)
+              if (bb[wd] & (0x80u << (8 * by))) nmask |= 1u << (wd * 4 + by);
+        }
+        // UMI
+        uint32_t umi = 0, ubad = 0, ulow = 0;
+        constexpr int UW = (UMI_LEN + 3) / 4;
+#pragma unroll
+        for (int u = 0; u < UW; u++) {
+          uint32_t w = ws[4 + u], q = wq[4 + u];
+          constexpr int full = UMI_LEN / 4;
+          uint32_t bmask = 0xFFFFFFFFu;
+          if (u >= full) {  // partial last word: keep UMI_LEN % 4 bytes
+            bmask = (1u << (8 * (UMI_LEN % 4))) - 1u;
+            w = (w & bmask) | (0x41414141u & ~bmask);
+            q = (q & bmask) | (0x49494949u & ~bmask);
+          }
+          uint32_t bad;
+          uint32_t p = pack4(w, &bad);
+          ubad |= bad & bmask;
+          ulow |= lowqual4(q) & bmask;
+          umi = (umi << 8) | p;
+        }
+        if constexpr (UMI_LEN % 4 != 0) umi >>= 2 * (4 - UMI_LEN % 4);
+        uint32_t feature = have_feat ? stage_feat(s)[j] : NO_FEATURE;
+        classify_read(a, bc, nmask, umi, ubad != 0, ulow != 0, feature, &res[k]);
+        nmask_r[k] = nmask;
+        bc_r[k] = bc;
+        bcq_r[k] = make_uint4(wq[0], wq[1], wq[2], wq[3]);
+        n_key += res[k].emit_key;
+        n_inv += res[k].invalid;
+      }
+    }
+    // block-wide placement of this tile's keys and invalid entries
+    uint32_t tot_key, tot_inv;
+    uint32_t off_key = block_exclusive_scan<THREADS>(n_key, &tot_key, scan_a);
+    uint32_t off_inv = block_exclusive_scan<THREADS>(n_inv, &tot_inv, scan_b);
+    if (tid == 0)
+      base_bcast = (tot_key | tot_inv)
+                       ? atomicAdd(a.counters, (unsigned long long)tot_key | ((unsigned long long)tot_inv << 32))
+                       : 0ull;
+    __syncthreads();  // also: every thread is done reading stage s
+    const unsigned long long base = base_bcast;
+    uint64_t kpos = (base & 0xFFFFFFFFull) + off_key;
+    uint64_t ipos = (base >> 32) + off_inv;
+    if (tid == 0) {
+      uint64_t next = tile + (uint64_t)STAGES * gridDim.x;
+      if (next < n_tiles) issue(next, s);
+    }
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
+      const int j = tid + k * THREADS;
+      if (j < cnt) {
+        uint64_t gi = first + j;
+        a.bc_out[gi] = res[k].bc_word;
+        a.umi_out[gi] = res[k].umi_word;
+        if (res[k].emit_key) a.keys[kpos++] = res[k].key;
+        if (res[k].invalid) {
+          a.inv_idx[ipos] = (uint32_t)gi;
+          a.inv_bc[ipos] = bc_r[k];
+          a.inv_nmask[ipos] = nmask_r[k];
+          a.inv_qual[ipos] = bcq_r[k];
+          ipos++;
+        }
+      }
+    }
+  }
+}
+
+// counters layout for the staged kernel: one packed 64-bit word (keys in the low half). The host keeps
+// the key counter and the per-batch invalid counter apart, so the kernel works on a scratch word that is
+// split afterwards.
+__global__ void split_counter_kernel(unsigned long long* packed, unsigned long long* keys_total,
+                                     unsigned long long* inv_total) {
+  unsigned long long v = *packed;
+  *keys_total = v & 0xFFFFFFFFull;
+  *inv_total = v >> 32;
+}
+__global__ void merge_counter_kernel(unsigned long long* packed, const unsigned long long* keys_total) {
+  *packed = *keys_total;  // invalid count of a new batch starts at 0
+}
+
+// ---------------------------------------------------------------------------
+// Pass 1, generic layout (any offsets / lengths <= 16): one thread per read, direct loads.
+// Used for unusual chemistries and for the corrector batch seam.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pass1_generic_kernel(const Pass1Args a) {
+  __shared__ uint32_t scan_a[9], scan_b[9];
+  __shared__ unsigned long long base_bcast;
+  const uint64_t n_blocks_work = (a.n + 255) / 256;
+  for (uint64_t blk = blockIdx.x; blk < n_blocks_work; blk += gridDim.x) {
+    uint64_t gi = blk * 256 + threadIdx.x;
+    ReadResult res;
+    res.emit_key = false;
+    res.invalid = false;
+    uint32_t bc = 0, nmask = 0;
+    uint8_t q16[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) q16[i] = 'I';
+    if (gi < a.n) {
+      const uint8_t* s = a.seq + gi * a.r1_len;
+      const uint8_t* q = a.have_qual ? a.qual + gi * a.r1_len : nullptr;
+      for (int i = 0; i < a.bc_len; i++) {
+        uint8_t c = s[a.bc_off + i];
+        uint32_t code = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+        if (code == 4u) {
+          nmask |= 1u << i;
+          code = 0u;
+        }
+        bc = (bc << 2) | code;
+        if (q) q16[i] = q[a.bc_off + i];
+      }
+      uint32_t umi = 0;
+      bool uhasn = false, ulow = false;
+      for (int i = 0; i < a.umi_len; i++) {
+        uint8_t c = s[a.umi_off + i];
+        uint32_t code = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+        if (code == 4u) {
+          uhasn = true;
+          code = 0u;
+        }
+        umi = (umi << 2) | code;
+        if (q) ulow |= (uint8_t)(q[a.umi_off + i] - 33) < 10;
+      }
+      uint32_t feature = a.feature ? a.feature[gi] : NO_FEATURE;
+      classify_read(a, bc, nmask, umi, uhasn, ulow, feature, &res);
+    }
+    uint32_t tot_key, tot_inv;
+    uint32_t off_key = block_exclusive_scan<256>(res.emit_key ? 1u : 0u, &tot_key, scan_a);
+    uint32_t off_inv = block_exclusive_scan<256>(res.invalid ? 1u : 0u, &tot_inv, scan_b);
+    if (threadIdx.x == 0)
+      base_bcast = (tot_key | tot_inv)
+                       ? atomicAdd(a.counters, (unsigned long long)tot_key | ((unsigned long long)tot_inv << 32))
+                       : 0ull;
+    __syncthreads();
+    const unsigned long long base = base_bcast;
+    if (gi < a.n) {
+      a.bc_out[gi] = res.bc_word;
+      a.umi_out[gi] = res.umi_word;
+      if (res.emit_key) a.keys[(base & 0xFFFFFFFFull) + off_key] = res.key;
+      if (res.invalid) {
+        uint64_t ipos = (base >> 32) + off_inv;
+        a.inv_idx[ipos] = (uint32_t)gi;
+        a.inv_bc[ipos] = bc;
+        a.inv_nmask[ipos] = nmask;
+        uint4 qq;
+        qq.x = q16[0] | (q16[1] << 8) | (q16[2] << 16) | ((uint32_t)q16[3] << 24);
+        qq.y = q16[4] | (q16[5] << 8) | (q16[6] << 16) | ((uint32_t)q16[7] << 24);
+        qq.z = q16[8] | (q16[9] << 8) | (q16[10] << 16) | ((uint32_t)q16[11] << 24);
+        qq.w = q16[12] | (q16[13] << 8) | (q16[14] << 16) | ((uint32_t)q16[15] << 24);
+        a.inv_qual[ipos] = qq;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int launch_pass1(const Pass1Args& a, int n_sms, cudaStream_t st) {
+  if (a.n == 0) return 0;
+  const bool std_layout = a.bc_off == 0 && a.bc_len == 16 && a.umi_off == 16 && a.have_qual &&
+                          ((uintptr_t)a.seq % 16 == 0) && ((uintptr_t)a.qual % 16 == 0) &&
+                          (a.feature == nullptr || (uintptr_t)a.feature % 16 == 0);
+  constexpr int THREADS = 256, RPT = 2, STAGES = 2;
+  constexpr int TILE = THREADS * RPT;
+  if (std_layout && a.r1_len == 28 && a.umi_len == 12) {
+    auto kern = pass1_staged_kernel<28, 12, THREADS, RPT, STAGES>;
+    size_t smem = (size_t)STAGES * (2 * (TILE * 28 + 16) + TILE * 4);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
+    uint64_t tiles = (a.n + TILE - 1) / TILE;
+    int grid = (int)std::min<uint64_t>(tiles, (uint64_t)n_sms * (per_sm > 0 ? per_sm : 1));
+    kern<<<grid, THREADS, smem, st>>>(a);
+    return 1;
+  }
+  if (std_layout && a.r1_len == 26 && a.umi_len == 10) {
+    auto kern = pass1_staged_kernel<26, 10, THREADS, RPT, STAGES>;
+    size_t smem = (size_t)STAGES * (2 * (TILE * 26 + 16) + TILE * 4);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
+    uint64_t tiles = (a.n + TILE - 1) / TILE;
+    int grid = (int)std::min<uint64_t>(tiles, (uint64_t)n_sms * (per_sm > 0 ? per_sm : 1));
+    kern<<<grid, THREADS, smem, st>>>(a);
+    return 1;
+  }
+  uint64_t blocks = (a.n + 255) / 256;
+  int grid = (int)std::min<uint64_t>(blocks, (uint64_t)n_sms * 8);
+  pass1_generic_kernel<<<grid, 256, 0, st>>>(a);
+  return 1;
+}
+
+// ---------------------------------------------------------------------------
+// Pass 2: Posterior::correct_barcode for every invalid read (corrector.rs:111-165).
+// One thread per invalid read: the neighbour mask comes from n_ord bucket scans, then the likelihoods are
+// accumulated strictly in the reference's (position ascending, base A,C,G,T) order with separate f64
+// multiply and add (no FMA), so every accept/reject decision is bit-identical.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pass2_kernel(const Pass2Args a) {
+  __shared__ uint32_t scan_a[9];
+  __shared__ unsigned long long base_bcast;
+  const uint64_t n_blocks_work = (a.n_invalid + 255) / 256;
+  for (uint64_t blk = blockIdx.x; blk < n_blocks_work; blk += gridDim.x) {
+    const uint64_t e = blk * 256 + threadIdx.x;
+    bool emit = false;
+    unsigned long long key = 0ull;
+    if (e < a.n_invalid) {
+      const uint32_t idx = a.inv_idx[e];
+      const uint32_t q = a.inv_bc[e];
+      const uint32_t nmask = a.inv_nmask[e];
+      const uint4 qq = a.inv_qual[e];
+      const uint32_t qw[4] = {qq.x, qq.y, qq.z, qq.w};
+      const int L = a.wl.L;
+      unsigned long long m;
+      if (nmask == 0u) {
+        m = wl_neighbor_mask(a.wl, q);
+      } else if ((nmask & (nmask - 1u)) == 0u) {
+        // a single non-ACGT base: only the four trials at that position can be whitelist sequences
+        int pn = __ffs(nmask) - 1;
+        m = 0xFull << (4 * pn);
+      } else {
+        m = 0ull;  // every trial still holds a non-ACGT base
+      }
+      bool have_best = false;
+      double best = 0.0, total = 0.0;
+      uint32_t best_rank = 0;
+      while (m) {
+        int bit = __ffsll((long long)m) - 1;
+        m &= m - 1ull;
+        int pos = bit >> 2;
+        uint32_t base = bit & 3;
+        int sh = 2 * (L - 1 - pos);
+        uint32_t trial = (q & ~(3u << sh)) | (base << sh);
+        int widx = wl_find(a.wl, trial);
+        if (widx < 0) continue;
+        uint32_t rank = wl_rank_of(a.wl, widx);
+        uint32_t raw = __ldg(a.prior + rank);
+        uint32_t qv = a.have_qual ? ((qw[pos >> 2] >> (8 * (pos & 3))) & 0xFFu) : 66u;
+        if (qv > 66u) qv = 66u;  // BC_MAX_QV
+        double lik = __dmul_rn(c_bc_prob[qv], (double)(1ull + (unsigned long long)raw));
+        if (!have_best || lik > best || (lik == best && rank >= best_rank)) {
+          have_best = true;
+          best = lik;
+          best_rank = rank;
+        }
+        total = __dadd_rn(total, lik);
+      }
+      bool accept = false;
+      if (have_best) {
+        bool ee_ok = true;
+        if (a.check_expected_errors) {
+          double ee = 0.0;
+          if (a.have_qual)
+            for (int i = 0; i < L; i++) ee = __dadd_rn(ee, c_bc_prob[(qw[i >> 2] >> (8 * (i & 3))) & 0xFFu]);
+          ee_ok = ee < a.max_expected_errors;
+        }
+        accept = ee_ok && (__ddiv_rn(best, total) >= a.threshold);
+      }
+      if (accept) {
+        a.bc_out[idx] = (ST_VALID_AFTER << BC_STATE_SHIFT) | best_rank;
+        if (a.corrected) atomicAdd(a.corrected + best_rank, 1u);
+        if (a.emit_keys) {
+          uint32_t uw = a.umi_out[idx];
+          uint32_t feature = a.feature ? a.feature[idx] : NO_FEATURE;
+          if ((uw & UMI_VALID_BIT) && feature != NO_FEATURE) {
+            emit = true;
+            key = make_key(a.kl, best_rank, feature, a.lib, uw & UMI_SEQ_MASK);
+          }
+        }
+      }
+    }
+    if (a.emit_keys) {
+      uint32_t tot;
+      uint32_t off = block_exclusive_scan<256>(emit ? 1u : 0u, &tot, scan_a);
+      if (threadIdx.x == 0) base_bcast = tot ? atomicAdd(a.counters, (unsigned long long)tot) : 0ull;
+      __syncthreads();
+      if (emit) a.keys[base_bcast + off] = key;
+      __syncthreads();
+    }
+  }
+}
+
+int launch_pass2(const Pass2Args& a, cudaStream_t st) {
+  if (a.n_invalid == 0) return 0;
+  uint64_t blocks = (a.n_invalid + 255) / 256;
+  int grid = (int)std::min<uint64_t>(blocks, 148ull * 64);
+  pass2_kernel<<<grid, 256, 0, st>>>(a);
+  return 1;
+}
+
+// ---------------------------------------------------------------------------
+// Feature-barcode libraries: tethered fixed-offset capture R2[fb_off : fb_off+fb_len].
+// exact_counts != nullptr: MAKE_SHARD pre-count of exact captures (make_shard_metrics.rs:337-345).
+// feat_dist   != nullptr: ALIGN_AND_COUNT extraction with Hamming-1 posterior correction
+// (feature_extraction.rs:34-117,447-471).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int fb_find(const uint32_t* __restrict__ keys, int n, uint32_t q) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    uint32_t e = keys[mid];
+    if (e == q) return mid;
+    if (e < q)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return -1;
+}
+
+__global__ void __launch_bounds__(256) fb_kernel(const FbArgs a) {
+  extern __shared__ uint32_t s_fb[];  // keys[n_fb] | index[n_fb]
+  uint32_t* s_keys = s_fb;
+  uint32_t* s_index = s_fb + a.n_fb;
+  for (int i = threadIdx.x; i < a.n_fb; i += blockDim.x) {
+    s_keys[i] = a.fb_keys[i];
+    s_index[i] = a.fb_index[i];
+  }
+  __syncthreads();
+  for (uint64_t gi = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; gi < a.n; gi += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t out = NO_FEATURE;
+    if (a.r2_len >= a.fb_off + a.fb_len) {
+      const uint8_t* s = a.r2_seq + gi * a.r2_len + a.fb_off;
+      const uint8_t* qp = a.r2_qual + gi * a.r2_len + a.fb_off;
+      uint32_t q = 0, nmask = 0;
+      for (int i = 0; i < a.fb_len; i++) {
+        uint8_t c = s[i];
+        uint32_t code = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+        if (code == 4u) {
+          nmask |= 1u << i;
+          code = 0u;
+        }
+        q = (q << 2) | code;
+      }
+      int hit = nmask ? -1 : fb_find(s_keys, a.n_fb, q);
+      if (hit >= 0) {
+        out = s_index[hit];
+      } else if (a.feat_dist && (nmask & (nmask - 1u)) == 0u) {
+        // correct_feature_barcode for a single candidate: trials in (position, A,C,G,T) order
+        double sum = 0.0, best = -1.0;
+        uint32_t best_f = NO_FEATURE;
+        for (int i = 0; i < a.fb_len; i++) {
+          if (nmask && !((nmask >> i) & 1u)) continue;  // other positions keep the N and cannot match
+          int sh = 2 * (a.fb_len - 1 - i);
+          uint32_t orig = nmask ? 4u : ((q >> sh) & 3u);
+          for (uint32_t b = 0; b < 4; b++) {
+            if (b == orig) continue;
+            uint32_t trial = (q & ~(3u << sh)) | (b << sh);
+            int h = fb_find(s_keys, a.n_fb, trial);
+            if (h < 0) continue;
+            uint32_t f = s_index[h];
+            uint32_t qv = (uint8_t)(qp[i] - 33);
+            if (qv > 33u) qv = 33u;  // FEATURE_MAX_QV
+            double lik = __dmul_rn(a.feat_dist[f], c_fb_prob[qv]);
+            sum = __dadd_rn(sum, lik);
+            if (lik > best) {
+              best = lik;
+              best_f = f;
+            }
+          }
+        }
+        if (best_f != NO_FEATURE && __ddiv_rn(best, sum) >= a.threshold) out = best_f;
+      }
+      if (a.exact_counts && hit >= 0) atomicAdd(a.exact_counts + out, 1ull);
+    }
+    if (a.feature_out) a.feature_out[gi] = out;
+  }
+}
+
+int launch_fb(const FbArgs& a, cudaStream_t st) {
+  if (a.n == 0) return 0;
+  uint64_t blocks = (a.n + 255) / 256;
+  int grid = (int)std::min<uint64_t>(blocks, 148ull * 8);
+  fb_kernel<<<grid, 256, (size_t)a.n_fb * 8, st>>>(a);
+  return 1;
+}
+
+// keys of a whole batch after its features are known (feature-barcode libraries)
+__global__ void __launch_bounds__(256) emit_keys_kernel(const EmitArgs a) {
+  __shared__ uint32_t scan_a[9];
+  __shared__ unsigned long long base_bcast;
+  const uint64_t n_blocks_work = (a.n + 255) / 256;
+  for (uint64_t blk = blockIdx.x; blk < n_blocks_work; blk += gridDim.x) {
+    uint64_t gi = blk * 256 + threadIdx.x;
+    bool emit = false;
+    unsigned long long key = 0;
+    if (gi < a.n) {
+      uint32_t bw = a.bc_out[gi], uw = a.umi_out[gi], f = a.feature[gi];
+      uint32_t st = bw >> BC_STATE_SHIFT;
+      if ((st == ST_VALID_BEFORE || st == ST_VALID_AFTER) && (uw & UMI_VALID_BIT) && f != NO_FEATURE) {
+        emit = true;
+        key = make_key(a.kl, bw & BC_RANK_MASK, f, a.lib, uw & UMI_SEQ_MASK);
+      }
+    }
+    uint32_t tot;
+    uint32_t off = block_exclusive_scan<256>(emit ? 1u : 0u, &tot, scan_a);
+    if (threadIdx.x == 0) base_bcast = tot ? atomicAdd(a.counters, (unsigned long long)tot) : 0ull;
+    __syncthreads();
+    if (emit) a.keys[base_bcast + off] = key;
+    __syncthreads();
+  }
+}
+
+int launch_emit_keys(const EmitArgs& a, cudaStream_t st) {
+  if (a.n == 0) return 0;
+  uint64_t blocks = (a.n + 255) / 256;
+  int grid = (int)std::min<uint64_t>(blocks, 148ull * 16);
+  emit_keys_kernel<<<grid, 256, 0, st>>>(a);
+  return 1;
+}
+
+__global__ void valid_counts_kernel(const uint32_t* prior, const uint32_t* corrected, uint32_t* out, uint64_t n) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    out[i] = prior[i] + corrected[i];
+}
+int launch_valid_counts(const uint32_t* prior, const uint32_t* corrected, uint32_t* out, uint64_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  int grid = (int)std::min<uint64_t>((n + 255) / 256, 148ull * 16);
+  valid_counts_kernel<<<grid, 256, 0, st>>>(prior, corrected, out, n);
+  return 1;
+}
+
+// exported for crgpu.cu
+void launch_split_counter(unsigned long long* packed, unsigned long long* keys_total, unsigned long long* inv_total,
+                          cudaStream_t st) {
+  split_counter_kernel<<<1, 1, 0, st>>>(packed, keys_total, inv_total);
+}
+void launch_merge_counter(unsigned long long* packed, const unsigned long long* keys_total, cudaStream_t st) {
+  merge_counter_kernel<<<1, 1, 0, st>>>(packed, keys_total);
+}

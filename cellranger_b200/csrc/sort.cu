@@ -1,0 +1,222 @@
+// sort.cu — device radix sort of the packed 64-bit dedup keys.
+//
+// Least-significant-digit radix sort, 8 bits per pass, restricted to the bits the key layout really
+// uses (KeyLayout::total_bits), so a 3' v2 key (55 bits) takes 7 passes and a 3' v3 key (62 bits) 8.
+// One upfront kernel builds the digit histograms of every pass; each pass is then a single "onesweep"
+// kernel: a tile of keys is ranked inside the block, the tile's digit counts are published through a
+// chained (decoupled look-back) scan, and the keys are scattered through shared memory so every digit
+// bin is written as one contiguous run.
+#include <algorithm>
+
+#include "kernels.h"
+
+namespace {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int SORT_THREADS = 512;
+constexpr int SORT_ITEMS = 12;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 6144 keys = 48 KB
+constexpr int MAX_PASSES = 8;
+
+// ---- upfront histograms: hist[pass][digit] over all keys ----
+__global__ void __launch_bounds__(512) radix_hist_kernel(const unsigned long long* __restrict__ keys, uint64_t n,
+                                                         int n_passes, unsigned long long* __restrict__ hist) {
+  __shared__ uint32_t s_hist[MAX_PASSES * RADIX];
+  for (int i = threadIdx.x; i < n_passes * RADIX; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    unsigned long long k = keys[i];
+    for (int p = 0; p < n_passes; p++) atomicAdd(&s_hist[p * RADIX + (int)((k >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_passes * RADIX; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(hist + i, (unsigned long long)s_hist[i]);
+}
+
+// exclusive scan of each pass's 256 bins (one block per pass)
+__global__ void radix_scan_hist_kernel(unsigned long long* hist) {
+  __shared__ unsigned long long s[RADIX];
+  unsigned long long* h = hist + (size_t)blockIdx.x * RADIX;
+  s[threadIdx.x] = h[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long run = 0;
+    for (int d = 0; d < RADIX; d++) {
+      unsigned long long c = s[d];
+      s[d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  h[threadIdx.x] = s[threadIdx.x];
+}
+
+// ---- one onesweep pass ----
+// desc[tile * RADIX + digit]: {status:2 | count:62} chained-scan descriptors of this pass.
+__global__ void __launch_bounds__(SORT_THREADS) radix_onesweep_kernel(const unsigned long long* __restrict__ in,
+                                                                      unsigned long long* __restrict__ out, uint64_t n,
+                                                                      int shift,
+                                                                      const unsigned long long* __restrict__ bin_base,
+                                                                      unsigned long long* __restrict__ desc,
+                                                                      uint32_t* __restrict__ ticket) {
+  constexpr int WARPS = SORT_THREADS / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_raw);         // SORT_TILE keys
+  uint32_t* s_warp_hist = reinterpret_cast<uint32_t*>(smem_raw + SORT_TILE * 8);         // WARPS * RADIX
+  uint32_t* s_bin_off = s_warp_hist + WARPS * RADIX;                                     // RADIX: tile-local exclusive
+  unsigned long long* s_bin_glob = reinterpret_cast<unsigned long long*>(s_bin_off + RADIX);  // RADIX
+  __shared__ uint32_t tile_s;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) tile_s = atomicAdd(ticket, 1u);
+  for (int i = tid; i < WARPS * RADIX; i += SORT_THREADS) s_warp_hist[i] = 0;
+  __syncthreads();
+  const uint32_t tile = tile_s;
+  const uint64_t tile_first = (uint64_t)tile * SORT_TILE;
+  const int cnt = (n - tile_first) < (uint64_t)SORT_TILE ? (int)(n - tile_first) : SORT_TILE;
+
+  // warp-striped load: warp w owns items [w*32*ITEMS, (w+1)*32*ITEMS), lane-strided
+  unsigned long long key[SORT_ITEMS];
+  uint32_t rank_in_warp[SORT_ITEMS];
+  const int warp_first = warp * 32 * SORT_ITEMS;
+#pragma unroll
+  for (int k = 0; k < SORT_ITEMS; k++) {
+    int idx = warp_first + k * 32 + lane;
+    key[k] = idx < cnt ? in[tile_first + idx] : ~0ull;
+  }
+  // rank each key among the keys of the same digit that precede it in this warp (match_any + popc)
+  uint32_t* my_hist = s_warp_hist + warp * RADIX;
+#pragma unroll
+  for (int k = 0; k < SORT_ITEMS; k++) {
+    int idx = warp_first + k * 32 + lane;
+    bool valid = idx < cnt;
+    uint32_t digit = valid ? (uint32_t)((key[k] >> shift) & (RADIX - 1)) : (uint32_t)RADIX;
+    uint32_t peers = __match_any_sync(0xFFFFFFFFu, digit);
+    uint32_t before = __popc(peers & ((1u << lane) - 1u));
+    uint32_t base = 0;
+    if (valid) base = my_hist[digit];
+    __syncwarp();
+    if (valid && before == 0) my_hist[digit] = base + __popc(peers);
+    __syncwarp();
+    rank_in_warp[k] = base + before;
+  }
+  __syncthreads();
+  // per digit: exclusive scan over the warps, tile total
+  for (int d = tid; d < RADIX; d += SORT_THREADS) {
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; w++) {
+      uint32_t c = s_warp_hist[w * RADIX + d];
+      s_warp_hist[w * RADIX + d] = run;
+      run += c;
+    }
+    s_bin_off[d] = run;  // tile count of digit d (turned into an exclusive offset below)
+  }
+  __syncthreads();
+  // chained scan over tiles, one descriptor per digit: threads 0..255 each own a digit
+  if (tid < RADIX) {
+    const int d = tid;
+    const unsigned long long mine = s_bin_off[d];
+    unsigned long long* my_desc = desc + (size_t)tile * RADIX + d;
+    unsigned long long excl = 0;
+    if (tile == 0) {
+      lb_store(my_desc, LB_PREFIX, mine);
+    } else {
+      lb_store(my_desc, LB_AGGREGATE, mine);
+      for (int64_t t = (int64_t)tile - 1; t >= 0; t--) {
+        unsigned long long w;
+        do {
+          w = lb_load(desc + (size_t)t * RADIX + d);
+        } while ((w >> 62) == LB_INVALID);
+        excl += w & 0x3FFFFFFFFFFFFFFFull;
+        if ((w >> 62) == LB_PREFIX) break;
+      }
+      lb_store(my_desc, LB_PREFIX, excl + mine);
+    }
+    s_bin_glob[d] = bin_base[d] + excl;
+  }
+  __syncthreads();
+  // tile-local exclusive offsets of the digits (serial over 256 in one warp via shuffles)
+  if (warp == 0) {
+    uint32_t carry = 0;
+#pragma unroll
+    for (int c = 0; c < RADIX / 32; c++) {
+      uint32_t v = s_bin_off[c * 32 + lane];
+      uint32_t inc = v;
+#pragma unroll
+      for (int dd = 1; dd < 32; dd <<= 1) {
+        uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, dd);
+        if (lane >= dd) inc += o;
+      }
+      s_bin_off[c * 32 + lane] = carry + inc - v;
+      carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+    }
+  }
+  __syncthreads();
+  // scatter into shared memory in digit order
+#pragma unroll
+  for (int k = 0; k < SORT_ITEMS; k++) {
+    int idx = warp_first + k * 32 + lane;
+    if (idx < cnt) {
+      uint32_t digit = (uint32_t)((key[k] >> shift) & (RADIX - 1));
+      uint32_t p = s_bin_off[digit] + s_warp_hist[warp * RADIX + digit] + rank_in_warp[k];
+      s_keys[p] = key[k];
+    }
+  }
+  __syncthreads();
+  // write out: consecutive threads write consecutive keys of a digit run
+  for (int p = tid; p < cnt; p += SORT_THREADS) {
+    unsigned long long k = s_keys[p];
+    uint32_t digit = (uint32_t)((k >> shift) & (RADIX - 1));
+    out[s_bin_glob[digit] + (uint32_t)(p - s_bin_off[digit])] = k;
+  }
+}
+
+}  // namespace
+
+size_t sort_temp_bytes(uint64_t n) {
+  uint64_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
+  // histograms + per-pass descriptors + tickets
+  return (size_t)MAX_PASSES * RADIX * 8 + (size_t)(tiles + 1) * RADIX * 8 + 256;
+}
+
+int sort_keys(unsigned long long* keys, unsigned long long* alt, uint64_t n, int end_bit, void* temp, size_t temp_bytes,
+              unsigned long long** out, cudaStream_t st) {
+  *out = keys;
+  if (n <= 1) return 0;
+  int n_passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
+  if (n_passes < 1) n_passes = 1;
+  if (n_passes > MAX_PASSES) n_passes = MAX_PASSES;
+  uint64_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
+  unsigned char* t = static_cast<unsigned char*>(temp);
+  unsigned long long* hist = reinterpret_cast<unsigned long long*>(t);
+  unsigned long long* desc = reinterpret_cast<unsigned long long*>(t + (size_t)MAX_PASSES * RADIX * 8);
+  uint32_t* ticket = reinterpret_cast<uint32_t*>(t + (size_t)MAX_PASSES * RADIX * 8 + (size_t)(tiles + 1) * RADIX * 8);
+  (void)temp_bytes;
+  int launches = 0;
+  cudaMemsetAsync(hist, 0, (size_t)MAX_PASSES * RADIX * 8, st);
+  int hgrid = (int)std::min<uint64_t>((n + 511) / 512, 148ull * 4);
+  radix_hist_kernel<<<hgrid, 512, 0, st>>>(keys, n, n_passes, hist);
+  radix_scan_hist_kernel<<<n_passes, RADIX, 0, st>>>(hist);
+  launches += 2;
+  const size_t smem = (size_t)SORT_TILE * 8 + (size_t)(SORT_THREADS / 32) * RADIX * 4 + RADIX * 4 + RADIX * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(radix_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  unsigned long long* src = keys;
+  unsigned long long* dst = alt;
+  for (int p = 0; p < n_passes; p++) {
+    cudaMemsetAsync(desc, 0, (size_t)tiles * RADIX * 8, st);
+    cudaMemsetAsync(ticket, 0, 4, st);
+    radix_onesweep_kernel<<<(unsigned)tiles, SORT_THREADS, smem, st>>>(src, dst, n, p * RADIX_BITS,
+                                                                      hist + (size_t)p * RADIX, desc, ticket);
+    launches++;
+    std::swap(src, dst);
+  }
+  *out = src;
+  return launches;
+}

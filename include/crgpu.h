@@ -1,0 +1,248 @@
+/* crgpu.h — C ABI of the B200-native barcode / UMI correction and counting path.
+ *
+ * This is the drop-in boundary: a Rust (cgo / JNI / ctypes ...) host binds these
+ * symbols and nothing else. Plain pointers and sizes only; the library owns all
+ * device memory behind the opaque context; every entry point returns 0 on
+ * success or a negative CRGPU_E_* code and never unwinds across the boundary
+ * (crgpu_last_error() returns the message of the calling thread's last failure).
+ * Calls on one context are serialised by the caller, as the reference's stage
+ * `main`s are (lib/rust/cr_lib/src/stages/barcode_correction.rs:265-370 is
+ * single threaded). There is no CPU fallback: without a CUDA device every
+ * compute entry point fails with CRGPU_E_CUDA.
+ *
+ * Each group below names the reference interface it replaces (paths relative
+ * to the reference checkout, lib/rust/<crate>/src/...). INTEGRATION.md shows
+ * the Rust `extern "C"` block and the stage adapters that call it.
+ *
+ * Sequence conventions: sequences cross the boundary as fixed-width ASCII
+ * (A,C,G,T,N), as the reference's SSeqGen does, or packed 2 bits per base with
+ * the first base most significant and A=0 C=1 G=2 T=3 (SSeqGen::encode_2bit_u32,
+ * used at lib/rust/tx_annotation/src/mark_dups.rs:347). A barcode is reported as
+ * its *content rank*: the index of its (translated) sequence in the sorted list
+ * of whitelist sequences, which is also the reference's Barcode sort order.
+ */
+#ifndef CRGPU_H
+#define CRGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRGPU_OK 0
+#define CRGPU_E_INVALID -1 /* bad argument / call order */
+#define CRGPU_E_CUDA -2    /* CUDA runtime failure (or no device) */
+#define CRGPU_E_NOMEM -3
+#define CRGPU_E_LIMIT -4 /* a documented capacity limit was exceeded */
+
+#define CRGPU_NO_FEATURE 0xFFFFFFFFu
+#define CRGPU_NO_RANK 0x3FFFFFFFu
+
+/* BarcodeSegmentState — lib/rust/barcode/src/lib.rs:270-283 (same numbering) */
+#define CRGPU_BC_NOT_CHECKED 0
+#define CRGPU_BC_VALID_BEFORE_CORRECTION 1
+#define CRGPU_BC_VALID_AFTER_CORRECTION 2
+#define CRGPU_BC_INVALID 3
+
+/* per-read flag bits returned by crgpu_reads_get(); DupInfo — tx_annotation/src/mark_dups.rs:61-72 */
+#define CRGPU_F_UMI_VALID 1u      /* UmiInfo::is_valid, umi/src/info.rs:20-37 */
+#define CRGPU_F_HAS_DUPINFO 2u    /* BarcodeDupMarker::process returned Some */
+#define CRGPU_F_UMI_CORRECTED 4u  /* DupInfo::is_corrected */
+#define CRGPU_F_LOW_SUPPORT 8u    /* DupInfo::is_low_support_umi */
+#define CRGPU_F_UMI_COUNT 16u     /* DupInfo::is_umi_count (the representative read) */
+
+typedef struct crgpu_ctx crgpu_ctx;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+int crgpu_version(void);
+const char* crgpu_last_error(void);
+int crgpu_ctx_create(int device, crgpu_ctx** out);
+void crgpu_ctx_destroy(crgpu_ctx* ctx);
+
+/* Posterior{max_expected_barcode_errors, bc_confidence_threshold} — barcode/src/corrector.rs:93-109;
+ * filter_umis — cr_lib/src/aligner.rs:270. Defaults: 0.975, f64::MAX, 1. */
+int crgpu_set_params(crgpu_ctx* ctx, double bc_confidence_threshold, double max_expected_barcode_errors,
+                     int filter_umis);
+
+/* ---- Whitelist — barcode/src/whitelist.rs:452-525 (Whitelist::{Plain,Trans}) ----
+ * seqs: n*L ASCII. translated: NULL for a plain whitelist, else n*L ASCII (raw -> translated).
+ * The first whitelist added defines the content space (its content sequences, sorted, define
+ * the barcode ranks); later whitelists must map into it. L <= 16. */
+int crgpu_whitelist_add(crgpu_ctx* ctx, const uint8_t* seqs, uint64_t n, int L, const uint8_t* translated,
+                        int* out_whitelist);
+int crgpu_whitelist_size(crgpu_ctx* ctx, uint64_t* out_n_content, int* out_L);
+/* content rank -> ASCII sequence (n*L bytes) */
+int crgpu_barcode_seqs(crgpu_ctx* ctx, const uint32_t* ranks, uint64_t n, uint8_t* out_ascii);
+
+/* ---- Library type: chemistry read layout + per-type behaviour ----
+ * ChemistryDef barcode/umi components — cr_types/src/chemistry/mod.rs:718-751,866-884;
+ * umi_correction = 0 for Multiplexing Capture (cr_lib/src/aligner.rs:313-318);
+ * a feature-barcode library takes its feature from a tethered fixed-offset capture in R2
+ * (cr_types/src/reference/feature_extraction.rs:358-471), a GEX library from the `feature` array. */
+typedef struct crgpu_library_def {
+  int32_t whitelist;
+  int32_t bc_offset, bc_length;   /* barcode = R1[bc_offset : +bc_length] */
+  int32_t umi_offset, umi_length; /* UMI     = R1[umi_offset : +umi_length] */
+  int32_t umi_correction;
+  int32_t is_feature_barcode;
+  int32_t feature_type;           /* id of the feature type this library's features carry */
+  int32_t fb_offset, fb_length;   /* capture = R2[fb_offset : +fb_length] */
+} crgpu_library_def;
+int crgpu_library_add(crgpu_ctx* ctx, const crgpu_library_def* def, int* out_library);
+
+/* FeatureReference (only what the path needs): feature_type[f] = 0 for genes, else the
+ * feature_type id of the owning library; fb_seqs[f*fb_stride ..] = capture sequence. */
+int crgpu_features_set(crgpu_ctx* ctx, int32_t n_features, const int32_t* feature_type, const uint8_t* fb_seqs,
+                       int32_t fb_stride);
+
+/* ---- Reads (what RnaRead carries onto the path — cr_types/src/rna_read.rs:379-467) ----
+ * Fixed-stride SoA. With on_device != 0 the pointers are device pointers (16-byte aligned),
+ * borrowed until crgpu_reads_clear(); otherwise host pointers, copied H2D on the context stream. */
+typedef struct crgpu_read_batch {
+  uint64_t n;
+  int32_t r1_len;
+  const uint8_t* r1_seq;
+  const uint8_t* r1_qual;
+  const uint32_t* feature; /* gene index or CRGPU_NO_FEATURE; NULL for feature-barcode libraries */
+  int32_t r2_len;
+  const uint8_t* r2_seq;
+  const uint8_t* r2_qual;
+  int32_t on_device;
+} crgpu_read_batch;
+int crgpu_reads_add(crgpu_ctx* ctx, int library, const crgpu_read_batch* batch, int* out_batch);
+int crgpu_reads_clear(crgpu_ctx* ctx);
+
+/* ---- Stage MAKE_SHARD hot loop: exact whitelist check + priors ----
+ * RnaProcessor::process_read → Whitelist::check_and_update (cr_types/src/rna_read.rs:285-368),
+ * MakeShardHistograms::observe (cr_lib/src/make_shard_metrics.rs:171-188),
+ * exact feature-barcode counts (make_shard_metrics.rs:337-345). Resets and fills the priors. */
+int crgpu_pass1(crgpu_ctx* ctx);
+
+/* Cross-chunk / cross-GPU state: priors are global per library type
+ * (cr_lib/src/stages/make_shard.rs:303-358). Device pointers so the host can all-reduce them. */
+int crgpu_prior_dev(crgpu_ctx* ctx, int library, uint32_t** out_dev_u32, uint64_t* out_n);
+int crgpu_prior_set(crgpu_ctx* ctx, int library, const uint32_t* host_counts, uint64_t n);
+int crgpu_fb_counts_dev(crgpu_ctx* ctx, unsigned long long** out_dev_u64, int32_t* out_n);
+
+/* ---- Stage BARCODE_CORRECTION: Posterior::correct_barcode over the invalid reads ----
+ * barcode/src/corrector.rs:111-165 driven as cr_lib/src/stages/barcode_correction.rs:76-99,327-345;
+ * feature-barcode correction with feat_dist (feature_extraction.rs:34-117, feature_checker.rs:8-50). */
+int crgpu_pass2(crgpu_ctx* ctx);
+
+/* Corrector plugin seam, batch form of trait CorrectBarcode (barcode/src/corrector.rs:73-81):
+ * n segments of the library's bc_length (ASCII) with qualities (or NULL = no qualities) against the
+ * library's whitelist and its CURRENT priors. out_rank[i] = content rank or CRGPU_NO_RANK;
+ * out_state[i] = ValidBeforeCorrection (exact hit), ValidAfterCorrection or Invalid. */
+int crgpu_correct_barcodes(crgpu_ctx* ctx, int library, const uint8_t* bc_ascii, const uint8_t* qual,
+                           uint64_t n, uint32_t* out_rank, uint8_t* out_state);
+
+/* ---- Barcode-owner sharding (replaces ShardReader::make_chunks ranges,
+ * cr_lib/src/stages/align_and_count.rs:519-524) ----
+ * After pass2 each context holds the packed keys of its local reads. */
+int crgpu_key_layout(crgpu_ctx* ctx, int32_t* rank_shift, int32_t* feature_shift, int32_t* lib_shift,
+                     int32_t* umi_bits);
+int crgpu_keys_dev(crgpu_ctx* ctx, unsigned long long** out_dev, uint64_t* out_n);
+/* reorder the local keys into n_parts contiguous groups by rank range [bounds[p], bounds[p+1]);
+ * out_counts[p] = keys in group p */
+int crgpu_keys_partition(crgpu_ctx* ctx, int32_t n_parts, const uint32_t* bounds, uint64_t* out_counts);
+/* replace the key set by n keys at a device pointer (copied) */
+int crgpu_keys_set(crgpu_ctx* ctx, const unsigned long long* dev_keys, uint64_t n);
+/* per-library valid-barcode counts (raw valid + corrected) as a device vector to all-reduce:
+ * corrected_barcode_counts of BARCODE_CORRECTION join (barcode_correction.rs:401-407) */
+int crgpu_valid_counts_dev(crgpu_ctx* ctx, int library, uint32_t** out_dev_u32, uint64_t* out_n);
+/* restrict the matrix columns this context owns to content ranks [lo, hi) */
+int crgpu_set_owned_range(crgpu_ctx* ctx, uint32_t lo, uint32_t hi);
+
+/* ---- Stage ALIGN_AND_COUNT (dedup part) + matrix ----
+ * DupBuilder::observe, correct_umis, determine_low_support_umigenes, BarcodeDupMarker::{new,process}
+ * (tx_annotation/src/mark_dups.rs:19-59,87-108,116-170,201-363), BcUmiInfo::feature_counts
+ * (cr_types/src/types.rs:180-188), BarcodeIndex (cr_types/src/barcode_index.rs:39-53),
+ * CSC assembly (cr_h5/src/count_matrix.rs:382-448). */
+int crgpu_count(crgpu_ctx* ctx);
+/* per-read DupInfo (corrected UMI, flags); optional, needs crgpu_count() first */
+int crgpu_annotate_reads(crgpu_ctx* ctx);
+
+/* pass1 + pass2 + count on one device */
+int crgpu_run(crgpu_ctx* ctx);
+int crgpu_sync(crgpu_ctx* ctx);
+
+/* ---- Results ---- */
+enum {
+  CRGPU_STAT_READS = 0,
+  CRGPU_STAT_VALID_BEFORE = 1,
+  CRGPU_STAT_CORRECTED = 2,
+  CRGPU_STAT_INVALID = 3,
+  CRGPU_STAT_KEYS = 4,          /* reads entering dedup (valid barcode, valid UMI, feature) */
+  CRGPU_STAT_DISTINCT_KEYS = 5, /* distinct (barcode, feature, library, raw UMI) */
+  CRGPU_STAT_UMI_CORRECTED_KEYS = 6,
+  CRGPU_STAT_LOW_SUPPORT_KEYS = 7,
+  CRGPU_STAT_MOLECULES = 8, /* UmiCount rows = total UMIs in the matrix */
+  CRGPU_STAT_NNZ = 9,
+  CRGPU_STAT_BARCODES = 10,
+  CRGPU_STAT_KERNEL_LAUNCHES = 11, /* kernels of this library launched so far */
+  CRGPU_STAT_UMI_CORRECTED_READS = 12,
+  CRGPU_STAT_LOW_SUPPORT_READS = 13,
+  CRGPU_STAT_COUNT = 16
+};
+int crgpu_stats(crgpu_ctx* ctx, uint64_t out[CRGPU_STAT_COUNT]);
+
+/* per-read results of one batch; any pointer may be NULL. bc_rank = content rank or CRGPU_NO_RANK;
+ * umi = processed UMI, 2-bit packed (raw UMI when there is no DupInfo; undefined bits when the UMI
+ * holds an N); feature = resolved feature index. */
+int crgpu_reads_get(crgpu_ctx* ctx, int batch, uint32_t* bc_rank, uint8_t* bc_state, uint32_t* umi,
+                    uint8_t* flags, uint32_t* feature);
+
+/* which: 0 = prior (reads valid before correction), 1 = corrected reads; n = content size */
+int crgpu_bc_counts_get(crgpu_ctx* ctx, int library, int which, uint32_t* out, uint64_t n);
+int crgpu_fb_counts_get(crgpu_ctx* ctx, int64_t* out, int32_t n);
+
+/* feature x barcode matrix in CSC (cr_h5/src/count_matrix.rs:24-55): barcode_rank[n_barcodes] sorted,
+ * indptr[n_barcodes+1], indices[nnz] (feature index), data[nnz] */
+int crgpu_matrix_dims(crgpu_ctx* ctx, uint64_t* n_barcodes, uint64_t* nnz, uint64_t* n_features);
+int crgpu_matrix_get(crgpu_ctx* ctx, uint32_t* barcode_rank, int64_t* indptr, uint32_t* indices, int32_t* data);
+
+/* UmiCount rows (cr_types/src/types.rs:148-160), sorted by (barcode, library, feature, umi):
+ * out5[5*i..] = {barcode column index, library, feature, umi 2-bit, read_count} */
+int crgpu_molecules_count(crgpu_ctx* ctx, uint64_t* n);
+int crgpu_molecules_get(crgpu_ctx* ctx, uint32_t* out5);
+
+/* ---- Synthetic workload generator (bench / tests; see cellranger_b200/synth.py) ---- */
+typedef struct crgpu_synth_params {
+  uint64_t seed_mix, seed_mol;
+  uint32_t n_whitelist, n_cells, n_genes, n_fb;
+  int32_t bc_len, umi_len, fb_offset, fb_len, is_fb;
+  uint32_t ambient_thr, unmapped_thr, bc_err_thr, umi_err_thr, n_thr, fb_err_thr, homopolymer_thr;
+  int32_t n_qual_ascii;
+  int32_t n_qual_classes, n_equal_classes;
+  uint32_t qual_thr[8], equal_thr[8];
+  uint8_t qual_val[8], equal_val[8];
+  /* host tables, copied to the device by the call */
+  const uint32_t* wl_packed;   /* [n_whitelist] true barcode sequence per content rank (raw for FB) */
+  const uint32_t* cell_rank;   /* [n_cells] */
+  const uint32_t* cell_cdf;    /* [n_cells] */
+  const uint32_t* n_mol;       /* [n_cells] */
+  const uint32_t* gene_cdf;    /* [n_genes] */
+  const uint32_t* fb_cdf;      /* [n_fb] */
+  const uint32_t* fb_packed;   /* [n_fb] */
+} crgpu_synth_params;
+/* fills device buffers (allocated by the caller through crgpu_dev_alloc) with reads [start, start+n) */
+int crgpu_synth_generate(crgpu_ctx* ctx, const crgpu_synth_params* p, uint64_t start, uint64_t n, uint8_t* dev_r1_seq,
+                         uint8_t* dev_r1_qual, uint32_t* dev_feature, uint8_t* dev_r2_seq, uint8_t* dev_r2_qual);
+int crgpu_dev_alloc(crgpu_ctx* ctx, uint64_t bytes, void** out_dev);
+int crgpu_dev_free(crgpu_ctx* ctx, void* dev);
+int crgpu_memcpy_d2h(crgpu_ctx* ctx, void* host, const void* dev, uint64_t bytes);
+int crgpu_memcpy_h2d(crgpu_ctx* ctx, void* dev, const void* host, uint64_t bytes);
+int crgpu_host_alloc_pinned(uint64_t bytes, void** out_host);
+int crgpu_host_free_pinned(void* host);
+
+/* timing of the last crgpu_pass1 / pass2 / count calls, measured with CUDA events on the context
+ * stream: out_ms[0..n) per named phase; names are returned as a NUL-separated list */
+int crgpu_phase_times(crgpu_ctx* ctx, float* out_ms, int32_t cap, int32_t* out_n, const char** out_names);
+/* the CUDA stream all work of this context is enqueued on (cudaStream_t as void*) */
+int crgpu_stream(crgpu_ctx* ctx, void** out_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRGPU_H */

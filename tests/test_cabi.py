@@ -1,0 +1,63 @@
+"""The C-ABI library loads and exports every symbol include/crgpu.h declares (no compute calls:
+this runs without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from cellranger_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "crgpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(crgpu_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_entry_points():
+    syms = _declared_symbols()
+    for must in ("crgpu_ctx_create", "crgpu_whitelist_add", "crgpu_pass1", "crgpu_pass2", "crgpu_count",
+                 "crgpu_correct_barcodes", "crgpu_matrix_get", "crgpu_keys_partition"):
+        assert must in syms
+
+
+def test_library_builds_and_exports_every_symbol():
+    so = build.build_library()
+    assert os.path.exists(so)
+    L = C.CDLL(so)
+    missing = [s for s in _declared_symbols() if not hasattr(L, s)]
+    assert not missing, f"symbols declared in crgpu.h but not exported: {missing}"
+
+
+def test_struct_sizes_match_header():
+    # crgpu_library_def: 10 x int32; crgpu_read_batch: see header
+    assert C.sizeof(_lib.LibraryDef) == 40
+    assert C.sizeof(_lib.ReadBatch) == 8 + 8 + 8 * 3 + 8 + 8 * 2 + 8
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    L = _lib.load()
+    ctx = C.c_void_p()
+    rc = L.crgpu_ctx_create(0, C.byref(ctx))
+    assert rc == -2  # CRGPU_E_CUDA
+    assert b"no CPU fallback" in L.crgpu_last_error()
+    from cellranger_b200 import GemWell, CrgpuError
+
+    with pytest.raises(CrgpuError):
+        GemWell()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "cellranger_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in txt.lower().replace("# oracle", ""), f"{f} mentions the oracle"

@@ -1,0 +1,289 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle. Needs a B200: -m gpu."""
+import numpy as np
+import pytest
+
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+F64_MAX = 1.7976931348623157e308
+
+
+# ---- the reference's known-answer tests, through the C ABI on the GPU ----
+
+def test_kat_barcode_correction_gpu(kats):
+    import cellranger_b200 as cb
+
+    for name in ("barcode_correction", "barcode_correction_no_counts"):
+        k = kats[name]
+        corr = cb.BarcodeCorrector(cb.Whitelist.plain(k["whitelist"]), k["counts"],
+                                   cb.Posterior(k["max_expected_errors"], k["threshold"]))
+        seqs = [c["seq"] for c in k["cases"]]
+        quals = [bytes(c["qual"]) for c in k["cases"]]
+        out, state = corr.correct_barcodes(seqs, quals)
+        for i, c in enumerate(k["cases"]):
+            if c["expect"] is None:
+                # "AAAAA" is itself on the whitelist: the batch seam reports the exact hit
+                if c["seq"] in k["whitelist"]:
+                    assert state[i] == cb.api.VALID_BEFORE_CORRECTION
+                else:
+                    assert state[i] == cb.api.INVALID, (name, c["name"])
+            else:
+                assert state[i] == cb.api.VALID_AFTER_CORRECTION, (name, c["name"])
+                assert bytes(out[i]).decode() == c["expect"], (name, c["name"])
+        corr.close()
+
+
+def test_kat_n_rescue_gpu(kats):
+    import cellranger_b200 as cb
+
+    k = kats["barcode_n_rescue"]
+    bc = k["whitelist"][0]
+    corr = cb.BarcodeCorrector(cb.Whitelist.plain(k["whitelist"]), {}, cb.Posterior(1.0, k["threshold"]))
+    seqs, quals = [], []
+    for p in range(16):
+        seqs.append(bc[:p] + "N" + bc[p + 1:])
+        q = [k["qual_else"]] * 16
+        q[p] = k["qual_at_n"]
+        quals.append(bytes(q))
+    seqs.append("NN" + bc[2:])
+    quals.append(bytes([53] * 16))
+    out, state = corr.correct_barcodes(seqs, quals)
+    for p in range(16):
+        assert state[p] == cb.api.VALID_AFTER_CORRECTION and bytes(out[p]).decode() == bc
+    assert state[16] == cb.api.INVALID
+    corr.close()
+
+
+def test_corrector_batch_matches_oracle_random():
+    """Random invalid segments with random priors and qualities: every accept/reject decision and every
+    corrected sequence must equal the oracle's (f64 posterior in the reference's operation order)."""
+    import cellranger_b200 as cb
+    from oracle import cro
+
+    rng = np.random.default_rng(7)
+    for L, W in ((16, 5000), (8, 3000), (5, 200)):
+        wl = np.unique(rng.integers(0, 4, size=(W, L)), axis=0)
+        wl_ascii = np.frombuffer(b"ACGT", dtype=np.uint8)[wl]
+        counts = {bytes(s): int(c) for s, c in zip(wl_ascii, rng.integers(0, 500, size=len(wl_ascii))) if c % 3}
+        corr = cb.BarcodeCorrector(cb.Whitelist.plain(wl_ascii), counts)
+        n = 3000
+        src = wl_ascii[rng.integers(0, len(wl_ascii), size=n)].copy()
+        for i in range(n):  # 1-2 substitutions, sometimes an N
+            for _ in range(rng.integers(1, 3)):
+                src[i, rng.integers(0, L)] = b"ACGT"[rng.integers(0, 4)]
+            if rng.random() < 0.1:
+                src[i, rng.integers(0, L)] = ord("N")
+        quals = rng.integers(33 + 2, 33 + 41, size=(n, L)).astype(np.uint8)
+        out, state = corr.correct_barcodes(src, quals)
+        wl_set = {bytes(s) for s in wl_ascii}
+        for i in range(n):
+            s = bytes(src[i])
+            if s in wl_set:
+                assert state[i] == 1
+                continue
+            exp = cro.kat_correct_barcode(wl_ascii, counts, s, bytes(quals[i]), F64_MAX, 0.975)
+            if exp is None:
+                assert state[i] == 3, (L, i, s)
+            else:
+                assert state[i] == 2 and bytes(out[i]) == exp, (L, i, s, exp, bytes(out[i]))
+        corr.close()
+
+
+def test_synth_device_matches_numpy():
+    import cellranger_b200 as cb
+    from cellranger_b200 import synth, synth_device
+
+    n = 50_000
+    for name in ("cfg1", "cfg5", "cfg4"):
+        cfg = synth.preset(name, n)
+        cfg.n_whitelist = 20_000
+        cfg.n_cells = 50
+        t = synth.make_tables(cfg, n)
+        gw = cb.GemWell()
+        for libname in (("gex", "fb") if cfg.n_fb_features else ("gex",)):
+            d = synth_device.generate_device(gw, t, 1000, n, libname)
+            h = d.to_host()
+            ref = synth.generate_reads(t, 1000, n, libname)
+            for key in h:
+                assert np.array_equal(h[key], ref[key]), (name, libname, key)
+            d.close()
+        gw.close()
+
+
+# ---- whole-path parity on the BASELINE.json configs, at sizes the oracle finishes in seconds ----
+
+@pytest.mark.parametrize("name,n,kw", [
+    ("cfg1", 200_000, {}),                                        # 3' v2, 737K whitelist
+    ("cfg2", 300_000, {"n_whitelist": 200_000, "n_cells": 400}),   # 3' v3 (12 bp UMI)
+    ("cfg5", 200_000, {"n_whitelist": 100_000, "n_cells": 20}),    # high error, saturated UMIs
+    ("cfg1", 1000, {"n_whitelist": 5000, "n_cells": 10}),          # ragged: below one tile
+    ("cfg1", 513, {"n_whitelist": 5000, "n_cells": 3}),            # one tile + 1
+])
+def test_full_path_matches_oracle(name, n, kw):
+    prob = helpers.make_problem(name, n, **kw)
+    o = helpers.run_oracle(prob)
+    gw = helpers.run_gpu(prob)
+    info = helpers.compare_all(o, gw, prob)
+    assert info["nnz"] > 0
+    gw.close()
+
+
+def test_feature_barcode_library_matches_oracle():
+    prob = helpers.make_problem("cfg4", 200_000, n_whitelist=100_000, n_cells=200)
+    assert prob["n_fb"] > 0
+    o = helpers.run_oracle(prob)
+    gw = helpers.run_gpu(prob)
+    info = helpers.compare_all(o, gw, prob)
+    assert info["nnz"] > 0
+    gw.close()
+
+
+def test_full_whitelist_sizes():
+    """The real whitelist sizes (737 280 and 6 794 880 entries) with their 2- and 3-ordering tables."""
+    for name, n in (("cfg1", 100_000), ("cfg2", 100_000)):
+        prob = helpers.make_problem(name, n, n_cells=100)
+        o = helpers.run_oracle(prob)
+        gw = helpers.run_gpu(prob)
+        helpers.compare_all(o, gw, prob)
+        gw.close()
+
+
+def test_edge_cases():
+    import cellranger_b200 as cb
+
+    prob = helpers.make_problem("cfg1", 4000, n_whitelist=3000, n_cells=5)
+    g = prob["gex"]
+    # all reads unmapped: barcodes still enter the barcode index, matrix has empty columns only
+    g["feature"][:] = 0xFFFFFFFF
+    o = helpers.run_oracle(prob)
+    gw = helpers.run_gpu(prob)
+    info = helpers.compare_all(o, gw, prob)
+    assert info["nnz"] == 0 and info["n_barcodes"] > 0
+    gw.close()
+    # every barcode invalid and uncorrectable (poly-N)
+    prob = helpers.make_problem("cfg1", 2000, n_whitelist=3000, n_cells=5)
+    prob["gex"]["r1_seq"][:, :16] = ord("N")
+    o = helpers.run_oracle(prob)
+    gw = helpers.run_gpu(prob)
+    info = helpers.compare_all(o, gw, prob)
+    assert info["n_barcodes"] == 0
+    gw.close()
+    # empty batch
+    prob = helpers.make_problem("cfg1", 1000, n_whitelist=3000, n_cells=5)
+    for k in ("r1_seq", "r1_qual", "feature", "true_rank"):
+        prob["gex"][k] = prob["gex"][k][:0]
+    gw = helpers.run_gpu(prob)
+    assert gw.stats()["reads"] == 0 and gw.count_matrix().data.shape[0] == 0
+    gw.close()
+
+
+def test_umi_chain_and_low_support_hand_case():
+    """A hand-built barcode: chain A->B->C (single hop), tie broken towards the larger UMI, a UMI seen
+    with two genes (low support), homopolymer and low-quality UMIs dropped."""
+    import cellranger_b200 as cb
+    from oracle import cro
+
+    wl = ["AAAACCCCGGGGTTTT", "ACGTACGTACGTACGT"]
+    rows = []  # (barcode, umi, gene, copies, qual char)
+
+    def add(bc, umi, gene, copies, q="I"):
+        for _ in range(copies):
+            rows.append((bc, umi, gene, q))
+
+    b = wl[0]
+    add(b, "AAAAAAAAAC", 5, 1)   # A -> B (count 2) ...
+    add(b, "AAAAAAAACC", 5, 2)   # B -> C (count 3): single hop, B keeps A's read
+    add(b, "AAAAAAACCC", 5, 3)   # C
+    add(b, "CCCCCCCCCA", 7, 1)   # tie 1:1 -> lexicographically larger CCCCCCCCCG
+    add(b, "CCCCCCCCCG", 7, 1)
+    add(b, "GATTACAGAT", 3, 4)   # same UMI on two genes: gene 9 is sub-maximal -> low support
+    add(b, "GATTACAGAT", 9, 1)
+    add(b, "TTTTGGGGCC", 3, 2)   # tie across genes -> both low support
+    add(b, "TTTTGGGGCC", 4, 2)
+    add(b, "GGGGGGGGGG", 3, 5)   # homopolymer: invalid UMI
+    add(b, "ACGTTGCAAC", 3, 2, q="*")  # Q9 < 10: invalid UMI
+    add(wl[1], "ACGTTGCAAC", 3, 2)
+    n = len(rows)
+    r1 = np.zeros((n, 26), dtype=np.uint8)
+    q1 = np.zeros((n, 26), dtype=np.uint8)
+    feat = np.zeros(n, dtype=np.uint32)
+    for i, (bc, umi, gene, q) in enumerate(rows):
+        r1[i] = np.frombuffer((bc + umi).encode(), dtype=np.uint8)
+        q1[i] = ord("I")
+        q1[i, 16:] = ord(q)
+        feat[i] = gene
+    o = cro.Oracle()
+    w = o.add_whitelist(wl)
+    lib = o.add_library(w, 0, 16, 16, 10)
+    o.set_features(np.zeros(16, dtype=np.int32))
+    o.add_reads(lib, r1, q1, feat)
+    o.run()
+    gw = cb.GemWell()
+    w2 = gw.add_whitelist(cb.Whitelist.plain(wl))
+    lib2 = gw.add_library(w2, cb.ChemistryDef.SC3Pv2())
+    gw.set_feature_reference(cb.FeatureReference(16))
+    gw.add_reads(lib2, r1, q1, feat)
+    gw.run(annotate_reads=True)
+    mo, mg = o.matrix(), gw.count_matrix()
+    assert np.array_equal(mo["indptr"], mg.indptr) and np.array_equal(mo["indices"], mg.indices)
+    assert np.array_equal(mo["data"], mg.data)
+    # spelled out: barcode 0 → gene 3: GATTACAGAT (1), gene 5: B and C (2), gene 7: CCCCCCCCCG (1)
+    assert mg.indices.tolist() == [3, 5, 7, 3] and mg.data.tolist() == [1, 2, 1, 1]
+    ro, rg = o.reads(), gw.reads(0)
+    assert np.array_equal(ro["flags"], rg["flags"])
+    has = (ro["flags"] & 2) != 0
+    assert np.array_equal(ro["umi"][has], cb.unpack_2bit(rg["umi"], 10)[has])
+    gw.close()
+
+
+def test_multiplexing_capture_disables_umi_correction():
+    import cellranger_b200 as cb
+    from oracle import cro
+
+    prob = helpers.make_problem("cfg1", 50_000, n_whitelist=5000, n_cells=20)
+    g = prob["gex"]
+    t = prob["tables"]
+    o = cro.Oracle()
+    w = o.add_whitelist(t.whitelist)
+    lib = o.add_library(w, 0, 16, 16, 10, umi_correction=False)
+    o.set_features(np.zeros(prob["cfg"].n_genes, dtype=np.int32))
+    o.add_reads(lib, g["r1_seq"], g["r1_qual"], g["feature"])
+    o.run(4)
+    gw = cb.GemWell()
+    w2 = gw.add_whitelist(cb.Whitelist.plain(t.whitelist))
+    lib2 = gw.add_library(w2, cb.ChemistryDef.SC3Pv2(), umi_correction=False)
+    gw.set_feature_reference(cb.FeatureReference(prob["cfg"].n_genes))
+    gw.add_reads(lib2, g["r1_seq"], g["r1_qual"], g["feature"])
+    gw.run(annotate_reads=True)
+    assert gw.stats()["umi_corrected_keys"] == 0
+    mo, mg = o.matrix(), gw.count_matrix()
+    assert np.array_equal(mo["data"], mg.data) and np.array_equal(mo["indices"], mg.indices)
+    gw.close()
+
+
+def test_size_independent_properties_large():
+    """2 M reads (the oracle is not run): sortedness, conservation and idempotence."""
+    import cellranger_b200 as cb
+
+    prob = helpers.make_problem("cfg1", 2_000_000)
+    gw = helpers.run_gpu(prob, annotate=True)
+    st = gw.stats()
+    m = gw.count_matrix()
+    assert st["valid_before"] + st["corrected"] + st["invalid"] == st["reads"] == 2_000_000
+    assert np.all(np.diff(m.barcode_rank.astype(np.int64)) > 0)  # barcode index strictly sorted
+    assert m.indptr[0] == 0 and m.indptr[-1] == len(m.data) and np.all(np.diff(m.indptr) >= 0)
+    for c in np.random.default_rng(0).integers(0, len(m.indptr) - 1, size=2000):  # features sorted per column
+        seg = m.indices[m.indptr[c]:m.indptr[c + 1]]
+        assert np.all(np.diff(seg.astype(np.int64)) > 0)
+    assert int(m.data.sum()) == st["molecules"] and np.all(m.data > 0)
+    mol = gw.molecules()
+    assert int(mol[:, 4].sum()) + st["low_support_reads"] == st["keys"]  # every deduped read is accounted for
+    r = gw.reads(0)
+    assert int(((r["flags"] & 16) != 0).sum()) == st["molecules"]  # one representative read per UMI
+    # idempotence: running the stages again gives the same matrix
+    gw.run(annotate_reads=False)
+    m2 = gw.count_matrix()
+    assert np.array_equal(m.indptr, m2.indptr) and np.array_equal(m.indices, m2.indices)
+    assert np.array_equal(m.data, m2.data)
+    gw.close()
