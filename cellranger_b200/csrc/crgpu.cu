@@ -1026,11 +1026,18 @@ int crgpu_count(crgpu_ctx* c) {
   phases_clear(c, "count");
   const uint64_t nk = c->n_keys;
   const uint64_t cap = std::max<uint64_t>(nk, 1);
-  if ((rc = phase_begin(c, "count.sort"))) return rc;
   if ((rc = c->sort_temp.ensure(sort_temp_bytes(cap)))) return rc;
+  if ((rc = phase_begin(c, "count.sort.hist"))) return rc;
+  c->launches += sort_histograms(c->keys.as<unsigned long long>(), nk, c->kl.total_bits, c->sort_temp.p, c->stream);
+  CHECK_KERNEL();
+  if ((rc = phase_end(c))) return rc;
+  {
+    std::string nm = "count.sort.onesweep_x" + std::to_string(sort_num_passes(c->kl.total_bits));
+    if ((rc = phase_begin(c, nm.c_str()))) return rc;
+  }
   unsigned long long* sorted = c->keys.as<unsigned long long>();
-  c->launches += sort_keys(c->keys.as<unsigned long long>(), c->keys_alt.as<unsigned long long>(), nk, c->kl.total_bits,
-                           c->sort_temp.p, c->sort_temp.cap, &sorted, c->stream);
+  c->launches += sort_passes(c->keys.as<unsigned long long>(), c->keys_alt.as<unsigned long long>(), nk,
+                             c->kl.total_bits, c->sort_temp.p, &sorted, c->stream);
   CHECK_KERNEL();
   if ((rc = phase_end(c))) return rc;
   if ((rc = phase_begin(c, "count.dedup"))) return rc;

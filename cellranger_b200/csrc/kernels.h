@@ -85,6 +85,10 @@ int launch_valid_counts(const uint32_t* prior, const uint32_t* corrected, uint32
 int sort_keys(unsigned long long* keys, unsigned long long* alt, uint64_t n, int end_bit, void* temp,
               size_t temp_bytes, unsigned long long** out, cudaStream_t st);
 size_t sort_temp_bytes(uint64_t n);
+int sort_num_passes(int end_bit);
+int sort_histograms(const unsigned long long* keys, uint64_t n, int end_bit, void* temp, cudaStream_t st);
+int sort_passes(unsigned long long* keys, unsigned long long* alt, uint64_t n, int end_bit, void* temp,
+                unsigned long long** out, cudaStream_t st);
 
 // ---- dedup / count (dedup_kernels.cu) ----
 struct DedupBuffers {

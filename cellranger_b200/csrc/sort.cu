@@ -182,31 +182,45 @@ size_t sort_temp_bytes(uint64_t n) {
   return (size_t)MAX_PASSES * RADIX * 8 + (size_t)(tiles + 1) * RADIX * 8 + 256;
 }
 
-int sort_keys(unsigned long long* keys, unsigned long long* alt, uint64_t n, int end_bit, void* temp, size_t temp_bytes,
-              unsigned long long** out, cudaStream_t st) {
-  *out = keys;
-  if (n <= 1) return 0;
+static int plan_passes(int end_bit) {
   int n_passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
   if (n_passes < 1) n_passes = 1;
   if (n_passes > MAX_PASSES) n_passes = MAX_PASSES;
+  return n_passes;
+}
+
+int sort_num_passes(int end_bit) { return plan_passes(end_bit); }
+
+// step 1: digit histograms of every pass + their exclusive scans
+int sort_histograms(const unsigned long long* keys, uint64_t n, int end_bit, void* temp, cudaStream_t st) {
+  if (n <= 1) return 0;
+  const int n_passes = plan_passes(end_bit);
+  unsigned long long* hist = reinterpret_cast<unsigned long long*>(temp);
+  cudaMemsetAsync(hist, 0, (size_t)MAX_PASSES * RADIX * 8, st);
+  int hgrid = (int)std::min<uint64_t>((n + 511) / 512, 148ull * 4);
+  radix_hist_kernel<<<hgrid, 512, 0, st>>>(keys, n, n_passes, hist);
+  radix_scan_hist_kernel<<<n_passes, RADIX, 0, st>>>(hist);
+  return 2;
+}
+
+// step 2: the onesweep passes; result in *out
+int sort_passes(unsigned long long* keys, unsigned long long* alt, uint64_t n, int end_bit, void* temp,
+                unsigned long long** out, cudaStream_t st) {
+  *out = keys;
+  if (n <= 1) return 0;
+  const int n_passes = plan_passes(end_bit);
   uint64_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
   unsigned char* t = static_cast<unsigned char*>(temp);
   unsigned long long* hist = reinterpret_cast<unsigned long long*>(t);
   unsigned long long* desc = reinterpret_cast<unsigned long long*>(t + (size_t)MAX_PASSES * RADIX * 8);
   uint32_t* ticket = reinterpret_cast<uint32_t*>(t + (size_t)MAX_PASSES * RADIX * 8 + (size_t)(tiles + 1) * RADIX * 8);
-  (void)temp_bytes;
-  int launches = 0;
-  cudaMemsetAsync(hist, 0, (size_t)MAX_PASSES * RADIX * 8, st);
-  int hgrid = (int)std::min<uint64_t>((n + 511) / 512, 148ull * 4);
-  radix_hist_kernel<<<hgrid, 512, 0, st>>>(keys, n, n_passes, hist);
-  radix_scan_hist_kernel<<<n_passes, RADIX, 0, st>>>(hist);
-  launches += 2;
   const size_t smem = (size_t)SORT_TILE * 8 + (size_t)(SORT_THREADS / 32) * RADIX * 4 + RADIX * 4 + RADIX * 8;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(radix_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
+  int launches = 0;
   unsigned long long* src = keys;
   unsigned long long* dst = alt;
   for (int p = 0; p < n_passes; p++) {
@@ -218,5 +232,13 @@ int sort_keys(unsigned long long* keys, unsigned long long* alt, uint64_t n, int
     std::swap(src, dst);
   }
   *out = src;
+  return launches;
+}
+
+int sort_keys(unsigned long long* keys, unsigned long long* alt, uint64_t n, int end_bit, void* temp, size_t temp_bytes,
+              unsigned long long** out, cudaStream_t st) {
+  (void)temp_bytes;
+  int launches = sort_histograms(keys, n, end_bit, temp, st);
+  launches += sort_passes(keys, alt, n, end_bit, temp, out, st);
   return launches;
 }

@@ -1,0 +1,149 @@
+"""Barcode-owner sharding of the path across the GPUs of one box (one process per GPU).
+
+The reference partitions the same way, by barcode range, but through files
+(ShardReader::make_chunks, lib/rust/cr_lib/src/stages/barcode_correction.rs:252-262 and
+stages/align_and_count.rs:519-524); priors are summed over every chunk in the MAKE_SHARD join
+(stages/make_shard.rs:303-358). Here:
+
+  1. every rank runs pass 1 on its own reads                      (local)
+  2. all-reduce(sum) of the per-library prior histograms          (priors are global)
+     + the exact feature-barcode counts
+  3. every rank corrects its own invalid reads                    (local)
+  4. all-reduce(sum) of the valid-barcode counts → barcode index, and → owner ranges of
+     contiguous content ranks balanced by read count
+  5. one all-to-all of the packed 64-bit keys to the rank that owns their barcode
+  6. dedup + counting, shard-local; the matrix is the concatenation of the ranks' column blocks
+
+`ShardedGemWell` only talks to an *engine* (the GPU GemWell through TorchEngine below); the host
+logic — owner ranges, split sizes, the exchange — is what the world_size-2 gloo tests cover.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class _DevArray:
+    """A raw device pointer as a __cuda_array_interface__ object (zero copy)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def dev_tensor(ptr: int, n: int, dtype: str, device) -> torch.Tensor:
+    if n == 0 or not ptr:
+        return torch.empty(0, dtype={"<i4": torch.int32, "<i8": torch.int64}[dtype], device=device)
+    return torch.as_tensor(_DevArray(ptr, n, dtype), device=device)
+
+
+class TorchEngine:
+    """GemWell (GPU) behind the engine interface; tensors alias the library's device buffers."""
+
+    def __init__(self, gw, n_libs: int):
+        self.gw = gw
+        self.n_libs = n_libs
+        self.device = torch.device("cuda", gw.device)
+        self._recv = None
+
+    def make_shard(self):
+        self.gw.make_shard()
+        self.gw.sync()
+
+    def prior_tensors(self) -> List[torch.Tensor]:
+        return [dev_tensor(*self.gw.prior_dev(l), "<i4", self.device) for l in range(self.n_libs)]
+
+    def fb_counts_tensor(self):
+        p, n = self.gw.fb_counts_dev()
+        return dev_tensor(p, n, "<i8", self.device) if n else None
+
+    def barcode_correction(self):
+        self.gw.barcode_correction()
+        self.gw.sync()
+
+    def valid_count_tensors(self) -> List[torch.Tensor]:
+        return [dev_tensor(*self.gw.valid_counts_dev(l), "<i4", self.device) for l in range(self.n_libs)]
+
+    def keys_partition(self, bounds: np.ndarray):
+        counts = self.gw.keys_partition(bounds)
+        p, n = self.gw.keys_dev()
+        return dev_tensor(p, n, "<i8", self.device), counts.astype(np.int64)
+
+    def new_keys(self, n: int) -> torch.Tensor:
+        self._recv = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)[:n]
+        return self._recv
+
+    def keys_set(self, t: torch.Tensor):
+        torch.cuda.synchronize(self.device)
+        self.gw.keys_set(t.data_ptr() if t.numel() else 0, int(t.numel()))
+
+    def set_owned_range(self, lo: int, hi: int):
+        self.gw.set_owned_range(lo, hi)
+
+    def align_and_count(self):
+        self.gw.align_and_count()
+
+    def sync(self):
+        torch.cuda.synchronize(self.device)
+
+
+def owner_bounds(valid_total: torch.Tensor, world: int) -> np.ndarray:
+    """Contiguous content-rank ranges [bounds[r], bounds[r+1]) holding ~equal numbers of valid reads:
+    the GPU analogue of ShardReader::make_chunks' equal-read barcode ranges."""
+    n = int(valid_total.numel())
+    if n == 0:
+        return np.zeros(world + 1, dtype=np.uint32)
+    csum = torch.cumsum(valid_total.to(torch.int64), 0)
+    total = int(csum[-1].item())
+    targets = torch.tensor([(total * r) // world for r in range(1, world)], dtype=torch.int64, device=csum.device)
+    cuts = torch.searchsorted(csum, targets, right=False) + 1 if world > 1 else torch.empty(0, dtype=torch.int64)
+    b = np.zeros(world + 1, dtype=np.int64)
+    b[world] = n
+    if world > 1:
+        b[1:world] = np.minimum(cuts.cpu().numpy(), n)
+    b = np.maximum.accumulate(b)
+    return b.astype(np.uint32)
+
+
+class ShardedGemWell:
+    def __init__(self, engine, rank: int, world: int, group=None):
+        self.e = engine
+        self.rank, self.world, self.group = rank, world, group
+        self.bounds = None
+        self.exchange_bytes = 0
+
+    def _allreduce(self, t: torch.Tensor):
+        if self.world > 1 and t is not None and t.numel():
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def run(self):
+        e = self.e
+        e.make_shard()
+        for t in e.prior_tensors():
+            self._allreduce(t)
+        self._allreduce(e.fb_counts_tensor())
+        e.sync()
+        e.barcode_correction()
+        valid = e.valid_count_tensors()
+        for t in valid:
+            self._allreduce(t)
+        e.sync()
+        total = valid[0].to(torch.int64)
+        for t in valid[1:]:
+            total = total + t.to(torch.int64)
+        self.bounds = owner_bounds(total, self.world)
+        if self.world > 1:
+            keys, send_counts = e.keys_partition(self.bounds)
+            sc = torch.as_tensor(send_counts, dtype=torch.int64, device=keys.device)
+            rc = torch.empty_like(sc)
+            dist.all_to_all_single(rc, sc, group=self.group)
+            recv_counts = rc.cpu().numpy()
+            recv = e.new_keys(int(recv_counts.sum()))
+            dist.all_to_all_single(recv, keys, output_split_sizes=[int(x) for x in recv_counts],
+                                   input_split_sizes=[int(x) for x in send_counts], group=self.group)
+            self.exchange_bytes = int(send_counts.sum() - send_counts[self.rank]) * 8
+            e.keys_set(recv)
+        e.set_owned_range(int(self.bounds[self.rank]), int(self.bounds[self.rank + 1]))
+        e.align_and_count()

@@ -788,6 +788,20 @@ void cro_add_reads(void* p, int lib, uint64_t n, int r1_len, const uint8_t* r1_s
   c.batches.push_back(b);
 }
 
+// drop the read batches and every per-run result; whitelists, libraries and features stay
+void cro_reset_reads(void* p) {
+  Ctx& c = *(Ctx*)p;
+  c.batches.clear();
+  c.n_reads = 0;
+  c.out.clear();
+  c.bc_content.clear();
+  c.umi_out.clear();
+  for (auto& l : c.libs) {
+    l.prior.clear();
+    l.corrected_counts.clear();
+  }
+}
+
 void cro_pass1(void* p, int threads) { pass1(*(Ctx*)p, threads); }
 void cro_pass2(void* p, int threads) { pass2(*(Ctx*)p, threads); }
 void cro_count(void* p, int threads) { count_stage(*(Ctx*)p, threads); }

@@ -124,6 +124,10 @@ class Oracle:
         self.L.cro_add_reads(self.ctx, lib, C.c_uint64(n), r1_len, _p(r1_seq), _p(r1_qual), _p(feat),
                              r2_len, _p(r2_seq), _p(r2_qual))
 
+    def reset_reads(self):
+        self.L.cro_reset_reads(self.ctx)
+        self._keep = []
+
     def pass1(self, threads=1):
         self.L.cro_pass1(self.ctx, threads)
 
