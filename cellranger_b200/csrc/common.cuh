@@ -37,6 +37,10 @@ struct DevWhitelist {
   const uint32_t* offs[CRGPU_MAX_ORD];  // (1 << p) + 1 bucket starts
   int rot[CRGPU_MAX_ORD];
   uint32_t resp[CRGPU_MAX_ORD];  // bit `pos` set: this ordering answers for mutations at base `pos`
+  // exact membership: a finer bucket table over ordering 0 (about 1.5 entries per bucket): start index of
+  // the bucket q >> exact_shift. keys[0] carries two 0xFFFFFFFF sentinels past its end.
+  const uint32_t* exact_offs;
+  int exact_shift;
 };
 
 // how the 64-bit dedup key is laid out: rank | feature | library | umi
@@ -53,29 +57,46 @@ __device__ __forceinline__ uint32_t rotr_bits(uint32_t q, int r, int nbits) {
 }
 
 // exact membership through ordering 0 (rot 0). Returns the entry index or -1.
-__device__ __forceinline__ int wl_find(const DevWhitelist& wl, uint32_t q) {
-  const uint32_t* __restrict__ offs = wl.offs[0];
-  const uint32_t* __restrict__ keys = wl.keys[0];
-  uint32_t b = wl.s >= 32 ? 0u : (q >> wl.s);
-  uint32_t lo = __ldg(offs + b), hi = __ldg(offs + b + 1);
-  if (hi - lo > 24) {  // oversized bucket: binary search
-    while (lo < hi) {
-      uint32_t mid = (lo + hi) >> 1;
-      uint32_t e = __ldg(keys + mid);
-      if (e == q) return (int)mid;
-      if (e < q)
-        lo = mid + 1;
-      else
-        hi = mid;
+// Split in two so that callers can issue the loads of several independent lookups before resolving any:
+// wl_find_begin() loads the bucket start, wl_find_probe() the first two entries, wl_find_end() decides.
+struct WlProbe {
+  uint32_t start, e0, e1;
+};
+__device__ __forceinline__ uint32_t wl_find_begin(const DevWhitelist& wl, uint32_t q) {
+  uint32_t b = wl.exact_shift >= 32 ? 0u : (q >> wl.exact_shift);
+  return __ldg(wl.exact_offs + b);
+}
+__device__ __forceinline__ WlProbe wl_find_probe(const DevWhitelist& wl, uint32_t start) {
+  WlProbe p;
+  p.start = start;
+  p.e0 = __ldg(wl.keys[0] + start);
+  p.e1 = __ldg(wl.keys[0] + start + 1);
+  return p;
+}
+__device__ __forceinline__ int wl_find_end(const DevWhitelist& wl, const WlProbe& p, uint32_t q) {
+  uint32_t idx;
+  if (p.e0 >= q) {
+    if (p.e0 != q) return -1;
+    idx = p.start;
+  } else if (p.e1 >= q) {
+    if (p.e1 != q) return -1;
+    idx = p.start + 1;
+  } else {
+    const uint32_t* __restrict__ keys = wl.keys[0];
+    idx = p.start + 2;
+    while (true) {  // the keys are sorted and end with 0xFFFFFFFF sentinels
+      uint32_t e = __ldg(keys + idx);
+      if (e >= q) {
+        if (e != q) return -1;
+        break;
+      }
+      idx++;
     }
-    return -1;
   }
-  for (uint32_t i = lo; i < hi; i++) {
-    uint32_t e = __ldg(keys + i);
-    if (e == q) return (int)i;
-    if (e > q) break;
-  }
-  return -1;
+  return idx < wl.W ? (int)idx : -1;  // a hit on a sentinel is a miss
+}
+__device__ __forceinline__ int wl_find(const DevWhitelist& wl, uint32_t q) {
+  return wl_find_end(wl, wl_find_probe(wl, wl_find_begin(wl, q)), q);
 }
 
 __device__ __forceinline__ uint32_t wl_rank_of(const DevWhitelist& wl, int idx) {

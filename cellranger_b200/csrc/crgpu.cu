@@ -141,7 +141,7 @@ struct crgpu_ctx {
 
   // dedup
   DevBuf dkeys, c0, best, inc, low, key2, key2_alt, lb_desc, tickets, scalars, ent_rank, ent_feature, ent_count, mol;
-  DevBuf col_of_rank, barcode_rank, indptr, mol_rows, min_read, rep_raw;
+  DevBuf col_of_rank, barcode_rank, indptr, mol_rows, min_read, rep_raw, ls_slots;
   uint64_t n_distinct = 0, n_mol = 0, nnz = 0, n_barcodes = 0;
   uint32_t own_lo = 0, own_hi = 0xFFFFFFFFu;
   bool annotated = false;
@@ -360,7 +360,8 @@ void crgpu_ctx_destroy(crgpu_ctx* c) {
   DevBuf* all[] = {&c->d_fb_counts, &c->d_feat_dist, &c->bc_out, &c->umi_out, &c->umi_proc, &c->flags, &c->keys,
                    &c->keys_alt, &c->sort_temp, &c->counters, &c->dkeys, &c->c0, &c->best, &c->inc, &c->low, &c->key2,
                    &c->key2_alt, &c->lb_desc, &c->tickets, &c->scalars, &c->ent_rank, &c->ent_feature, &c->ent_count,
-                   &c->mol, &c->col_of_rank, &c->barcode_rank, &c->indptr, &c->mol_rows, &c->min_read, &c->rep_raw};
+                   &c->mol, &c->col_of_rank, &c->barcode_rank, &c->indptr, &c->mol_rows, &c->min_read, &c->rep_raw,
+                   &c->ls_slots};
   for (auto* b : all) b->release();
   for (auto& p : c->phases) {
     cudaEventDestroy(p.second.first);
@@ -447,7 +448,7 @@ int crgpu_whitelist_add(crgpu_ctx* c, const uint8_t* seqs, uint64_t n, int L, co
     std::vector<std::pair<uint32_t, uint32_t>> rk(W);
     for (uint32_t i = 0; i < W; i++) rk[i] = {rotr_host(kv[i].first, r, nbits), rank[i]};
     if (r != 0) std::sort(rk.begin(), rk.end());
-    std::vector<uint32_t> keys(W), vals(W), offs(n_buckets + 1, 0);
+    std::vector<uint32_t> keys(W + 2, 0xFFFFFFFFu), vals(W), offs(n_buckets + 1, 0);  // two sentinels
     for (uint32_t i = 0; i < W; i++) {
       keys[i] = rk[i].first;
       vals[i] = rk[i].second;
@@ -457,10 +458,28 @@ int crgpu_whitelist_add(crgpu_ctx* c, const uint8_t* seqs, uint64_t n, int L, co
     for (uint64_t b = 0; b < n_buckets; b++) offs[b + 1] += offs[b];
     DevBuf dk, dv, dof;
     int rc;
-    if ((rc = dk.ensure((size_t)W * 4))) return rc;
+    if ((rc = dk.ensure((size_t)(W + 2) * 4))) return rc;
     if ((rc = dof.ensure((n_buckets + 1) * 4))) return rc;
-    CU(cudaMemcpy(dk.p, keys.data(), (size_t)W * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dk.p, keys.data(), (size_t)(W + 2) * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dof.p, offs.data(), (n_buckets + 1) * 4, cudaMemcpyHostToDevice));
+    if (o == 0) {
+      // finer table for exact membership: about 1.5 entries per bucket
+      int pe = 0;
+      while (pe < nbits && ((uint64_t)W >> pe) > 1) pe++;
+      if (pe > 0) pe -= 1;
+      if (pe > 26) pe = 26;
+      const int eshift = nbits - pe;
+      const uint64_t nb = 1ull << pe;
+      std::vector<uint32_t> eo(nb + 1, 0);
+      for (uint32_t i = 0; i < W; i++) eo[(eshift >= 32 ? 0 : (keys[i] >> eshift)) + 1]++;
+      for (uint64_t b = 0; b < nb; b++) eo[b + 1] += eo[b];
+      DevBuf de;
+      if ((rc = de.ensure((nb + 1) * 4))) return rc;
+      CU(cudaMemcpy(de.p, eo.data(), (nb + 1) * 4, cudaMemcpyHostToDevice));
+      w->dev.exact_offs = de.as<uint32_t>();
+      w->dev.exact_shift = eshift;
+      w->bufs.push_back(de);
+    }
     w->dev.keys[o] = dk.as<uint32_t>();
     w->dev.offs[o] = dof.as<uint32_t>();
     w->bufs.push_back(dk);
@@ -1075,13 +1094,24 @@ int crgpu_count(crgpu_ctx* c) {
   b.scalars = c->scalars.as<unsigned long long>();
   b.sort_temp = c->sort_temp.p;
   b.sort_temp_bytes = c->sort_temp.cap;
+  {
+    int slot_bits = 16;
+    while (slot_bits < 29 && (1ull << slot_bits) < 8 * cap) slot_bits++;
+    if ((rc = c->ls_slots.ensure(((size_t)1 << slot_bits) / 4))) return rc;
+    b.slots = c->ls_slots.as<uint32_t>();
+    b.slots_bytes = c->ls_slots.cap;
+  }
   b.ent_rank = c->ent_rank.as<uint32_t>();
   b.ent_feature = c->ent_feature.as<uint32_t>();
   b.ent_count = c->ent_count.as<uint32_t>();
   b.mol = c->mol.as<uint32_t>();
   b.cap = cap;
   uint64_t m = 0;
-  c->launches += run_dedup(b, &m, c->stream);
+  {
+    int nl = run_dedup(b, &m, c->stream);
+    if (nl < 0) return fail(CRGPU_E_INVALID, "internal: low-support slot table too small");
+    c->launches += nl;
+  }
   CHECK_KERNEL();
   c->n_distinct = m;
   if ((rc = phase_end(c))) return rc;

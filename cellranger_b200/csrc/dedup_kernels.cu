@@ -105,121 +105,271 @@ __device__ __forceinline__ bool hamming1_2bit(unsigned long long a, unsigned lon
   return y != 0ull && (y & (y - 1ull)) == 0ull;
 }
 
-__global__ void __launch_bounds__(256) correct_umis_kernel(const unsigned long long* __restrict__ dkeys,
-                                                           const uint32_t* __restrict__ c0, uint64_t m, KeyLayout kl,
-                                                           uint32_t corr_mask, uint32_t* __restrict__ best,
-                                                           unsigned long long* __restrict__ inc,
-                                                           unsigned long long* __restrict__ scalars) {
+// candidate update shared by every search strategy: argmax of the tuple (count, umi)
+struct BestPick {
+  uint32_t count;
+  unsigned long long umi;
+  uint32_t idx;
+  __device__ __forceinline__ void consider(uint32_t tc, unsigned long long tu, uint32_t ti) {
+    if (tc > count || (tc == count && tu > umi)) {
+      count = tc;
+      umi = tu;
+      idx = ti;
+    }
+  }
+};
+
+// Search in global memory for segments too long for the shared-memory window: locate the segment, then
+// binary-search the three mutants of each UMI base side by side (independent chains).
+__device__ __noinline__ void correct_one_global(const unsigned long long* __restrict__ dkeys,
+                                                const uint32_t* __restrict__ c0, uint64_t m, int ub, uint64_t j,
+                                                BestPick* bp) {
+  const unsigned long long key = dkeys[j];
+  const unsigned long long seg = key >> ub;
+  const unsigned long long umask = (1ull << ub) - 1ull;
+  // gallop outwards to bracket the segment, then bisect
+  uint64_t lo = j, step = 64;
+  while (true) {
+    uint64_t probe = lo >= step ? lo - step : 0;
+    if ((dkeys[probe] >> ub) != seg) {
+      uint64_t a = probe, b = lo;  // dkeys[a] outside, dkeys[b] inside
+      while (b - a > 1) {
+        uint64_t mid = (a + b) >> 1;
+        if ((dkeys[mid] >> ub) == seg)
+          b = mid;
+        else
+          a = mid;
+      }
+      lo = b;
+      break;
+    }
+    lo = probe;
+    if (probe == 0) break;
+    step <<= 1;
+  }
+  uint64_t hi = j;
+  step = 64;
+  while (true) {
+    uint64_t probe = hi + step < m ? hi + step : m - 1;
+    if ((dkeys[probe] >> ub) != seg) {
+      uint64_t a = hi, b = probe;  // dkeys[a] inside, dkeys[b] outside
+      while (b - a > 1) {
+        uint64_t mid = (a + b) >> 1;
+        if ((dkeys[mid] >> ub) == seg)
+          a = mid;
+        else
+          b = mid;
+      }
+      hi = a;
+      break;
+    }
+    hi = probe;
+    if (probe == m - 1) break;
+    step <<= 1;
+  }
+  const uint64_t s_lo = lo, s_hi = hi + 1;
+  for (int sh = 0; sh < ub; sh += 2) {
+    unsigned long long t[3];
+    uint64_t a[3], b[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      t[d] = key ^ ((unsigned long long)(d + 1) << sh);
+      a[d] = s_lo;
+      b[d] = s_hi;
+    }
+    bool more = true;
+    while (more) {
+      more = false;
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        if (a[d] < b[d]) {
+          uint64_t mid = (a[d] + b[d]) >> 1;
+          if (dkeys[mid] < t[d])
+            a[d] = mid + 1;
+          else
+            b[d] = mid;
+          more = true;
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+      if (a[d] < s_hi && dkeys[a[d]] == t[d]) bp->consider(c0[a[d]], t[d] & umask, (uint32_t)a[d]);
+  }
+}
+
+// Tiled kernel: a block answers CU_TILE consecutive keys out of a shared-memory window that also holds
+// CU_HALO keys on each side, so every segment of up to CU_HALO keys that touches the tile is complete in
+// shared memory. Segments of one key need nothing, short ones are compared pairwise, longer ones probe a
+// shared-memory hash set with the 3L mutants; only segments longer than the halo go to global memory.
+constexpr int CU_THREADS = 512;
+constexpr int CU_TILE = 2048;
+constexpr int CU_HALO = 1024;
+constexpr int CU_WIN = CU_TILE + 2 * CU_HALO;
+constexpr int CU_SLOTS = 2 * CU_WIN;
+constexpr int CU_SMALL = 12;
+constexpr uint32_t CU_EMPTY = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t cu_hash(unsigned long long k) {
+  return (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> 51) & (CU_SLOTS - 1);
+}
+
+__global__ void __launch_bounds__(CU_THREADS) correct_umis_kernel(const unsigned long long* __restrict__ dkeys,
+                                                                  const uint32_t* __restrict__ c0, uint64_t m,
+                                                                  KeyLayout kl, uint32_t corr_mask,
+                                                                  uint32_t* __restrict__ best,
+                                                                  unsigned long long* __restrict__ inc,
+                                                                  unsigned long long* __restrict__ scalars) {
+  extern __shared__ __align__(16) unsigned char cu_smem[];
+  unsigned long long* w_key = reinterpret_cast<unsigned long long*>(cu_smem);          // CU_WIN
+  uint32_t* w_c0 = reinterpret_cast<uint32_t*>(w_key + CU_WIN);                          // CU_WIN
+  uint32_t* table = w_c0 + CU_WIN;                                                       // CU_SLOTS
+  unsigned short* seg_lo = reinterpret_cast<unsigned short*>(table + CU_SLOTS);          // CU_WIN
+  unsigned short* seg_hi = seg_lo + CU_WIN;                                              // CU_WIN (exclusive end)
+  __shared__ unsigned long long s_corr, s_corr_reads;
+  __shared__ int s_need_hash;
+
   const int ub = kl.umi_bits;
   const unsigned long long umask = (1ull << ub) - 1ull;
   const uint32_t lmask = (1u << (kl.feature_shift - kl.lib_shift)) - 1u;
+  const int tid = threadIdx.x;
+  const uint64_t q_lo = (uint64_t)blockIdx.x * CU_TILE;
+  const uint64_t q_hi = q_lo + CU_TILE < m ? q_lo + CU_TILE : m;
+  const uint64_t w_lo = q_lo >= CU_HALO ? q_lo - CU_HALO : 0;
+  const uint64_t w_hi = q_hi + CU_HALO < m ? q_hi + CU_HALO : m;
+  const int wn = (int)(w_hi - w_lo);
+
+  if (tid == 0) {
+    s_corr = 0;
+    s_corr_reads = 0;
+    s_need_hash = 0;
+  }
+  for (int i = tid; i < wn; i += CU_THREADS) {
+    w_key[i] = dkeys[w_lo + i];
+    w_c0[i] = c0[w_lo + i];
+  }
+  for (int i = tid; i < CU_SLOTS; i += CU_THREADS) table[i] = CU_EMPTY;
+  __syncthreads();
+  // is the first / last segment of the window cut by the window edge?
+  const bool cut_l = w_lo > 0 && (dkeys[w_lo - 1] >> ub) == (w_key[0] >> ub);
+  const bool cut_r = w_hi < m && (dkeys[w_hi] >> ub) == (w_key[wn - 1] >> ub);
+
+  // segment bounds of every window element: each thread owns a contiguous chunk, chunks are stitched
+  // through shared memory (first pass: local runs; second pass: extend across chunk borders)
+  constexpr int PER = CU_WIN / CU_THREADS;  // 8
+  {
+    const int c_lo = tid * PER;
+    int run_start = c_lo;
+    for (int k = 0; k < PER; k++) {
+      int i = c_lo + k;
+      if (i >= wn) break;
+      if (k > 0 && (w_key[i] >> ub) != (w_key[i - 1] >> ub)) run_start = i;
+      seg_lo[i] = (unsigned short)run_start;
+    }
+  }
+  __syncthreads();
+  {
+    // extend the run that starts at a chunk border backwards while the segment continues
+    const int c_lo = tid * PER;
+    if (c_lo < wn && c_lo > 0 && (w_key[c_lo] >> ub) == (w_key[c_lo - 1] >> ub)) {
+      const unsigned long long sg = w_key[c_lo] >> ub;
+      int s = c_lo - 1;
+      // jump chunk by chunk: seg_lo of the previous element already points to its local run start
+      while (true) {
+        s = seg_lo[s];
+        if (s == 0 || (s % PER) != 0 || (w_key[s - 1] >> ub) != sg) break;
+        s = s - 1;
+      }
+      for (int k = 0; k < PER; k++) {
+        int i = c_lo + k;
+        if (i >= wn || (w_key[i] >> ub) != sg) break;
+        seg_lo[i] = (unsigned short)s;  // only elements whose local run began at the chunk border
+      }
+    }
+  }
+  __syncthreads();
+  // exclusive end: one pass from the right using seg_lo of the successor
+  {
+    const int c_lo = tid * PER;
+    for (int k = 0; k < PER; k++) {
+      int i = c_lo + k;
+      if (i >= wn) break;
+      if (i + 1 >= wn || seg_lo[i + 1] != seg_lo[i]) {
+        // i is the last element of its segment: publish the end to the whole segment lazily via the head
+        seg_hi[seg_lo[i]] = (unsigned short)(i + 1);
+      }
+    }
+  }
+  __syncthreads();
+  // hash the members of the longer segments
+  for (int i = tid; i < wn; i += CU_THREADS) {
+    int s = seg_lo[i];
+    int n = (int)seg_hi[s] - s;
+    if (n > CU_SMALL) {
+      s_need_hash = 1;
+      uint32_t h = cu_hash(w_key[i]);
+      while (atomicCAS(&table[h], CU_EMPTY, (uint32_t)i) != CU_EMPTY) h = (h + 1) & (CU_SLOTS - 1);
+    }
+  }
+  __syncthreads();
+
   unsigned long long n_corr = 0, n_corr_reads = 0;
-  for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < m; j += (uint64_t)gridDim.x * blockDim.x) {
-    const unsigned long long key = dkeys[j];
-    const unsigned long long seg = key >> ub;
+  const int q_off = (int)(q_lo - w_lo);
+  const int qn = (int)(q_hi - q_lo);
+  for (int qi = tid; qi < qn; qi += CU_THREADS) {
+    const int i = q_off + qi;
+    const uint64_t j = w_lo + i;
+    const unsigned long long key = w_key[i];
     const uint32_t lib = (uint32_t)(key >> kl.lib_shift) & lmask;
-    uint32_t bj = (uint32_t)j;
+    BestPick bp{w_c0[i], key & umask, (uint32_t)j};
     if ((corr_mask >> lib) & 1u) {
-      uint32_t bcount = c0[j];
-      unsigned long long bumi = key & umask;
-      constexpr int WINDOW = 48;
-      bool big = (j >= WINDOW && (dkeys[j - WINDOW] >> ub) == seg) || (j + WINDOW < m && (dkeys[j + WINDOW] >> ub) == seg);
-      if (!big) {
-        for (int64_t k = (int64_t)j - 1; k >= 0; k--) {
-          unsigned long long o = dkeys[k];
-          if ((o >> ub) != seg) break;
-          if (hamming1_2bit(o, key)) {
-            uint32_t tc = c0[k];
-            unsigned long long tu = o & umask;
-            if (tc > bcount || (tc == bcount && tu > bumi)) {
-              bcount = tc;
-              bumi = tu;
-              bj = (uint32_t)k;
-            }
+      const int s = seg_lo[i];
+      const int e = seg_hi[s];
+      const int n = e - s;
+      if ((s == 0 && cut_l) || (e == wn && cut_r)) {
+        correct_one_global(dkeys, c0, m, ub, j, &bp);
+      } else if (n > 1) {
+        if (n <= CU_SMALL) {
+          for (int k = s; k < e; k++) {
+            unsigned long long o = w_key[k];
+            if (hamming1_2bit(o, key)) bp.consider(w_c0[k], o & umask, (uint32_t)(w_lo + k));
           }
-        }
-        for (uint64_t k = j + 1; k < m; k++) {
-          unsigned long long o = dkeys[k];
-          if ((o >> ub) != seg) break;
-          if (hamming1_2bit(o, key)) {
-            uint32_t tc = c0[k];
-            unsigned long long tu = o & umask;
-            if (tc > bcount || (tc == bcount && tu > bumi)) {
-              bcount = tc;
-              bumi = tu;
-              bj = (uint32_t)k;
-            }
-          }
-        }
-      } else {
-        // large segment: locate it, then binary-search each of the 3L mutants
-        uint64_t lo = 0, hi = j;
-        const unsigned long long seg_first = seg << ub;
-        while (lo < hi) {
-          uint64_t mid = (lo + hi) >> 1;
-          if (dkeys[mid] < seg_first)
-            lo = mid + 1;
-          else
-            hi = mid;
-        }
-        const uint64_t s_lo = lo;
-        lo = j;
-        hi = m;
-        while (lo < hi) {
-          uint64_t mid = (lo + hi) >> 1;
-          if ((dkeys[mid] >> ub) <= seg)
-            lo = mid + 1;
-          else
-            hi = mid;
-        }
-        const uint64_t s_hi = lo;
-        for (int sh = 0; sh < ub; sh += 2) {
-          for (unsigned long long d = 1; d < 4; d++) {
-            unsigned long long t = key ^ (d << sh);
-            uint64_t a = s_lo, b = s_hi;
-            while (a < b) {
-              uint64_t mid = (a + b) >> 1;
-              if (dkeys[mid] < t)
-                a = mid + 1;
-              else
-                b = mid;
-            }
-            if (a < s_hi && dkeys[a] == t) {
-              uint32_t tc = c0[a];
-              unsigned long long tu = t & umask;
-              if (tc > bcount || (tc == bcount && tu > bumi)) {
-                bcount = tc;
-                bumi = tu;
-                bj = (uint32_t)a;
+        } else {
+          for (int sh = 0; sh < ub; sh += 2) {
+#pragma unroll
+            for (unsigned long long d = 1; d < 4; d++) {
+              const unsigned long long t = key ^ (d << sh);
+              uint32_t h = cu_hash(t);
+              while (true) {
+                uint32_t idx = table[h];
+                if (idx == CU_EMPTY) break;
+                if (w_key[idx] == t) {
+                  bp.consider(w_c0[idx], t & umask, (uint32_t)(w_lo + idx));
+                  break;
+                }
+                h = (h + 1) & (CU_SLOTS - 1);
               }
             }
           }
         }
       }
     }
-    best[j] = bj;
-    if (bj != (uint32_t)j) {
-      uint32_t c = c0[j];
-      atomicAdd(inc + bj, (1ull << 40) | (unsigned long long)c);
+    best[j] = bp.idx;
+    if (bp.idx != (uint32_t)j) {
+      uint32_t c = w_c0[i];
+      atomicAdd(inc + bp.idx, (1ull << 40) | (unsigned long long)c);
       n_corr++;
       n_corr_reads += c;
     }
   }
-  // block reduction of the statistics
-  __shared__ unsigned long long s_a, s_b;
-  if (threadIdx.x == 0) {
-    s_a = 0;
-    s_b = 0;
-  }
-  __syncthreads();
   if (n_corr) {
-    atomicAdd(&s_a, n_corr);
-    atomicAdd(&s_b, n_corr_reads);
+    atomicAdd(&s_corr, n_corr);
+    atomicAdd(&s_corr_reads, n_corr_reads);
   }
   __syncthreads();
-  if (threadIdx.x == 0 && s_a) {
-    atomicAdd(scalars + 3, s_a);
-    atomicAdd(scalars + 5, s_b);
+  if (tid == 0 && s_corr) {
+    atomicAdd(scalars + 3, s_corr);
+    atomicAdd(scalars + 5, s_corr_reads);
   }
 }
 
@@ -251,6 +401,69 @@ __global__ void make_key2_kernel(const unsigned long long* __restrict__ dkeys, u
   }
 }
 
+// ---- pre-filter for the (rank, library, umi) regrouping ----
+// A UMI is only ever low support when the same (barcode, library, UMI) occurs with two or more
+// features, which is rare. Each distinct key hashes its (rank, library, umi) into a table of 2-bit
+// slots: the first visitor sets bit 0, any later visitor sets bit 1. Keys whose slot has bit 1 are the
+// candidates (all true groups plus hash collisions); only they are sorted and regrouped exactly.
+__device__ __forceinline__ unsigned long long group_hash(unsigned long long key, const KeyLayout& kl,
+                                                         const FieldMasks& fm) {
+  unsigned long long umi = key & ((1ull << fm.ubits) - 1ull);
+  unsigned long long lib = (key >> kl.lib_shift) & ((1ull << fm.lbits) - 1ull);
+  unsigned long long rank = key >> kl.rank_shift;
+  unsigned long long g = ((rank << fm.lbits | lib) << fm.ubits) | umi;
+  g ^= g >> 31;
+  g *= 0x9E3779B97F4A7C15ull;
+  g ^= g >> 29;
+  g *= 0xBF58476D1CE4E5B9ull;
+  g ^= g >> 32;
+  return g;
+}
+
+__global__ void __launch_bounds__(256) ls_mark_kernel(const unsigned long long* __restrict__ dkeys, uint64_t m,
+                                                      KeyLayout kl, uint32_t* __restrict__ slots, int slot_bits) {
+  const FieldMasks fm = field_masks(kl);
+  for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < m; j += (uint64_t)gridDim.x * blockDim.x) {
+    unsigned long long h = group_hash(dkeys[j], kl, fm) >> (64 - slot_bits);
+    uint32_t bit = 1u << (2 * (h & 15));
+    uint32_t old = atomicOr(slots + (h >> 4), bit);
+    if (old & bit) atomicOr(slots + (h >> 4), bit << 1);
+  }
+}
+
+__global__ void __launch_bounds__(256) ls_collect_kernel(const unsigned long long* __restrict__ dkeys, uint64_t m,
+                                                         KeyLayout kl, const uint32_t* __restrict__ slots,
+                                                         int slot_bits, unsigned long long* __restrict__ cand,
+                                                         unsigned long long* __restrict__ n_cand) {
+  __shared__ uint32_t scan_s[9];
+  __shared__ unsigned long long base_s;
+  const FieldMasks fm = field_masks(kl);
+  const uint64_t n_blocks_work = (m + 255) / 256;
+  for (uint64_t blk = blockIdx.x; blk < n_blocks_work; blk += gridDim.x) {
+    uint64_t j = blk * 256 + threadIdx.x;
+    bool hit = false;
+    unsigned long long k2 = 0;
+    if (j < m) {
+      unsigned long long k = dkeys[j];
+      unsigned long long h = group_hash(k, kl, fm) >> (64 - slot_bits);
+      hit = (slots[h >> 4] >> (2 * (h & 15) + 1)) & 1u;
+      if (hit) {
+        unsigned long long umi = k & ((1ull << fm.ubits) - 1ull);
+        unsigned long long lib = (k >> kl.lib_shift) & ((1ull << fm.lbits) - 1ull);
+        unsigned long long feat = (k >> kl.feature_shift) & ((1ull << fm.fbits) - 1ull);
+        unsigned long long rank = k >> kl.rank_shift;
+        k2 = (((rank << fm.lbits | lib) << fm.ubits | umi) << fm.fbits) | feat;
+      }
+    }
+    uint32_t tot;
+    uint32_t off = block_exclusive_scan<256>(hit ? 1u : 0u, &tot, scan_s);
+    if (threadIdx.x == 0) base_s = tot ? atomicAdd(n_cand, (unsigned long long)tot) : 0ull;
+    __syncthreads();
+    if (hit) cand[base_s + off] = k2;
+    __syncthreads();
+  }
+}
+
 __device__ __forceinline__ uint64_t lower_bound_u64(const unsigned long long* a, uint64_t n, unsigned long long v) {
   uint64_t lo = 0, hi = n;
   while (lo < hi) {
@@ -263,8 +476,9 @@ __device__ __forceinline__ uint64_t lower_bound_u64(const unsigned long long* a,
   return lo;
 }
 
-__global__ void __launch_bounds__(256) low_support_kernel(const unsigned long long* __restrict__ key2s, uint64_t m,
-                                                          KeyLayout kl, const unsigned long long* __restrict__ dkeys,
+__global__ void __launch_bounds__(256) low_support_kernel(const unsigned long long* __restrict__ key2s, uint64_t n2,
+                                                          uint64_t m, KeyLayout kl,
+                                                          const unsigned long long* __restrict__ dkeys,
                                                           const uint32_t* __restrict__ c0,
                                                           const uint32_t* __restrict__ best,
                                                           const unsigned long long* __restrict__ inc,
@@ -273,17 +487,17 @@ __global__ void __launch_bounds__(256) low_support_kernel(const unsigned long lo
   const FieldMasks fm = field_masks(kl);
   const unsigned long long fmask = (1ull << fm.fbits) - 1ull;
   unsigned long long n_low = 0;
-  for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < m; k += (uint64_t)gridDim.x * blockDim.x) {
+  for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n2; k += (uint64_t)gridDim.x * blockDim.x) {
     const unsigned long long g = key2s[k] >> fm.fbits;
     if (k > 0 && (key2s[k - 1] >> fm.fbits) == g) continue;          // not the group head
-    if (k + 1 >= m || (key2s[k + 1] >> fm.fbits) != g) continue;     // a single gene: never low support
+    if (k + 1 >= n2 || (key2s[k + 1] >> fm.fbits) != g) continue;     // a single gene: never low support
     // group head with >= 2 features
     const unsigned long long umi = g & ((1ull << fm.ubits) - 1ull);
     const unsigned long long lib = (g >> fm.ubits) & ((1ull << fm.lbits) - 1ull);
     const unsigned long long rank = g >> (fm.ubits + fm.lbits);
     uint64_t mx = 0, n_at_max = 0;
     for (int pass = 0; pass < 2; pass++) {
-      for (uint64_t t = k; t < m && (key2s[t] >> fm.fbits) == g; t++) {
+      for (uint64_t t = k; t < n2 && (key2s[t] >> fm.fbits) == g; t++) {
         unsigned long long feat = key2s[t] & fmask;
         unsigned long long pk = (rank << kl.rank_shift) | (feat << kl.feature_shift) | (lib << kl.lib_shift) | umi;
         uint64_t j = lower_bound_u64(dkeys, m, pk);
@@ -370,18 +584,39 @@ int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
   // 2. UMI correction targets + incoming counts
   cudaMemsetAsync(b.inc, 0, m * 8, st);
   cudaMemsetAsync(b.low, 0, m, st);
-  correct_umis_kernel<<<grid_for(m, 256, 148 * 32), 256, 0, st>>>(b.dkeys, b.c0, m, b.kl, b.umi_correction_mask,
-                                                                  b.best, b.inc, b.scalars);
-  launches++;
-  // 3. low-support filter: regroup by (rank, library, umi)
+  {
+    const size_t smem = (size_t)CU_WIN * 8 + (size_t)CU_WIN * 4 + (size_t)CU_SLOTS * 4 + (size_t)CU_WIN * 2 * 2;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(correct_umis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_set = true;
+    }
+    const unsigned blocks = (unsigned)((m + CU_TILE - 1) / CU_TILE);
+    correct_umis_kernel<<<blocks, CU_THREADS, smem, st>>>(b.dkeys, b.c0, m, b.kl, b.umi_correction_mask, b.best,
+                                                          b.inc, b.scalars);
+    launches++;
+  }
+  // 3. low-support filter: candidates by hashing (rank, library, umi), exact regrouping of those only
   if (b.filter_umis) {
-    make_key2_kernel<<<grid_for(m), 256, 0, st>>>(b.dkeys, m, b.kl, b.key2);
-    launches++;
-    unsigned long long* sorted2 = nullptr;
-    launches += sort_keys(b.key2, b.key2_alt, m, b.kl.total_bits, b.sort_temp, b.sort_temp_bytes, &sorted2, st);
-    low_support_kernel<<<grid_for(m, 256, 148 * 32), 256, 0, st>>>(sorted2, m, b.kl, b.dkeys, b.c0, b.best, b.inc,
-                                                                   b.low, b.scalars);
-    launches++;
+    int slot_bits = 16;
+    while (slot_bits < 29 && (1ull << slot_bits) < 8 * m) slot_bits++;
+    const size_t slot_bytes = ((size_t)1 << slot_bits) / 4;  // 2 bits per slot
+    if (b.slots_bytes < slot_bytes) return -1;
+    cudaMemsetAsync(b.slots, 0, slot_bytes, st);
+    ls_mark_kernel<<<grid_for(m, 256, 148 * 32), 256, 0, st>>>(b.dkeys, m, b.kl, b.slots, slot_bits);
+    ls_collect_kernel<<<grid_for(m, 256, 148 * 16), 256, 0, st>>>(b.dkeys, m, b.kl, b.slots, slot_bits, b.key2,
+                                                                 b.scalars + 9);
+    launches += 2;
+    unsigned long long n_cand = 0;
+    cudaMemcpyAsync(&n_cand, b.scalars + 9, 8, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    if (n_cand) {
+      unsigned long long* sorted2 = nullptr;
+      launches += sort_keys(b.key2, b.key2_alt, n_cand, b.kl.total_bits, b.sort_temp, b.sort_temp_bytes, &sorted2, st);
+      low_support_kernel<<<grid_for(n_cand, 256, 148 * 32), 256, 0, st>>>(sorted2, n_cand, m, b.kl, b.dkeys, b.c0,
+                                                                          b.best, b.inc, b.low, b.scalars);
+      launches++;
+    }
   }
   low_reads_kernel<<<grid_for(m), 256, 0, st>>>(b.c0, b.best, b.low, m, b.scalars);
   launches++;

@@ -112,22 +112,87 @@ __device__ __forceinline__ void load_record(const uint8_t* base, int j, uint32_t
   }
 }
 
+// result of packing one R1 record
+struct Packed {
+  uint32_t bc, nmask, umi;
+  bool umi_has_n, umi_lowq;
+  uint4 bcq;
+};
+
+template <int R1_LEN, int UMI_LEN>
+__device__ __forceinline__ void pack_record(const uint8_t* s_seq, const uint8_t* s_qual, int j, Packed* o) {
+  constexpr int NW = (R1_LEN + 3) / 4;
+  uint32_t ws[NW], wq[NW];
+  load_record<R1_LEN>(s_seq, j, ws);
+  load_record<R1_LEN>(s_qual, j, wq);
+  uint32_t bad0, bad1, bad2, bad3;
+  o->bc = (pack4(ws[0], &bad0) << 24) | (pack4(ws[1], &bad1) << 16) | (pack4(ws[2], &bad2) << 8) | pack4(ws[3], &bad3);
+  uint32_t nmask = 0;
+  if (bad0 | bad1 | bad2 | bad3) {  // bit `pos` for every non-ACGT base (rare path)
+    uint32_t bb[4] = {bad0, bad1, bad2, bad3};
+#pragma unroll
+    for (int wd = 0; wd < 4; wd++)
+#pragma unroll
+      for (int by = 0; by < 4; by++)
+        if (bb[wd] & (0x80u << (8 * by))) nmask |= 1u << (wd * 4 + by);
+  }
+  o->nmask = nmask;
+  uint32_t umi = 0, ubad = 0, ulow = 0;
+  constexpr int UW = (UMI_LEN + 3) / 4;
+#pragma unroll
+  for (int u = 0; u < UW; u++) {
+    uint32_t w = ws[4 + u], q = wq[4 + u];
+    constexpr int full = UMI_LEN / 4;
+    uint32_t bmask = 0xFFFFFFFFu;
+    if (u >= full) {  // partial last word: keep UMI_LEN % 4 bytes
+      bmask = (1u << (8 * (UMI_LEN % 4))) - 1u;
+      w = (w & bmask) | (0x41414141u & ~bmask);
+      q = (q & bmask) | (0x49494949u & ~bmask);
+    }
+    uint32_t bad;
+    uint32_t p = pack4(w, &bad);
+    ubad |= bad & bmask;
+    ulow |= lowqual4(q) & bmask;
+    umi = (umi << 8) | p;
+  }
+  if constexpr (UMI_LEN % 4 != 0) umi >>= 2 * (4 - UMI_LEN % 4);
+  o->umi = umi;
+  o->umi_has_n = ubad != 0;
+  o->umi_lowq = ulow != 0;
+  o->bcq = make_uint4(wq[0], wq[1], wq[2], wq[3]);
+}
+
+__device__ __forceinline__ unsigned long long make_evict_first_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                              unsigned long long policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
 template <int R1_LEN, int UMI_LEN, int THREADS, int RPT, int STAGES>
 __global__ void __launch_bounds__(THREADS) pass1_staged_kernel(const Pass1Args a) {
   constexpr int TILE = THREADS * RPT;
   constexpr int SEQ_BYTES = TILE * R1_LEN;
   constexpr int REC_PAD = 16;  // the unaligned record loader reads one word past a record
   constexpr int STAGE_BYTES = 2 * (SEQ_BYTES + REC_PAD) + TILE * 4;
-  constexpr int NW = (R1_LEN + 3) / 4;
+  constexpr int NWARPS = THREADS / 32;
   static_assert(SEQ_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t mbar[STAGES];
-  __shared__ uint32_t scan_a[THREADS / 32 + 1], scan_b[THREADS / 32 + 1];
-  __shared__ unsigned long long base_bcast;
+  __shared__ uint32_t warp_tot[2][NWARPS];
+  __shared__ unsigned long long base_bcast[2];
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t n_tiles = (a.n + TILE - 1) / TILE;
   const bool have_feat = a.feature != nullptr;
+  const unsigned long long policy = make_evict_first_policy();  // the reads stream through L2 once
 
   if (tid == 0) {
 #pragma unroll
@@ -147,9 +212,9 @@ __global__ void __launch_bounds__(THREADS) pass1_staged_kernel(const Pass1Args a
     if (first + TILE <= a.n) {
       uint32_t bytes = 2 * SEQ_BYTES + (have_feat ? TILE * 4 : 0);
       mbar_expect_tx(&mbar[s], bytes);
-      bulk_g2s(stage_seq(s), a.seq + first * R1_LEN, SEQ_BYTES, &mbar[s]);
-      bulk_g2s(stage_qual(s), a.qual + first * R1_LEN, SEQ_BYTES, &mbar[s]);
-      if (have_feat) bulk_g2s(stage_feat(s), a.feature + first, TILE * 4, &mbar[s]);
+      bulk_g2s_hint(stage_seq(s), a.seq + first * R1_LEN, SEQ_BYTES, &mbar[s], policy);
+      bulk_g2s_hint(stage_qual(s), a.qual + first * R1_LEN, SEQ_BYTES, &mbar[s], policy);
+      if (have_feat) bulk_g2s_hint(stage_feat(s), a.feature + first, TILE * 4, &mbar[s], policy);
     }
   };
 
@@ -184,90 +249,109 @@ __global__ void __launch_bounds__(THREADS) pass1_staged_kernel(const Pass1Args a
       __syncthreads();
     }
 
-    ReadResult res[RPT];
-    uint32_t nmask_r[RPT], bc_r[RPT];
-    uint4 bcq_r[RPT];
-    uint32_t n_key = 0, n_inv = 0;
+    // ---- phase 1: shared memory -> registers, 2-bit packing, UMI checks ----
+    Packed pk[RPT];
+    uint32_t feat[RPT];
+    bool live[RPT];
 #pragma unroll
     for (int k = 0; k < RPT; k++) {
       const int j = tid + k * THREADS;
-      res[k].emit_key = false;
-      res[k].invalid = false;
-      if (j < cnt) {
-        uint32_t ws[NW], wq[NW];
-        load_record<R1_LEN>(stage_seq(s), j, ws);
-        load_record<R1_LEN>(stage_qual(s), j, wq);
-        uint32_t bad0, bad1, bad2, bad3;
-        uint32_t bc = (pack4(ws[0], &bad0) << 24) | (pack4(ws[1], &bad1) << 16) | (pack4(ws[2], &bad2) << 8) |
-                      pack4(ws[3], &bad3);
-        uint32_t nmask = 0;
-        if (bad0 | bad1 | bad2 | bad3) {
-          // bit `pos` for every non-ACGT base (rare path)
-          uint32_t bb[4] = {bad0, bad1, bad2, bad3};
-#pragma unroll
-          for (int wd = 0; wd < 4; wd++)
-#pragma unroll
-            for (int by = 0; by < 4; by++)
-              if (bb[wd] & (0x80u << (8 * by))) nmask |= 1u << (wd * 4 + by);
-        }
-        // UMI
-        uint32_t umi = 0, ubad = 0, ulow = 0;
-        constexpr int UW = (UMI_LEN + 3) / 4;
-#pragma unroll
-        for (int u = 0; u < UW; u++) {
-          uint32_t w = ws[4 + u], q = wq[4 + u];
-          constexpr int full = UMI_LEN / 4;
-          uint32_t bmask = 0xFFFFFFFFu;
-          if (u >= full) {  // partial last word: keep UMI_LEN % 4 bytes
-            bmask = (1u << (8 * (UMI_LEN % 4))) - 1u;
-            w = (w & bmask) | (0x41414141u & ~bmask);
-            q = (q & bmask) | (0x49494949u & ~bmask);
-          }
-          uint32_t bad;
-          uint32_t p = pack4(w, &bad);
-          ubad |= bad & bmask;
-          ulow |= lowqual4(q) & bmask;
-          umi = (umi << 8) | p;
-        }
-        if constexpr (UMI_LEN % 4 != 0) umi >>= 2 * (4 - UMI_LEN % 4);
-        uint32_t feature = have_feat ? stage_feat(s)[j] : NO_FEATURE;
-        classify_read(a, bc, nmask, umi, ubad != 0, ulow != 0, feature, &res[k]);
-        nmask_r[k] = nmask;
-        bc_r[k] = bc;
-        bcq_r[k] = make_uint4(wq[0], wq[1], wq[2], wq[3]);
-        n_key += res[k].emit_key;
-        n_inv += res[k].invalid;
+      live[k] = j < cnt;
+      if (live[k]) {
+        pack_record<R1_LEN, UMI_LEN>(stage_seq(s), stage_qual(s), j, &pk[k]);
+        feat[k] = have_feat ? stage_feat(s)[j] : NO_FEATURE;
+      } else {
+        pk[k].bc = 0;
+        pk[k].nmask = 1;
+        pk[k].umi = 0;
+        pk[k].umi_has_n = true;
+        pk[k].umi_lowq = false;
+        pk[k].bcq = make_uint4(0, 0, 0, 0);
+        feat[k] = NO_FEATURE;
       }
     }
-    // block-wide placement of this tile's keys and invalid entries
-    uint32_t tot_key, tot_inv;
-    uint32_t off_key = block_exclusive_scan<THREADS>(n_key, &tot_key, scan_a);
-    uint32_t off_inv = block_exclusive_scan<THREADS>(n_inv, &tot_inv, scan_b);
-    if (tid == 0)
-      base_bcast = (tot_key | tot_inv)
-                       ? atomicAdd(a.counters, (unsigned long long)tot_key | ((unsigned long long)tot_inv << 32))
-                       : 0ull;
-    __syncthreads();  // also: every thread is done reading stage s
-    const unsigned long long base = base_bcast;
-    uint64_t kpos = (base & 0xFFFFFFFFull) + off_key;
-    uint64_t ipos = (base >> 32) + off_inv;
+    __syncthreads();  // stage s is free again: refill it right away, two tiles ahead
     if (tid == 0) {
       uint64_t next = tile + (uint64_t)STAGES * gridDim.x;
       if (next < n_tiles) issue(next, s);
     }
+
+    // ---- phase 2: exact whitelist lookups, all loads of the RPT reads in flight together ----
+    uint32_t st0[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; k++) st0[k] = wl_find_begin(a.wl, pk[k].bc);
+    WlProbe pr[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; k++) pr[k] = wl_find_probe(a.wl, st0[k]);
+    uint32_t bcw[RPT], umw[RPT];
+    unsigned long long key[RPT];
+    bool emit[RPT], inval[RPT];
+    uint32_t n_key = 0, n_inv = 0;
 #pragma unroll
     for (int k = 0; k < RPT; k++) {
-      const int j = tid + k * THREADS;
-      if (j < cnt) {
-        uint64_t gi = first + j;
-        a.bc_out[gi] = res[k].bc_word;
-        a.umi_out[gi] = res[k].umi_word;
-        if (res[k].emit_key) a.keys[kpos++] = res[k].key;
-        if (res[k].invalid) {
+      int idx = pk[k].nmask ? -1 : wl_find_end(a.wl, pr[k], pk[k].bc);
+      const uint32_t rep = 0x55555555u & mask_bits(2 * UMI_LEN);
+      bool homopolymer = pk[k].umi == (pk[k].umi & 3u) * rep;
+      bool umi_valid = !(pk[k].umi_has_n || homopolymer || pk[k].umi_lowq);
+      umw[k] = (pk[k].umi & UMI_SEQ_MASK) | (umi_valid ? UMI_VALID_BIT : 0u) | (pk[k].umi_has_n ? UMI_HASN_BIT : 0u);
+      emit[k] = false;
+      inval[k] = false;
+      key[k] = 0ull;
+      if (idx >= 0) {
+        uint32_t rank = wl_rank_of(a.wl, idx);
+        if (a.prior) atomicAdd(a.prior + rank, 1u);
+        bcw[k] = (ST_VALID_BEFORE << BC_STATE_SHIFT) | rank;
+        if (a.emit_keys && umi_valid && feat[k] != NO_FEATURE) {
+          emit[k] = true;
+          key[k] = make_key(a.kl, rank, feat[k], a.lib, pk[k].umi);
+        }
+      } else {
+        bcw[k] = (ST_INVALID << BC_STATE_SHIFT) | BC_RANK_MASK;
+        inval[k] = live[k];
+      }
+      n_key += emit[k];
+      n_inv += inval[k];
+    }
+
+    // ---- phase 3: one block scan places the tile's keys and invalid entries (counts packed 16+16) ----
+    const uint32_t v = n_key | (n_inv << 16);
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    const int par = it & 1;
+    if (lane == 31) warp_tot[par][warp] = inc;
+    __syncthreads();
+    uint32_t wsum = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < NWARPS; w++) {
+      uint32_t c = warp_tot[par][w];
+      if (w < warp) wsum += c;
+      tot += c;
+    }
+    const uint32_t excl = wsum + inc - v;
+    if (tid == 0)
+      base_bcast[par] = tot ? atomicAdd(a.counters, (unsigned long long)(tot & 0xFFFFu) |
+                                                        ((unsigned long long)(tot >> 16) << 32))
+                            : 0ull;
+    __syncthreads();
+    const unsigned long long base = base_bcast[par];
+    uint64_t kpos = (base & 0xFFFFFFFFull) + (excl & 0xFFFFu);
+    uint64_t ipos = (base >> 32) + (excl >> 16);
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
+      if (live[k]) {
+        uint64_t gi = first + tid + k * THREADS;
+        __stcs(a.bc_out + gi, bcw[k]);
+        __stcs(a.umi_out + gi, umw[k]);
+        if (emit[k]) __stcs(a.keys + kpos++, key[k]);
+        if (inval[k]) {
           a.inv_idx[ipos] = (uint32_t)gi;
-          a.inv_bc[ipos] = bc_r[k];
-          a.inv_nmask[ipos] = nmask_r[k];
-          a.inv_qual[ipos] = bcq_r[k];
+          a.inv_bc[ipos] = pk[k].bc;
+          a.inv_nmask[ipos] = pk[k].nmask;
+          a.inv_qual[ipos] = pk[k].bcq;
           ipos++;
         }
       }

@@ -55,7 +55,7 @@ __global__ void radix_scan_hist_kernel(unsigned long long* hist) {
 
 // ---- one onesweep pass ----
 // desc[tile * RADIX + digit]: {status:2 | count:62} chained-scan descriptors of this pass.
-__global__ void __launch_bounds__(SORT_THREADS) radix_onesweep_kernel(const unsigned long long* __restrict__ in,
+__global__ void __launch_bounds__(SORT_THREADS, 2) radix_onesweep_kernel(const unsigned long long* __restrict__ in,
                                                                       unsigned long long* __restrict__ out, uint64_t n,
                                                                       int shift,
                                                                       const unsigned long long* __restrict__ bin_base,
@@ -86,21 +86,27 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_onesweep_kernel(const unsi
     int idx = warp_first + k * 32 + lane;
     key[k] = idx < cnt ? in[tile_first + idx] : ~0ull;
   }
-  // rank each key among the keys of the same digit that precede it in this warp (match_any + popc)
+  // rank each key among the keys of the same digit that precede it in this warp: the match masks of all
+  // items are computed first (independent), then the lowest peer lane claims the warp-private counter
+  // with one shared-memory atomic per (item, digit) and hands the old value to its peers by shuffle.
   uint32_t* my_hist = s_warp_hist + warp * RADIX;
+  uint32_t peers[SORT_ITEMS];
+#pragma unroll
+  for (int k = 0; k < SORT_ITEMS; k++) {
+    int idx = warp_first + k * 32 + lane;
+    uint32_t digit = idx < cnt ? (uint32_t)((key[k] >> shift) & (RADIX - 1)) : (uint32_t)RADIX;
+    peers[k] = __match_any_sync(0xFFFFFFFFu, digit);
+  }
 #pragma unroll
   for (int k = 0; k < SORT_ITEMS; k++) {
     int idx = warp_first + k * 32 + lane;
     bool valid = idx < cnt;
-    uint32_t digit = valid ? (uint32_t)((key[k] >> shift) & (RADIX - 1)) : (uint32_t)RADIX;
-    uint32_t peers = __match_any_sync(0xFFFFFFFFu, digit);
-    uint32_t before = __popc(peers & ((1u << lane) - 1u));
+    uint32_t digit = (uint32_t)((key[k] >> shift) & (RADIX - 1));
+    int leader = __ffs(peers[k]) - 1;
     uint32_t base = 0;
-    if (valid) base = my_hist[digit];
-    __syncwarp();
-    if (valid && before == 0) my_hist[digit] = base + __popc(peers);
-    __syncwarp();
-    rank_in_warp[k] = base + before;
+    if (valid && lane == leader) base = atomicAdd(&my_hist[digit], (uint32_t)__popc(peers[k]));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    rank_in_warp[k] = base + __popc(peers[k] & ((1u << lane) - 1u));
   }
   __syncthreads();
   // per digit: exclusive scan over the warps, tile total
