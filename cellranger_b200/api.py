@@ -368,6 +368,14 @@ class GemWell:
         check(self.L.crgpu_valid_counts_dev(self._ctx, library, C.byref(p), C.byref(n)))
         return p.value, int(n.value)
 
+    def corrected_dev(self, library: int):
+        p, n = C.c_void_p(), C.c_uint64()
+        check(self.L.crgpu_corrected_dev(self._ctx, library, C.byref(p), C.byref(n)))
+        return p.value, int(n.value)
+
+    def valid_counts_refresh(self):
+        check(self.L.crgpu_valid_counts_refresh(self._ctx), "crgpu_valid_counts_refresh")
+
     def fb_counts_dev(self):
         p, n = C.c_void_p(), C.c_int32()
         check(self.L.crgpu_fb_counts_dev(self._ctx, C.byref(p), C.byref(n)))

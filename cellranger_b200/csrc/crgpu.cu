@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -1029,6 +1030,24 @@ int crgpu_valid_counts_dev(crgpu_ctx* c, int lib, uint32_t** out, uint64_t* n) {
   return CRGPU_OK;
 }
 
+int crgpu_corrected_dev(crgpu_ctx* c, int lib, uint32_t** out, uint64_t* n) {
+  if (!c || lib < 0 || lib >= (int)c->libs.size()) return fail(CRGPU_E_INVALID, "bad argument");
+  if (out) *out = c->libs[lib]->corrected.as<uint32_t>();
+  if (n) *n = c->content.size();
+  return CRGPU_OK;
+}
+
+int crgpu_valid_counts_refresh(crgpu_ctx* c) {
+  if (!c) return fail(CRGPU_E_INVALID, "ctx is NULL");
+  CU(cudaSetDevice(c->device));
+  for (auto* l : c->libs) {
+    c->launches += launch_valid_counts(l->prior.as<uint32_t>(), l->corrected.as<uint32_t>(), l->valid.as<uint32_t>(),
+                                       c->content.size(), c->stream);
+    CHECK_KERNEL();
+  }
+  return CRGPU_OK;
+}
+
 int crgpu_set_owned_range(crgpu_ctx* c, uint32_t lo, uint32_t hi) {
   if (!c) return fail(CRGPU_E_INVALID, "ctx is NULL");
   c->own_lo = lo;
@@ -1082,6 +1101,7 @@ int crgpu_count(crgpu_ctx* c) {
   for (size_t l = 0; l < c->libs.size(); l++)
     if (c->libs[l]->def.umi_correction) b.umi_correction_mask |= 1u << l;
   b.filter_umis = c->filter_umis;
+  b.verify = getenv("CRGPU_VERIFY") != nullptr;
   b.dkeys = c->dkeys.as<unsigned long long>();
   b.c0 = c->c0.as<uint32_t>();
   b.best = c->best.as<uint32_t>();
@@ -1150,6 +1170,8 @@ int crgpu_count(crgpu_ctx* c) {
   c->stats[CRGPU_STAT_UMI_CORRECTED_READS] = m ? hs[5] : 0;
   c->stats[CRGPU_STAT_LOW_SUPPORT_READS] = m ? hs[6] : 0;
   c->stats[CRGPU_STAT_MOLECULES] = c->n_mol;
+  c->stats[CRGPU_STAT_SORT_VIOLATIONS] = m ? hs[10] : 0;
+  c->stats[CRGPU_STAT_RLE_VIOLATIONS] = m ? hs[11] : 0;
   c->stats[CRGPU_STAT_NNZ] = c->nnz;
   c->stats[CRGPU_STAT_BARCODES] = c->n_barcodes;
   c->stage = 3;

@@ -565,6 +565,22 @@ __global__ void low_reads_kernel(const uint32_t* __restrict__ c0, const uint32_t
   if ((threadIdx.x & 31) == 0 && s) atomicAdd(scalars + 6, s);
 }
 
+// debug verification (CRGPU_VERIFY=1): order violations in a key array; strict = equal neighbours count too
+__global__ void order_violations_kernel(const unsigned long long* __restrict__ a, uint64_t n, int strict,
+                                        unsigned long long* out) {
+  unsigned long long bad = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x + 1; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    bad += strict ? (a[i] <= a[i - 1]) : (a[i] < a[i - 1]);
+  for (int d = 16; d > 0; d >>= 1) bad += __shfl_xor_sync(0xFFFFFFFFu, bad, d);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(out, bad);
+}
+int launch_order_violations(const unsigned long long* a, uint64_t n, int strict, unsigned long long* out,
+                            cudaStream_t st) {
+  if (n < 2) return 0;
+  order_violations_kernel<<<grid_for(n), 256, 0, st>>>(a, n, strict, out);
+  return 1;
+}
+
 // Work buffers reused across phases:
 //   key2 / key2_alt : sort scratch for the (rank, lib, umi, feature) grouping, later molecule keys
 int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
@@ -581,6 +597,10 @@ int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
   if (m == 0) return launches;
   run_lengths_kernel<<<grid_for(m), 256, 0, st>>>(b.best, m, b.n_keys, b.c0);
   launches++;
+  if (b.verify) {
+    launches += launch_order_violations(b.sorted, b.n_keys, 0, b.scalars + 10, st);
+    launches += launch_order_violations(b.dkeys, m, 1, b.scalars + 11, st);
+  }
   // 2. UMI correction targets + incoming counts
   cudaMemsetAsync(b.inc, 0, m * 8, st);
   cudaMemsetAsync(b.low, 0, m, st);

@@ -26,6 +26,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -185,7 +188,8 @@ __global__ void __launch_bounds__(THREADS) pass1_staged_kernel(const Pass1Args a
   constexpr int NWARPS = THREADS / 32;
   static_assert(SEQ_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t mbar[STAGES];
+  __shared__ __align__(8) uint64_t mbar[STAGES];       // "full": bulk copies of a stage have landed
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];  // "empty": every warp has read the stage
   __shared__ uint32_t warp_tot[2][NWARPS];
   __shared__ unsigned long long base_bcast[2];
 
@@ -196,7 +200,10 @@ __global__ void __launch_bounds__(THREADS) pass1_staged_kernel(const Pass1Args a
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < STAGES; s++) mbar_init(&mbar[s], 1);
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&mbar[s], 1);
+      mbar_init(&empty_bar[s], NWARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -270,10 +277,19 @@ __global__ void __launch_bounds__(THREADS) pass1_staged_kernel(const Pass1Args a
         feat[k] = NO_FEATURE;
       }
     }
-    __syncthreads();  // stage s is free again: refill it right away, two tiles ahead
+    // Stage s is free once every warp has read its records: each warp arrives on the stage's "empty"
+    // mbarrier, thread 0 waits for that phase and only then lets the bulk copies (async proxy) overwrite
+    // the stage. A plain bar.sync is NOT enough here: it does not order the other warps' generic-proxy
+    // reads before an async-proxy write issued right behind it (seen on B200 as stale feature words).
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
     if (tid == 0) {
       uint64_t next = tile + (uint64_t)STAGES * gridDim.x;
-      if (next < n_tiles) issue(next, s);
+      if (next < n_tiles) {
+        mbar_wait(&empty_bar[s], parity);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(next, s);
+      }
     }
 
     // ---- phase 2: exact whitelist lookups, all loads of the RPT reads in flight together ----

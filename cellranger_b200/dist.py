@@ -9,8 +9,8 @@ stages/align_and_count.rs:519-524); priors are summed over every chunk in the MA
   2. all-reduce(sum) of the per-library prior histograms          (priors are global)
      + the exact feature-barcode counts
   3. every rank corrects its own invalid reads                    (local)
-  4. all-reduce(sum) of the valid-barcode counts → barcode index, and → owner ranges of
-     contiguous content ranks balanced by read count
+  4. all-reduce(sum) of the corrected-read counts; prior + corrected = the valid-barcode counts
+     (barcode index) → owner ranges of contiguous content ranks balanced by read count
   5. one all-to-all of the packed 64-bit keys to the rank that owns their barcode
   6. dedup + counting, shard-local; the matrix is the concatenation of the ranks' column blocks
 
@@ -63,7 +63,13 @@ class TorchEngine:
         self.gw.barcode_correction()
         self.gw.sync()
 
+    def corrected_tensors(self) -> List[torch.Tensor]:
+        return [dev_tensor(*self.gw.corrected_dev(l), "<i4", self.device) for l in range(self.n_libs)]
+
     def valid_count_tensors(self) -> List[torch.Tensor]:
+        """valid = prior + corrected, recomputed from the (now global) vectors."""
+        self.gw.valid_counts_refresh()
+        self.gw.sync()
         return [dev_tensor(*self.gw.valid_counts_dev(l), "<i4", self.device) for l in range(self.n_libs)]
 
     def keys_partition(self, bounds: np.ndarray):
@@ -126,10 +132,10 @@ class ShardedGemWell:
         self._allreduce(e.fb_counts_tensor())
         e.sync()
         e.barcode_correction()
-        valid = e.valid_count_tensors()
-        for t in valid:
+        for t in e.corrected_tensors():
             self._allreduce(t)
         e.sync()
+        valid = e.valid_count_tensors()  # identical on every rank
         total = valid[0].to(torch.int64)
         for t in valid[1:]:
             total = total + t.to(torch.int64)

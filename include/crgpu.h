@@ -151,6 +151,10 @@ int crgpu_keys_set(crgpu_ctx* ctx, const unsigned long long* dev_keys, uint64_t 
 /* per-library valid-barcode counts (raw valid + corrected) as a device vector to all-reduce:
  * corrected_barcode_counts of BARCODE_CORRECTION join (barcode_correction.rs:401-407) */
 int crgpu_valid_counts_dev(crgpu_ctx* ctx, int library, uint32_t** out_dev_u32, uint64_t* out_n);
+/* per-library counts of the reads corrected by this context (device vector, to all-reduce), and the
+ * recomputation valid = prior + corrected after both have been made global */
+int crgpu_corrected_dev(crgpu_ctx* ctx, int library, uint32_t** out_dev_u32, uint64_t* out_n);
+int crgpu_valid_counts_refresh(crgpu_ctx* ctx);
 /* restrict the matrix columns this context owns to content ranks [lo, hi) */
 int crgpu_set_owned_range(crgpu_ctx* ctx, uint32_t lo, uint32_t hi);
 
@@ -183,6 +187,8 @@ enum {
   CRGPU_STAT_KERNEL_LAUNCHES = 11, /* kernels of this library launched so far */
   CRGPU_STAT_UMI_CORRECTED_READS = 12,
   CRGPU_STAT_LOW_SUPPORT_READS = 13,
+  CRGPU_STAT_SORT_VIOLATIONS = 14, /* with CRGPU_VERIFY=1 in the environment: order violations found after */
+  CRGPU_STAT_RLE_VIOLATIONS = 15,  /* the radix sort and after the run-length encoding (must be 0) */
   CRGPU_STAT_COUNT = 16
 };
 int crgpu_stats(crgpu_ctx* ctx, uint64_t out[CRGPU_STAT_COUNT]);
