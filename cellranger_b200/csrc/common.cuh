@@ -38,7 +38,7 @@ struct DevWhitelist {
   int rot[CRGPU_MAX_ORD];
   uint32_t resp[CRGPU_MAX_ORD];  // bit `pos` set: this ordering answers for mutations at base `pos`
   // exact membership: a finer bucket table over ordering 0 (about 1.5 entries per bucket): start index of
-  // the bucket q >> exact_shift. keys[0] carries two 0xFFFFFFFF sentinels past its end.
+  // the bucket q >> exact_shift. keys[0] carries four 0xFFFFFFFF sentinels past its end.
   const uint32_t* exact_offs;
   int exact_shift;
 };
@@ -60,7 +60,7 @@ __device__ __forceinline__ uint32_t rotr_bits(uint32_t q, int r, int nbits) {
 // Split in two so that callers can issue the loads of several independent lookups before resolving any:
 // wl_find_begin() loads the bucket start, wl_find_probe() the first two entries, wl_find_end() decides.
 struct WlProbe {
-  uint32_t start, e0, e1;
+  uint32_t start, e0, e1, e2, e3;
 };
 __device__ __forceinline__ uint32_t wl_find_begin(const DevWhitelist& wl, uint32_t q) {
   uint32_t b = wl.exact_shift >= 32 ? 0u : (q >> wl.exact_shift);
@@ -69,8 +69,11 @@ __device__ __forceinline__ uint32_t wl_find_begin(const DevWhitelist& wl, uint32
 __device__ __forceinline__ WlProbe wl_find_probe(const DevWhitelist& wl, uint32_t start) {
   WlProbe p;
   p.start = start;
-  p.e0 = __ldg(wl.keys[0] + start);
-  p.e1 = __ldg(wl.keys[0] + start + 1);
+  const uint32_t* __restrict__ k = wl.keys[0] + start;  // four sentinels follow the last key
+  p.e0 = __ldg(k);
+  p.e1 = __ldg(k + 1);
+  p.e2 = __ldg(k + 2);
+  p.e3 = __ldg(k + 3);
   return p;
 }
 __device__ __forceinline__ int wl_find_end(const DevWhitelist& wl, const WlProbe& p, uint32_t q) {
@@ -81,9 +84,15 @@ __device__ __forceinline__ int wl_find_end(const DevWhitelist& wl, const WlProbe
   } else if (p.e1 >= q) {
     if (p.e1 != q) return -1;
     idx = p.start + 1;
+  } else if (p.e2 >= q) {
+    if (p.e2 != q) return -1;
+    idx = p.start + 2;
+  } else if (p.e3 >= q) {
+    if (p.e3 != q) return -1;
+    idx = p.start + 3;
   } else {
     const uint32_t* __restrict__ keys = wl.keys[0];
-    idx = p.start + 2;
+    idx = p.start + 4;
     while (true) {  // the keys are sorted and end with 0xFFFFFFFF sentinels
       uint32_t e = __ldg(keys + idx);
       if (e >= q) {

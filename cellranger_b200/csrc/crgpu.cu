@@ -449,7 +449,7 @@ int crgpu_whitelist_add(crgpu_ctx* c, const uint8_t* seqs, uint64_t n, int L, co
     std::vector<std::pair<uint32_t, uint32_t>> rk(W);
     for (uint32_t i = 0; i < W; i++) rk[i] = {rotr_host(kv[i].first, r, nbits), rank[i]};
     if (r != 0) std::sort(rk.begin(), rk.end());
-    std::vector<uint32_t> keys(W + 2, 0xFFFFFFFFu), vals(W), offs(n_buckets + 1, 0);  // two sentinels
+    std::vector<uint32_t> keys(W + 4, 0xFFFFFFFFu), vals(W), offs(n_buckets + 1, 0);  // four sentinels
     for (uint32_t i = 0; i < W; i++) {
       keys[i] = rk[i].first;
       vals[i] = rk[i].second;
@@ -459,15 +459,15 @@ int crgpu_whitelist_add(crgpu_ctx* c, const uint8_t* seqs, uint64_t n, int L, co
     for (uint64_t b = 0; b < n_buckets; b++) offs[b + 1] += offs[b];
     DevBuf dk, dv, dof;
     int rc;
-    if ((rc = dk.ensure((size_t)(W + 2) * 4))) return rc;
+    if ((rc = dk.ensure((size_t)(W + 4) * 4))) return rc;
     if ((rc = dof.ensure((n_buckets + 1) * 4))) return rc;
-    CU(cudaMemcpy(dk.p, keys.data(), (size_t)(W + 2) * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dk.p, keys.data(), (size_t)(W + 4) * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dof.p, offs.data(), (n_buckets + 1) * 4, cudaMemcpyHostToDevice));
     if (o == 0) {
       // finer table for exact membership: about 1.5 entries per bucket
       int pe = 0;
-      while (pe < nbits && ((uint64_t)W >> pe) > 1) pe++;
-      if (pe > 0) pe -= 1;
+      while (pe < nbits && (1ull << pe) < (uint64_t)W) pe++;  // ceil(log2 W)
+      if (pe > 0) pe -= 1;                                     // 1..2 entries per bucket
       if (pe > 26) pe = 26;
       const int eshift = nbits - pe;
       const uint64_t nb = 1ull << pe;

@@ -200,34 +200,36 @@ __device__ __noinline__ void correct_one_global(const unsigned long long* __rest
 
 // Tiled kernel: a block answers CU_TILE consecutive keys out of a shared-memory window that also holds
 // CU_HALO keys on each side, so every segment of up to CU_HALO keys that touches the tile is complete in
-// shared memory. Segments of one key need nothing, short ones are compared pairwise, longer ones probe a
-// shared-memory hash set with the 3L mutants; only segments longer than the halo go to global memory.
+// shared memory. Segments of one key need nothing; short ones are compared pairwise by the owning thread;
+// the keys of longer ones are first compacted into a work list and then answered densely (no divergence)
+// by probing a shared-memory hash set with the 3L mutants; only segments longer than the halo go to
+// global memory.
 constexpr int CU_THREADS = 512;
-constexpr int CU_TILE = 2048;
-constexpr int CU_HALO = 1024;
-constexpr int CU_WIN = CU_TILE + 2 * CU_HALO;
-constexpr int CU_SLOTS = 2 * CU_WIN;
-constexpr int CU_SMALL = 12;
-constexpr uint32_t CU_EMPTY = 0xFFFFFFFFu;
+constexpr int CU_TILE = 3072;
+constexpr int CU_HALO = 1536;
+constexpr int CU_WIN = CU_TILE + 2 * CU_HALO;  // 6144
+constexpr int CU_SLOTS = 16384;
+constexpr int CU_SMALL = 40;
+constexpr unsigned short CU_EMPTY = 0xFFFFu;
 
 __device__ __forceinline__ uint32_t cu_hash(unsigned long long k) {
-  return (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> 51) & (CU_SLOTS - 1);
+  return (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> 50) & (CU_SLOTS - 1);
 }
 
-__global__ void __launch_bounds__(CU_THREADS) correct_umis_kernel(const unsigned long long* __restrict__ dkeys,
-                                                                  const uint32_t* __restrict__ c0, uint64_t m,
-                                                                  KeyLayout kl, uint32_t corr_mask,
-                                                                  uint32_t* __restrict__ best,
-                                                                  unsigned long long* __restrict__ inc,
-                                                                  unsigned long long* __restrict__ scalars) {
+__global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsigned long long* __restrict__ dkeys,
+                                                                     const uint32_t* __restrict__ c0, uint64_t m,
+                                                                     KeyLayout kl, uint32_t corr_mask,
+                                                                     uint32_t* __restrict__ best,
+                                                                     unsigned long long* __restrict__ inc,
+                                                                     unsigned long long* __restrict__ scalars) {
   extern __shared__ __align__(16) unsigned char cu_smem[];
-  unsigned long long* w_key = reinterpret_cast<unsigned long long*>(cu_smem);          // CU_WIN
-  uint32_t* w_c0 = reinterpret_cast<uint32_t*>(w_key + CU_WIN);                          // CU_WIN
-  uint32_t* table = w_c0 + CU_WIN;                                                       // CU_SLOTS
-  unsigned short* seg_lo = reinterpret_cast<unsigned short*>(table + CU_SLOTS);          // CU_WIN
-  unsigned short* seg_hi = seg_lo + CU_WIN;                                              // CU_WIN (exclusive end)
+  unsigned long long* w_key = reinterpret_cast<unsigned long long*>(cu_smem);      // CU_WIN
+  unsigned short* table = reinterpret_cast<unsigned short*>(w_key + CU_WIN);        // CU_SLOTS
+  unsigned short* seg_lo = table + CU_SLOTS;                                        // CU_WIN
+  unsigned short* seg_hi = seg_lo + CU_WIN;                                         // CU_WIN (exclusive end, at head)
+  unsigned short* work = seg_hi + CU_WIN;                                           // CU_TILE: hash-path queries
   __shared__ unsigned long long s_corr, s_corr_reads;
-  __shared__ int s_need_hash;
+  __shared__ uint32_t s_nwork;
 
   const int ub = kl.umi_bits;
   const unsigned long long umask = (1ull << ub) - 1ull;
@@ -242,13 +244,13 @@ __global__ void __launch_bounds__(CU_THREADS) correct_umis_kernel(const unsigned
   if (tid == 0) {
     s_corr = 0;
     s_corr_reads = 0;
-    s_need_hash = 0;
+    s_nwork = 0;
   }
-  for (int i = tid; i < wn; i += CU_THREADS) {
-    w_key[i] = dkeys[w_lo + i];
-    w_c0[i] = c0[w_lo + i];
+  for (int i = tid; i < wn; i += CU_THREADS) w_key[i] = dkeys[w_lo + i];
+  {
+    uint32_t* t32 = reinterpret_cast<uint32_t*>(table);
+    for (int i = tid; i < CU_SLOTS / 2; i += CU_THREADS) t32[i] = 0xFFFFFFFFu;
   }
-  for (int i = tid; i < CU_SLOTS; i += CU_THREADS) table[i] = CU_EMPTY;
   __syncthreads();
   // is the first / last segment of the window cut by the window edge?
   const bool cut_l = w_lo > 0 && (dkeys[w_lo - 1] >> ub) == (w_key[0] >> ub);
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(CU_THREADS) correct_umis_kernel(const unsigned
 
   // segment bounds of every window element: each thread owns a contiguous chunk, chunks are stitched
   // through shared memory (first pass: local runs; second pass: extend across chunk borders)
-  constexpr int PER = CU_WIN / CU_THREADS;  // 8
+  constexpr int PER = CU_WIN / CU_THREADS;  // 12
   {
     const int c_lo = tid * PER;
     int run_start = c_lo;
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(CU_THREADS) correct_umis_kernel(const unsigned
     if (c_lo < wn && c_lo > 0 && (w_key[c_lo] >> ub) == (w_key[c_lo - 1] >> ub)) {
       const unsigned long long sg = w_key[c_lo] >> ub;
       int s = c_lo - 1;
-      // jump chunk by chunk: seg_lo of the previous element already points to its local run start
+      // jump chunk by chunk: seg_lo of the previous element points to its run start (local or extended)
       while (true) {
         s = seg_lo[s];
         if (s == 0 || (s % PER) != 0 || (w_key[s - 1] >> ub) != sg) break;
@@ -288,16 +290,12 @@ __global__ void __launch_bounds__(CU_THREADS) correct_umis_kernel(const unsigned
     }
   }
   __syncthreads();
-  // exclusive end: one pass from the right using seg_lo of the successor
   {
     const int c_lo = tid * PER;
     for (int k = 0; k < PER; k++) {
       int i = c_lo + k;
       if (i >= wn) break;
-      if (i + 1 >= wn || seg_lo[i + 1] != seg_lo[i]) {
-        // i is the last element of its segment: publish the end to the whole segment lazily via the head
-        seg_hi[seg_lo[i]] = (unsigned short)(i + 1);
-      }
+      if (i + 1 >= wn || seg_lo[i + 1] != seg_lo[i]) seg_hi[seg_lo[i]] = (unsigned short)(i + 1);
     }
   }
   __syncthreads();
@@ -306,61 +304,116 @@ __global__ void __launch_bounds__(CU_THREADS) correct_umis_kernel(const unsigned
     int s = seg_lo[i];
     int n = (int)seg_hi[s] - s;
     if (n > CU_SMALL) {
-      s_need_hash = 1;
       uint32_t h = cu_hash(w_key[i]);
-      while (atomicCAS(&table[h], CU_EMPTY, (uint32_t)i) != CU_EMPTY) h = (h + 1) & (CU_SLOTS - 1);
+      while (atomicCAS(&table[h], CU_EMPTY, (unsigned short)i) != CU_EMPTY) h = (h + 1) & (CU_SLOTS - 1);
     }
   }
-  __syncthreads();
 
   unsigned long long n_corr = 0, n_corr_reads = 0;
   const int q_off = (int)(q_lo - w_lo);
   const int qn = (int)(q_hi - q_lo);
+  auto finish = [&](int i, const BestPick& bp, uint32_t own_c0) {
+    const uint64_t j = w_lo + i;
+    best[j] = bp.idx;
+    if (bp.idx != (uint32_t)j) {
+      atomicAdd(inc + bp.idx, (1ull << 40) | (unsigned long long)own_c0);
+      n_corr++;
+      n_corr_reads += own_c0;
+    }
+  };
+  // pass A: singletons, short segments (pairwise), cut segments (global); longer ones go to the work list
   for (int qi = tid; qi < qn; qi += CU_THREADS) {
     const int i = q_off + qi;
     const uint64_t j = w_lo + i;
     const unsigned long long key = w_key[i];
     const uint32_t lib = (uint32_t)(key >> kl.lib_shift) & lmask;
-    BestPick bp{w_c0[i], key & umask, (uint32_t)j};
-    if ((corr_mask >> lib) & 1u) {
-      const int s = seg_lo[i];
-      const int e = seg_hi[s];
-      const int n = e - s;
-      if ((s == 0 && cut_l) || (e == wn && cut_r)) {
-        correct_one_global(dkeys, c0, m, ub, j, &bp);
-      } else if (n > 1) {
-        if (n <= CU_SMALL) {
-          for (int k = s; k < e; k++) {
-            unsigned long long o = w_key[k];
-            if (hamming1_2bit(o, key)) bp.consider(w_c0[k], o & umask, (uint32_t)(w_lo + k));
-          }
-        } else {
-          for (int sh = 0; sh < ub; sh += 2) {
+    const int s = seg_lo[i];
+    const int e = seg_hi[s];
+    const int n = e - s;
+    if (!((corr_mask >> lib) & 1u) || n == 1) {
+      best[j] = (uint32_t)j;
+      continue;
+    }
+    if ((s == 0 && cut_l) || (e == wn && cut_r)) {
+      const uint32_t own = c0[j];
+      BestPick bp{own, key & umask, (uint32_t)j};
+      correct_one_global(dkeys, c0, m, ub, j, &bp);
+      finish(i, bp, own);
+    } else if (n <= CU_SMALL) {
+      uint32_t hits = 0;  // neighbours are rare: find them first, fetch their counts only then
+      int first_hit = -1;
+      for (int k = s; k < e; k++) {
+        if (hamming1_2bit(w_key[k], key)) {
+          hits++;
+          if (first_hit < 0) first_hit = k;
+        }
+      }
+      if (hits == 0) {
+        best[j] = (uint32_t)j;
+      } else {
+        const uint32_t own = c0[j];
+        BestPick bp{own, key & umask, (uint32_t)j};
+        for (int k = first_hit; k < e; k++) {
+          unsigned long long o = w_key[k];
+          if (hamming1_2bit(o, key)) bp.consider(c0[w_lo + k], o & umask, (uint32_t)(w_lo + k));
+        }
+        finish(i, bp, own);
+      }
+    } else {
+      work[atomicAdd(&s_nwork, 1u)] = (unsigned short)i;
+    }
+  }
+  __syncthreads();
+  // pass B: the work list, one thread per key, every lane busy
+  const int nwork = (int)s_nwork;
+  for (int w = tid; w < nwork; w += CU_THREADS) {
+    const int i = work[w];
+    const uint64_t j = w_lo + i;
+    const unsigned long long key = w_key[i];
+    uint32_t found[4];
+    int nfound = 0;
+    for (int sh = 0; sh < ub; sh += 2) {
 #pragma unroll
-            for (unsigned long long d = 1; d < 4; d++) {
-              const unsigned long long t = key ^ (d << sh);
-              uint32_t h = cu_hash(t);
-              while (true) {
-                uint32_t idx = table[h];
-                if (idx == CU_EMPTY) break;
-                if (w_key[idx] == t) {
-                  bp.consider(w_c0[idx], t & umask, (uint32_t)(w_lo + idx));
-                  break;
-                }
-                h = (h + 1) & (CU_SLOTS - 1);
-              }
-            }
+      for (unsigned long long d = 1; d < 4; d++) {
+        const unsigned long long t = key ^ (d << sh);
+        uint32_t h = cu_hash(t);
+        while (true) {
+          unsigned short idx = table[h];
+          if (idx == CU_EMPTY) break;
+          if (w_key[idx] == t) {
+            if (nfound < 4) found[nfound] = idx;
+            nfound++;
+            break;
           }
+          h = (h + 1) & (CU_SLOTS - 1);
         }
       }
     }
-    best[j] = bp.idx;
-    if (bp.idx != (uint32_t)j) {
-      uint32_t c = w_c0[i];
-      atomicAdd(inc + bp.idx, (1ull << 40) | (unsigned long long)c);
-      n_corr++;
-      n_corr_reads += c;
+    if (nfound == 0) {
+      best[j] = (uint32_t)j;
+      continue;
     }
+    const uint32_t own = c0[j];
+    BestPick bp{own, key & umask, (uint32_t)j};
+    if (nfound <= 4) {
+      for (int f = 0; f < nfound; f++) bp.consider(c0[w_lo + found[f]], w_key[found[f]] & umask, (uint32_t)(w_lo + found[f]));
+    } else {  // more neighbours than the register list holds: walk the mutants again
+      for (int sh = 0; sh < ub; sh += 2)
+        for (unsigned long long d = 1; d < 4; d++) {
+          const unsigned long long t = key ^ (d << sh);
+          uint32_t h = cu_hash(t);
+          while (true) {
+            unsigned short idx = table[h];
+            if (idx == CU_EMPTY) break;
+            if (w_key[idx] == t) {
+              bp.consider(c0[w_lo + idx], t & umask, (uint32_t)(w_lo + idx));
+              break;
+            }
+            h = (h + 1) & (CU_SLOTS - 1);
+          }
+        }
+    }
+    finish(i, bp, own);
   }
   if (n_corr) {
     atomicAdd(&s_corr, n_corr);
@@ -605,7 +658,7 @@ int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
   cudaMemsetAsync(b.inc, 0, m * 8, st);
   cudaMemsetAsync(b.low, 0, m, st);
   {
-    const size_t smem = (size_t)CU_WIN * 8 + (size_t)CU_WIN * 4 + (size_t)CU_SLOTS * 4 + (size_t)CU_WIN * 2 * 2;
+    const size_t smem = (size_t)CU_WIN * 8 + (size_t)CU_SLOTS * 2 + (size_t)CU_WIN * 2 * 2 + (size_t)CU_TILE * 2;
     static bool attr_set = false;
     if (!attr_set) {
       cudaFuncSetAttribute(correct_umis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

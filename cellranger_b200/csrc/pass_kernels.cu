@@ -6,6 +6,9 @@
 // lib/rust/cr_lib/src/make_shard_metrics.rs:171-188 (priors), lib/rust/umi/src/info.rs:20-74 (UMI
 // validity), lib/rust/barcode/src/corrector.rs:111-171 (posterior),
 // lib/rust/cr_types/src/reference/feature_extraction.rs:34-117,447-471 (feature barcodes).
+#include <algorithm>
+#include <cstdlib>
+
 #include "kernels.h"
 
 __constant__ double c_bc_prob[256];  // probability(q) = pow(10, -(q-33)/10), filled by host libm
@@ -463,35 +466,40 @@ __global__ void __launch_bounds__(256) pass1_generic_kernel(const Pass1Args a) {
   }
 }
 
+template <int R1_LEN, int UMI_LEN, int THREADS, int RPT, int STAGES>
+static int launch_staged(const Pass1Args& a, int n_sms, cudaStream_t st) {
+  constexpr int TILE = THREADS * RPT;
+  auto kern = pass1_staged_kernel<R1_LEN, UMI_LEN, THREADS, RPT, STAGES>;
+  size_t smem = (size_t)STAGES * (2 * (TILE * R1_LEN + 16) + TILE * 4);
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
+  uint64_t tiles = (a.n + TILE - 1) / TILE;
+  int grid = (int)std::min<uint64_t>(tiles, (uint64_t)n_sms * (per_sm > 0 ? per_sm : 1));
+  kern<<<grid, THREADS, smem, st>>>(a);
+  return 1;
+}
+
+template <int R1_LEN, int UMI_LEN>
+static int launch_staged_cfg(const Pass1Args& a, int n_sms, cudaStream_t st) {
+  const int cfg = getenv("CRGPU_P1_CFG") ? atoi(getenv("CRGPU_P1_CFG")) : 0;
+  switch (cfg) {
+    case 1: return launch_staged<R1_LEN, UMI_LEN, 128, 2, 2>(a, n_sms, st);
+    case 2: return launch_staged<R1_LEN, UMI_LEN, 128, 4, 2>(a, n_sms, st);
+    case 3: return launch_staged<R1_LEN, UMI_LEN, 256, 1, 2>(a, n_sms, st);
+    case 4: return launch_staged<R1_LEN, UMI_LEN, 128, 2, 3>(a, n_sms, st);
+    case 5: return launch_staged<R1_LEN, UMI_LEN, 256, 2, 3>(a, n_sms, st);
+    default: return launch_staged<R1_LEN, UMI_LEN, 256, 2, 2>(a, n_sms, st);
+  }
+}
+
 int launch_pass1(const Pass1Args& a, int n_sms, cudaStream_t st) {
   if (a.n == 0) return 0;
   const bool std_layout = a.bc_off == 0 && a.bc_len == 16 && a.umi_off == 16 && a.have_qual &&
                           ((uintptr_t)a.seq % 16 == 0) && ((uintptr_t)a.qual % 16 == 0) &&
                           (a.feature == nullptr || (uintptr_t)a.feature % 16 == 0);
-  constexpr int THREADS = 256, RPT = 2, STAGES = 2;
-  constexpr int TILE = THREADS * RPT;
-  if (std_layout && a.r1_len == 28 && a.umi_len == 12) {
-    auto kern = pass1_staged_kernel<28, 12, THREADS, RPT, STAGES>;
-    size_t smem = (size_t)STAGES * (2 * (TILE * 28 + 16) + TILE * 4);
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
-    uint64_t tiles = (a.n + TILE - 1) / TILE;
-    int grid = (int)std::min<uint64_t>(tiles, (uint64_t)n_sms * (per_sm > 0 ? per_sm : 1));
-    kern<<<grid, THREADS, smem, st>>>(a);
-    return 1;
-  }
-  if (std_layout && a.r1_len == 26 && a.umi_len == 10) {
-    auto kern = pass1_staged_kernel<26, 10, THREADS, RPT, STAGES>;
-    size_t smem = (size_t)STAGES * (2 * (TILE * 26 + 16) + TILE * 4);
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
-    uint64_t tiles = (a.n + TILE - 1) / TILE;
-    int grid = (int)std::min<uint64_t>(tiles, (uint64_t)n_sms * (per_sm > 0 ? per_sm : 1));
-    kern<<<grid, THREADS, smem, st>>>(a);
-    return 1;
-  }
+  if (std_layout && a.r1_len == 28 && a.umi_len == 12) return launch_staged_cfg<28, 12>(a, n_sms, st);
+  if (std_layout && a.r1_len == 26 && a.umi_len == 10) return launch_staged_cfg<26, 10>(a, n_sms, st);
   uint64_t blocks = (a.n + 255) / 256;
   int grid = (int)std::min<uint64_t>(blocks, (uint64_t)n_sms * 8);
   pass1_generic_kernel<<<grid, 256, 0, st>>>(a);

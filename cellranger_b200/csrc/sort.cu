@@ -7,6 +7,7 @@
 // chained (decoupled look-back) scan, and the keys are scattered through shared memory so every digit
 // bin is written as one contiguous run.
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.h"
 
@@ -14,10 +15,8 @@ namespace {
 
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
-constexpr int SORT_THREADS = 512;
-constexpr int SORT_ITEMS = 12;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 6144 keys = 48 KB
 constexpr int MAX_PASSES = 8;
+constexpr int MIN_TILE = 2048;  // smallest tile of any configuration (sizes the descriptor scratch)
 
 // ---- upfront histograms: hist[pass][digit] over all keys ----
 __global__ void __launch_bounds__(512) radix_hist_kernel(const unsigned long long* __restrict__ keys, uint64_t n,
@@ -55,18 +54,21 @@ __global__ void radix_scan_hist_kernel(unsigned long long* hist) {
 
 // ---- one onesweep pass ----
 // desc[tile * RADIX + digit]: {status:2 | count:62} chained-scan descriptors of this pass.
-__global__ void __launch_bounds__(SORT_THREADS, 2) radix_onesweep_kernel(const unsigned long long* __restrict__ in,
+template <int SORT_THREADS, int SORT_ITEMS, int MIN_BLOCKS, int RANK_ATOMIC>
+__global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) radix_onesweep_kernel(const unsigned long long* __restrict__ in,
                                                                       unsigned long long* __restrict__ out, uint64_t n,
                                                                       int shift,
                                                                       const unsigned long long* __restrict__ bin_base,
                                                                       unsigned long long* __restrict__ desc,
                                                                       uint32_t* __restrict__ ticket) {
   constexpr int WARPS = SORT_THREADS / 32;
+  constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_raw);         // SORT_TILE keys
   uint32_t* s_warp_hist = reinterpret_cast<uint32_t*>(smem_raw + SORT_TILE * 8);         // WARPS * RADIX
   uint32_t* s_bin_off = s_warp_hist + WARPS * RADIX;                                     // RADIX: tile-local exclusive
   unsigned long long* s_bin_glob = reinterpret_cast<unsigned long long*>(s_bin_off + RADIX);  // RADIX
+  uint32_t* s_bin_cnt = reinterpret_cast<uint32_t*>(s_bin_glob + RADIX);                       // RADIX: tile counts
   __shared__ uint32_t tile_s;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -102,11 +104,21 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) radix_onesweep_kernel(const u
     int idx = warp_first + k * 32 + lane;
     bool valid = idx < cnt;
     uint32_t digit = (uint32_t)((key[k] >> shift) & (RADIX - 1));
-    int leader = __ffs(peers[k]) - 1;
-    uint32_t base = 0;
-    if (valid && lane == leader) base = atomicAdd(&my_hist[digit], (uint32_t)__popc(peers[k]));
-    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    rank_in_warp[k] = base + __popc(peers[k] & ((1u << lane) - 1u));
+    uint32_t before = __popc(peers[k] & ((1u << lane) - 1u));
+    if constexpr (RANK_ATOMIC) {
+      int leader = __ffs(peers[k]) - 1;
+      uint32_t base = 0;
+      if (valid && lane == leader) base = atomicAdd(&my_hist[digit], (uint32_t)__popc(peers[k]));
+      base = __shfl_sync(0xFFFFFFFFu, base, leader);
+      rank_in_warp[k] = base + before;
+    } else {
+      uint32_t base = 0;
+      if (valid) base = my_hist[digit];
+      __syncwarp();
+      if (valid && before == 0) my_hist[digit] = base + __popc(peers[k]);
+      __syncwarp();
+      rank_in_warp[k] = base + before;
+    }
   }
   __syncthreads();
   // per digit: exclusive scan over the warps, tile total
@@ -121,30 +133,15 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) radix_onesweep_kernel(const u
     s_bin_off[d] = run;  // tile count of digit d (turned into an exclusive offset below)
   }
   __syncthreads();
-  // chained scan over tiles, one descriptor per digit: threads 0..255 each own a digit
-  if (tid < RADIX) {
-    const int d = tid;
+  // Publish this tile's digit counts right away (AGGREGATE), so that successors can already add them up
+  // while this block is still scattering; the walk back over the predecessors comes as late as possible.
+  for (int d = tid; d < RADIX; d += SORT_THREADS) {
     const unsigned long long mine = s_bin_off[d];
-    unsigned long long* my_desc = desc + (size_t)tile * RADIX + d;
-    unsigned long long excl = 0;
-    if (tile == 0) {
-      lb_store(my_desc, LB_PREFIX, mine);
-    } else {
-      lb_store(my_desc, LB_AGGREGATE, mine);
-      for (int64_t t = (int64_t)tile - 1; t >= 0; t--) {
-        unsigned long long w;
-        do {
-          w = lb_load(desc + (size_t)t * RADIX + d);
-        } while ((w >> 62) == LB_INVALID);
-        excl += w & 0x3FFFFFFFFFFFFFFFull;
-        if ((w >> 62) == LB_PREFIX) break;
-      }
-      lb_store(my_desc, LB_PREFIX, excl + mine);
-    }
-    s_bin_glob[d] = bin_base[d] + excl;
+    s_bin_cnt[d] = (uint32_t)mine;
+    lb_store(desc + (size_t)tile * RADIX + d, tile == 0 ? LB_PREFIX : LB_AGGREGATE, mine);
   }
   __syncthreads();
-  // tile-local exclusive offsets of the digits (serial over 256 in one warp via shuffles)
+  // tile-local exclusive offsets of the digits (one warp, shuffles)
   if (warp == 0) {
     uint32_t carry = 0;
 #pragma unroll
@@ -171,6 +168,22 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) radix_onesweep_kernel(const u
       s_keys[p] = key[k];
     }
   }
+  // chained scan over tiles (decoupled look-back), one descriptor per digit
+  for (int d = tid; d < RADIX; d += SORT_THREADS) {
+    unsigned long long excl = 0;
+    if (tile != 0) {
+      for (int64_t t = (int64_t)tile - 1; t >= 0; t--) {
+        unsigned long long w;
+        do {
+          w = lb_load(desc + (size_t)t * RADIX + d);
+        } while ((w >> 62) == LB_INVALID);
+        excl += w & 0x3FFFFFFFFFFFFFFFull;
+        if ((w >> 62) == LB_PREFIX) break;
+      }
+      lb_store(desc + (size_t)tile * RADIX + d, LB_PREFIX, excl + (unsigned long long)s_bin_cnt[d]);
+    }
+    s_bin_glob[d] = bin_base[d] + excl;
+  }
   __syncthreads();
   // write out: consecutive threads write consecutive keys of a digit run
   for (int p = tid; p < cnt; p += SORT_THREADS) {
@@ -183,7 +196,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) radix_onesweep_kernel(const u
 }  // namespace
 
 size_t sort_temp_bytes(uint64_t n) {
-  uint64_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
+  uint64_t tiles = (n + MIN_TILE - 1) / MIN_TILE;
   // histograms + per-pass descriptors + tickets
   return (size_t)MAX_PASSES * RADIX * 8 + (size_t)(tiles + 1) * RADIX * 8 + 256;
 }
@@ -209,36 +222,53 @@ int sort_histograms(const unsigned long long* keys, uint64_t n, int end_bit, voi
   return 2;
 }
 
-// step 2: the onesweep passes; result in *out
-int sort_passes(unsigned long long* keys, unsigned long long* alt, uint64_t n, int end_bit, void* temp,
-                unsigned long long** out, cudaStream_t st) {
-  *out = keys;
-  if (n <= 1) return 0;
-  const int n_passes = plan_passes(end_bit);
-  uint64_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
+template <int THREADS, int ITEMS, int MIN_BLOCKS, int RANK_ATOMIC>
+static int run_passes(unsigned long long* keys, unsigned long long* alt, uint64_t n, int n_passes, void* temp,
+                      unsigned long long** out, cudaStream_t st) {
+  constexpr int TILE = THREADS * ITEMS;
+  uint64_t tiles = (n + TILE - 1) / TILE;
+  uint64_t max_tiles = (n + MIN_TILE - 1) / MIN_TILE;
   unsigned char* t = static_cast<unsigned char*>(temp);
   unsigned long long* hist = reinterpret_cast<unsigned long long*>(t);
   unsigned long long* desc = reinterpret_cast<unsigned long long*>(t + (size_t)MAX_PASSES * RADIX * 8);
-  uint32_t* ticket = reinterpret_cast<uint32_t*>(t + (size_t)MAX_PASSES * RADIX * 8 + (size_t)(tiles + 1) * RADIX * 8);
-  const size_t smem = (size_t)SORT_TILE * 8 + (size_t)(SORT_THREADS / 32) * RADIX * 4 + RADIX * 4 + RADIX * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(radix_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
+  uint32_t* ticket = reinterpret_cast<uint32_t*>(t + (size_t)MAX_PASSES * RADIX * 8 + (size_t)(max_tiles + 1) * RADIX * 8);
+  const size_t smem = (size_t)TILE * 8 + (size_t)(THREADS / 32) * RADIX * 4 + RADIX * 4 + RADIX * 8 + RADIX * 4;
+  auto kern = radix_onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS, RANK_ATOMIC>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int launches = 0;
   unsigned long long* src = keys;
   unsigned long long* dst = alt;
   for (int p = 0; p < n_passes; p++) {
     cudaMemsetAsync(desc, 0, (size_t)tiles * RADIX * 8, st);
     cudaMemsetAsync(ticket, 0, 4, st);
-    radix_onesweep_kernel<<<(unsigned)tiles, SORT_THREADS, smem, st>>>(src, dst, n, p * RADIX_BITS,
-                                                                      hist + (size_t)p * RADIX, desc, ticket);
+    kern<<<(unsigned)tiles, THREADS, smem, st>>>(src, dst, n, p * RADIX_BITS, hist + (size_t)p * RADIX, desc, ticket);
     launches++;
     std::swap(src, dst);
   }
   *out = src;
   return launches;
+}
+
+// step 2: the onesweep passes; result in *out
+int sort_passes(unsigned long long* keys, unsigned long long* alt, uint64_t n, int end_bit, void* temp,
+                unsigned long long** out, cudaStream_t st) {
+  *out = keys;
+  if (n <= 1) return 0;
+  const int np = plan_passes(end_bit);
+  const int cfg = getenv("CRGPU_SORT_CFG") ? atoi(getenv("CRGPU_SORT_CFG")) : 0;
+  switch (cfg) {
+    case 1: return run_passes<512, 12, 2, 1>(keys, alt, n, np, temp, out, st);
+    case 2: return run_passes<256, 16, 4, 0>(keys, alt, n, np, temp, out, st);
+    case 3: return run_passes<256, 24, 3, 0>(keys, alt, n, np, temp, out, st);
+    case 4: return run_passes<384, 16, 2, 0>(keys, alt, n, np, temp, out, st);
+    case 5: return run_passes<128, 16, 8, 0>(keys, alt, n, np, temp, out, st);
+    case 6: return run_passes<256, 12, 4, 0>(keys, alt, n, np, temp, out, st);
+    case 7: return run_passes<256, 8, 6, 0>(keys, alt, n, np, temp, out, st);
+    case 8: return run_passes<512, 16, 1, 0>(keys, alt, n, np, temp, out, st);
+    case 9: return run_passes<1024, 12, 1, 0>(keys, alt, n, np, temp, out, st);
+    case 10: return run_passes<512, 20, 1, 0>(keys, alt, n, np, temp, out, st);
+    default: return run_passes<512, 12, 2, 0>(keys, alt, n, np, temp, out, st);
+  }
 }
 
 int sort_keys(unsigned long long* keys, unsigned long long* alt, uint64_t n, int end_bit, void* temp, size_t temp_bytes,
