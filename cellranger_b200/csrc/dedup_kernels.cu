@@ -119,91 +119,13 @@ struct BestPick {
   }
 };
 
-// Search in global memory for segments too long for the shared-memory window: locate the segment, then
-// binary-search the three mutants of each UMI base side by side (independent chains).
-__device__ __noinline__ void correct_one_global(const unsigned long long* __restrict__ dkeys,
-                                                const uint32_t* __restrict__ c0, uint64_t m, int ub, uint64_t j,
-                                                BestPick* bp) {
-  const unsigned long long key = dkeys[j];
-  const unsigned long long seg = key >> ub;
-  const unsigned long long umask = (1ull << ub) - 1ull;
-  // gallop outwards to bracket the segment, then bisect
-  uint64_t lo = j, step = 64;
-  while (true) {
-    uint64_t probe = lo >= step ? lo - step : 0;
-    if ((dkeys[probe] >> ub) != seg) {
-      uint64_t a = probe, b = lo;  // dkeys[a] outside, dkeys[b] inside
-      while (b - a > 1) {
-        uint64_t mid = (a + b) >> 1;
-        if ((dkeys[mid] >> ub) == seg)
-          b = mid;
-        else
-          a = mid;
-      }
-      lo = b;
-      break;
-    }
-    lo = probe;
-    if (probe == 0) break;
-    step <<= 1;
-  }
-  uint64_t hi = j;
-  step = 64;
-  while (true) {
-    uint64_t probe = hi + step < m ? hi + step : m - 1;
-    if ((dkeys[probe] >> ub) != seg) {
-      uint64_t a = hi, b = probe;  // dkeys[a] inside, dkeys[b] outside
-      while (b - a > 1) {
-        uint64_t mid = (a + b) >> 1;
-        if ((dkeys[mid] >> ub) == seg)
-          a = mid;
-        else
-          b = mid;
-      }
-      hi = a;
-      break;
-    }
-    hi = probe;
-    if (probe == m - 1) break;
-    step <<= 1;
-  }
-  const uint64_t s_lo = lo, s_hi = hi + 1;
-  for (int sh = 0; sh < ub; sh += 2) {
-    unsigned long long t[3];
-    uint64_t a[3], b[3];
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-      t[d] = key ^ ((unsigned long long)(d + 1) << sh);
-      a[d] = s_lo;
-      b[d] = s_hi;
-    }
-    bool more = true;
-    while (more) {
-      more = false;
-#pragma unroll
-      for (int d = 0; d < 3; d++) {
-        if (a[d] < b[d]) {
-          uint64_t mid = (a[d] + b[d]) >> 1;
-          if (dkeys[mid] < t[d])
-            a[d] = mid + 1;
-          else
-            b[d] = mid;
-          more = true;
-        }
-      }
-    }
-#pragma unroll
-    for (int d = 0; d < 3; d++)
-      if (a[d] < s_hi && dkeys[a[d]] == t[d]) bp->consider(c0[a[d]], t[d] & umask, (uint32_t)a[d]);
-  }
-}
-
 // Tiled kernel: a block answers CU_TILE consecutive keys out of a shared-memory window that also holds
 // CU_HALO keys on each side, so every segment of up to CU_HALO keys that touches the tile is complete in
 // shared memory. Segments of one key need nothing; short ones are compared pairwise by the owning thread;
 // the keys of longer ones are first compacted into a work list and then answered densely (no divergence)
-// by probing a shared-memory hash set with the 3L mutants; only segments longer than the halo go to
-// global memory.
+// by probing a shared-memory hash set with the 3L mutants. A segment longer than the halo is cut by the
+// window edge: its keys are also probed against further windows (the hash holds full 64-bit keys, so a
+// mutant can only match a key of its own segment) until the whole segment has been seen.
 constexpr int CU_THREADS = 512;
 constexpr int CU_TILE = 3072;
 constexpr int CU_HALO = 1536;
@@ -303,7 +225,7 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
   for (int i = tid; i < wn; i += CU_THREADS) {
     int s = seg_lo[i];
     int n = (int)seg_hi[s] - s;
-    if (n > CU_SMALL) {
+    if (n > CU_SMALL || (s == 0 && cut_l) || ((int)seg_hi[s] == wn && cut_r)) {
       uint32_t h = cu_hash(w_key[i]);
       while (atomicCAS(&table[h], CU_EMPTY, (unsigned short)i) != CU_EMPTY) h = (h + 1) & (CU_SLOTS - 1);
     }
@@ -330,15 +252,13 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
     const int s = seg_lo[i];
     const int e = seg_hi[s];
     const int n = e - s;
-    if (!((corr_mask >> lib) & 1u) || n == 1) {
+    const bool is_cut = (s == 0 && cut_l) || (e == wn && cut_r);
+    if (!((corr_mask >> lib) & 1u) || (n == 1 && !is_cut)) {
       best[j] = (uint32_t)j;
       continue;
     }
-    if ((s == 0 && cut_l) || (e == wn && cut_r)) {
-      const uint32_t own = c0[j];
-      BestPick bp{own, key & umask, (uint32_t)j};
-      correct_one_global(dkeys, c0, m, ub, j, &bp);
-      finish(i, bp, own);
+    if (is_cut) {
+      work[atomicAdd(&s_nwork, 1u)] = (unsigned short)(i | 0x8000);  // cut segment: more windows follow
     } else if (n <= CU_SMALL) {
       uint32_t hits = 0;  // neighbours are rare: find them first, fetch their counts only then
       int first_hit = -1;
@@ -367,7 +287,8 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
   // pass B: the work list, one thread per key, every lane busy
   const int nwork = (int)s_nwork;
   for (int w = tid; w < nwork; w += CU_THREADS) {
-    const int i = work[w];
+    const int i = work[w] & 0x7FFF;
+    const bool is_cut = (work[w] & 0x8000) != 0;
     const uint64_t j = w_lo + i;
     const unsigned long long key = w_key[i];
     uint32_t found[4];
@@ -395,6 +316,7 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
     }
     const uint32_t own = c0[j];
     BestPick bp{own, key & umask, (uint32_t)j};
+    if (is_cut) nfound = 5;  // keep the code below simple: take the general path
     if (nfound <= 4) {
       for (int f = 0; f < nfound; f++) bp.consider(c0[w_lo + found[f]], w_key[found[f]] & umask, (uint32_t)(w_lo + found[f]));
     } else {  // more neighbours than the register list holds: walk the mutants again
@@ -413,7 +335,88 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
           }
         }
     }
-    finish(i, bp, own);
+    if (is_cut)
+      best[j] = bp.idx;  // provisional: the rest of the segment is still to come
+    else
+      finish(i, bp, own);
+  }
+  // further windows for the cut segments (block-uniform conditions)
+  if (cut_l || cut_r) {
+    const unsigned long long seg_l = w_key[0] >> ub, seg_r = w_key[wn - 1] >> ub;
+    const uint64_t home_lo = w_lo;
+    for (int side = 0; side < 2; side++) {
+      if (side == 0 ? !cut_l : !cut_r) continue;
+      const unsigned long long seg_s = side == 0 ? seg_l : seg_r;
+      uint64_t edge = side == 0 ? w_lo : w_hi;  // the window grows away from the home window
+      bool more = true;
+      while (more) {
+        uint64_t a, b;
+        if (side == 0) {
+          b = edge;
+          a = b >= (uint64_t)CU_WIN ? b - CU_WIN : 0;
+          more = a > 0 && (dkeys[a - 1] >> ub) == seg_s;
+          edge = a;
+        } else {
+          a = edge;
+          b = a + CU_WIN < m ? a + CU_WIN : m;
+          more = b < m && (dkeys[b] >> ub) == seg_s;
+          edge = b;
+        }
+        const int xn = (int)(b - a);
+        __syncthreads();  // everyone is done with the previous window
+        for (int i = tid; i < xn; i += CU_THREADS) w_key[i] = dkeys[a + i];
+        {
+          uint32_t* t32 = reinterpret_cast<uint32_t*>(table);
+          for (int i = tid; i < CU_SLOTS / 2; i += CU_THREADS) t32[i] = 0xFFFFFFFFu;
+        }
+        __syncthreads();
+        for (int i = tid; i < xn; i += CU_THREADS) {
+          if ((w_key[i] >> ub) != seg_s) continue;
+          uint32_t h = cu_hash(w_key[i]);
+          while (atomicCAS(&table[h], CU_EMPTY, (unsigned short)i) != CU_EMPTY) h = (h + 1) & (CU_SLOTS - 1);
+        }
+        __syncthreads();
+        for (int w = tid; w < nwork; w += CU_THREADS) {
+          if (!(work[w] & 0x8000)) continue;
+          const uint64_t j = home_lo + (work[w] & 0x7FFF);
+          const unsigned long long key = dkeys[j];
+          if ((key >> ub) != seg_s) continue;
+          uint32_t cur = best[j];
+          BestPick bp{c0[cur], dkeys[cur] & umask, cur};
+          bool changed = false;
+          for (int sh = 0; sh < ub; sh += 2)
+            for (unsigned long long d = 1; d < 4; d++) {
+              const unsigned long long t = key ^ (d << sh);
+              uint32_t h = cu_hash(t);
+              while (true) {
+                unsigned short idx = table[h];
+                if (idx == CU_EMPTY) break;
+                if (w_key[idx] == t) {
+                  uint32_t before = bp.idx;
+                  bp.consider(c0[a + idx], t & umask, (uint32_t)(a + idx));
+                  changed |= bp.idx != before;
+                  break;
+                }
+                h = (h + 1) & (CU_SLOTS - 1);
+              }
+            }
+          if (changed) best[j] = bp.idx;
+        }
+      }
+    }
+    __syncthreads();
+    // the cut keys have seen their whole segment: account for the corrected ones
+    for (int w = tid; w < nwork; w += CU_THREADS) {
+      if (!(work[w] & 0x8000)) continue;
+      const uint64_t j = home_lo + (work[w] & 0x7FFF);
+      const uint32_t bj = best[j];
+      if (bj != (uint32_t)j) {
+        const uint32_t own = c0[j];
+        atomicAdd(inc + bj, (1ull << 40) | (unsigned long long)own);
+        n_corr++;
+        n_corr_reads += own;
+      }
+    }
   }
   if (n_corr) {
     atomicAdd(&s_corr, n_corr);

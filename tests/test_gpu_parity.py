@@ -319,3 +319,45 @@ def test_repeated_runs_are_deterministic(monkeypatch):
             assert np.array_equal(m.indptr, ref_m.indptr) and np.array_equal(m.indices, ref_m.indices)
             assert np.array_equal(m.data, ref_m.data)
     gw.close()
+
+
+def test_long_umi_segments_span_several_windows():
+    """(barcode, gene) segments far longer than the shared-memory window of the UMI-correction kernel
+    (one cell, one or two genes, up to ~40 k distinct UMIs each): every key must still see its whole segment."""
+    import cellranger_b200 as cb
+    from oracle import cro
+
+    rng = np.random.default_rng(5)
+    wl = ["AAAACCCCGGGGTTTT", "ACGTACGTACGTACGT"]
+    n = 120_000
+    r1 = np.zeros((n, 26), dtype=np.uint8)
+    r1[:, :16] = np.frombuffer(wl[0].encode(), dtype=np.uint8)
+    r1[n // 2:, :16] = np.frombuffer(wl[1].encode(), dtype=np.uint8)
+    umis = rng.integers(0, 4, size=(n, 10))
+    umis[:, :2] = 0  # 4^8 = 65536 UMIs: dense Hamming-1 neighbourhoods, chains and ties
+    r1[:, 16:] = np.frombuffer(b"ACGT", dtype=np.uint8)[umis]
+    q1 = np.full((n, 26), ord("I"), dtype=np.uint8)
+    feat = (rng.random(n) < 0.7).astype(np.uint32)  # gene 0: ~30 %, gene 1: ~70 %
+    o = cro.Oracle()
+    w = o.add_whitelist(wl)
+    lib = o.add_library(w, 0, 16, 16, 10)
+    o.set_features(np.zeros(2, dtype=np.int32))
+    o.add_reads(lib, r1, q1, feat)
+    o.run(4)
+    gw = cb.GemWell()
+    w2 = gw.add_whitelist(cb.Whitelist.plain(wl))
+    lib2 = gw.add_library(w2, cb.ChemistryDef.SC3Pv2())
+    gw.set_feature_reference(cb.FeatureReference(2))
+    gw.add_reads(lib2, r1, q1, feat)
+    gw.run(annotate_reads=True)
+    assert gw.stats()["distinct_keys"] > 50_000
+    mo, mg = o.matrix(), gw.count_matrix()
+    assert np.array_equal(mo["indptr"], mg.indptr) and np.array_equal(mo["indices"], mg.indices)
+    assert np.array_equal(mo["data"], mg.data)
+    ro, rg = o.reads(), gw.reads(0)
+    assert np.array_equal(ro["flags"], rg["flags"])
+    has = (ro["flags"] & 2) != 0
+    assert np.array_equal(ro["umi"][has], cb.unpack_2bit(rg["umi"], 10)[has])
+    so, sg = o.stats(), gw.stats()
+    assert so["umi_corrected_reads"] == sg["umi_corrected_reads"] and so["low_support_reads"] == sg["low_support_reads"]
+    gw.close()
