@@ -1078,7 +1078,7 @@ int crgpu_count(crgpu_ctx* c) {
                              c->kl.total_bits, c->sort_temp.p, &sorted, c->stream);
   CHECK_KERNEL();
   if ((rc = phase_end(c))) return rc;
-  if ((rc = phase_begin(c, "count.dedup"))) return rc;
+  if ((rc = phase_begin(c, "count.dedup.alloc"))) return rc;
   if ((rc = c->dkeys.ensure(cap * 8))) return rc;
   if ((rc = c->c0.ensure(cap * 4))) return rc;
   if ((rc = c->best.ensure(cap * 4))) return rc;
@@ -1102,6 +1102,12 @@ int crgpu_count(crgpu_ctx* c) {
     if (c->libs[l]->def.umi_correction) b.umi_correction_mask |= 1u << l;
   b.filter_umis = c->filter_umis;
   b.verify = getenv("CRGPU_VERIFY") != nullptr;
+  b.mark = [](void* user, const char* name) {
+    crgpu_ctx* cc = static_cast<crgpu_ctx*>(user);
+    phase_end(cc);
+    phase_begin(cc, name);
+  };
+  b.mark_user = c;
   b.dkeys = c->dkeys.as<unsigned long long>();
   b.c0 = c->c0.as<uint32_t>();
   b.best = c->best.as<uint32_t>();

@@ -121,21 +121,70 @@ struct BestPick {
 
 // Tiled kernel: a block answers CU_TILE consecutive keys out of a shared-memory window that also holds
 // CU_HALO keys on each side, so every segment of up to CU_HALO keys that touches the tile is complete in
-// shared memory. Segments of one key need nothing; short ones are compared pairwise by the owning thread;
-// the keys of longer ones are first compacted into a work list and then answered densely (no divergence)
-// by probing a shared-memory hash set with the 3L mutants. A segment longer than the halo is cut by the
-// window edge: its keys are also probed against further windows (the hash holds full 64-bit keys, so a
-// mutant can only match a key of its own segment) until the whole segment has been seen.
+// shared memory. All window keys go into a shared-memory hash set (full 64-bit keys, so a mutant can only
+// match a key of its own segment) and into a 64 Kbit presence bitmap. Keys whose segment is a singleton
+// need nothing; the others are compacted into a work list and answered densely: each of the 3L mutants
+// is first tested against the bitmap (one shared load; almost always absent) and only then probed in the
+// hash set. A segment longer than the halo is cut by the window edge: its keys are probed against
+// further windows until the whole segment has been seen.
 constexpr int CU_THREADS = 512;
-constexpr int CU_TILE = 3072;
-constexpr int CU_HALO = 1536;
-constexpr int CU_WIN = CU_TILE + 2 * CU_HALO;  // 6144
-constexpr int CU_SLOTS = 16384;
-constexpr int CU_SMALL = 40;
-constexpr unsigned short CU_EMPTY = 0xFFFFu;
+constexpr int CU_TILE = 2048;
+constexpr int CU_HALO = 1024;
+constexpr int CU_WIN = CU_TILE + 2 * CU_HALO;  // 4096
+constexpr int CU_SLOTS = 8192;                 // 32-bit slots: native shared-memory CAS
+constexpr int CU_BITS = 65536;                 // presence bitmap
+constexpr uint32_t CU_EMPTY = 0xFFFFFFFFu;
 
-__device__ __forceinline__ uint32_t cu_hash(unsigned long long k) {
-  return (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> 50) & (CU_SLOTS - 1);
+__device__ __forceinline__ unsigned long long cu_mix(unsigned long long k) { return k * 0x9E3779B97F4A7C15ull; }
+__device__ __forceinline__ uint32_t cu_slot(unsigned long long h) { return (uint32_t)(h >> 51) & (CU_SLOTS - 1); }
+__device__ __forceinline__ uint32_t cu_bit(unsigned long long h) { return (uint32_t)(h >> 32) & (CU_BITS - 1); }
+
+// insert the keys w_key[0..n) that pass `take` into the hash set and the bitmap (tables already cleared)
+template <typename Take>
+__device__ __forceinline__ void cu_build(const unsigned long long* w_key, int n, uint32_t* table, uint32_t* bitmap,
+                                         Take take) {
+  for (int i = threadIdx.x; i < n; i += CU_THREADS) {
+    const unsigned long long k = w_key[i];
+    if (!take(k)) continue;
+    const unsigned long long h = cu_mix(k);
+    const uint32_t b = cu_bit(h);
+    atomicOr(&bitmap[b >> 5], 1u << (b & 31));
+    uint32_t sl = cu_slot(h);
+    while (atomicCAS(&table[sl], CU_EMPTY, (uint32_t)i) != CU_EMPTY) sl = (sl + 1) & (CU_SLOTS - 1);
+  }
+}
+
+// probe the 3L mutants of `key`; `hit(idx)` is called with the window index of every neighbour found.
+// Two phases so that a warp does not diverge on every mutant: first all mutants are tested against the
+// bitmap (straight-line code, one shared load each) into a candidate mask, then only the few candidates
+// (bitmap false positives and true neighbours) are looked up in the hash set.
+template <typename Hit>
+__device__ __forceinline__ void cu_probe(const unsigned long long* w_key, const uint32_t* table,
+                                         const uint32_t* bitmap, unsigned long long key, int ub, Hit hit) {
+  unsigned long long cand = 0ull;
+  int m_idx = 0;
+  for (int sh = 0; sh < ub; sh += 2) {
+#pragma unroll
+    for (unsigned long long d = 1; d < 4; d++, m_idx++) {
+      const uint32_t b = cu_bit(cu_mix(key ^ (d << sh)));
+      cand |= (unsigned long long)((bitmap[b >> 5] >> (b & 31)) & 1u) << m_idx;
+    }
+  }
+  while (cand) {
+    const int mi = __ffsll((long long)cand) - 1;
+    cand &= cand - 1ull;
+    const unsigned long long t = key ^ ((unsigned long long)(mi % 3 + 1) << (2 * (mi / 3)));
+    uint32_t sl = cu_slot(cu_mix(t));
+    while (true) {
+      const uint32_t idx = table[sl];
+      if (idx == CU_EMPTY) break;
+      if (w_key[idx] == t) {
+        hit(idx);
+        break;
+      }
+      sl = (sl + 1) & (CU_SLOTS - 1);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsigned long long* __restrict__ dkeys,
@@ -145,11 +194,10 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
                                                                      unsigned long long* __restrict__ inc,
                                                                      unsigned long long* __restrict__ scalars) {
   extern __shared__ __align__(16) unsigned char cu_smem[];
-  unsigned long long* w_key = reinterpret_cast<unsigned long long*>(cu_smem);      // CU_WIN
-  unsigned short* table = reinterpret_cast<unsigned short*>(w_key + CU_WIN);        // CU_SLOTS
-  unsigned short* seg_lo = table + CU_SLOTS;                                        // CU_WIN
-  unsigned short* seg_hi = seg_lo + CU_WIN;                                         // CU_WIN (exclusive end, at head)
-  unsigned short* work = seg_hi + CU_WIN;                                           // CU_TILE: hash-path queries
+  unsigned long long* w_key = reinterpret_cast<unsigned long long*>(cu_smem);  // CU_WIN
+  uint32_t* table = reinterpret_cast<uint32_t*>(w_key + CU_WIN);                // CU_SLOTS
+  uint32_t* bitmap = table + CU_SLOTS;                                          // CU_BITS / 32
+  unsigned short* work = reinterpret_cast<unsigned short*>(bitmap + CU_BITS / 32);  // CU_TILE
   __shared__ unsigned long long s_corr, s_corr_reads;
   __shared__ uint32_t s_nwork;
 
@@ -169,185 +217,63 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
     s_nwork = 0;
   }
   for (int i = tid; i < wn; i += CU_THREADS) w_key[i] = dkeys[w_lo + i];
-  {
-    uint32_t* t32 = reinterpret_cast<uint32_t*>(table);
-    for (int i = tid; i < CU_SLOTS / 2; i += CU_THREADS) t32[i] = 0xFFFFFFFFu;
-  }
+  for (int i = tid; i < CU_SLOTS; i += CU_THREADS) table[i] = CU_EMPTY;
+  for (int i = tid; i < CU_BITS / 32; i += CU_THREADS) bitmap[i] = 0u;
   __syncthreads();
   // is the first / last segment of the window cut by the window edge?
-  const bool cut_l = w_lo > 0 && (dkeys[w_lo - 1] >> ub) == (w_key[0] >> ub);
-  const bool cut_r = w_hi < m && (dkeys[w_hi] >> ub) == (w_key[wn - 1] >> ub);
+  const unsigned long long seg_l = w_key[0] >> ub, seg_r = w_key[wn - 1] >> ub;
+  const bool cut_l = w_lo > 0 && (dkeys[w_lo - 1] >> ub) == seg_l;
+  const bool cut_r = w_hi < m && (dkeys[w_hi] >> ub) == seg_r;
+  cu_build(w_key, wn, table, bitmap, [](unsigned long long) { return true; });
 
-  // segment bounds of every window element: each thread owns a contiguous chunk, chunks are stitched
-  // through shared memory (first pass: local runs; second pass: extend across chunk borders)
-  constexpr int PER = CU_WIN / CU_THREADS;  // 12
-  {
-    const int c_lo = tid * PER;
-    int run_start = c_lo;
-    for (int k = 0; k < PER; k++) {
-      int i = c_lo + k;
-      if (i >= wn) break;
-      if (k > 0 && (w_key[i] >> ub) != (w_key[i - 1] >> ub)) run_start = i;
-      seg_lo[i] = (unsigned short)run_start;
-    }
-  }
-  __syncthreads();
-  {
-    // extend the run that starts at a chunk border backwards while the segment continues
-    const int c_lo = tid * PER;
-    if (c_lo < wn && c_lo > 0 && (w_key[c_lo] >> ub) == (w_key[c_lo - 1] >> ub)) {
-      const unsigned long long sg = w_key[c_lo] >> ub;
-      int s = c_lo - 1;
-      // jump chunk by chunk: seg_lo of the previous element points to its run start (local or extended)
-      while (true) {
-        s = seg_lo[s];
-        if (s == 0 || (s % PER) != 0 || (w_key[s - 1] >> ub) != sg) break;
-        s = s - 1;
-      }
-      for (int k = 0; k < PER; k++) {
-        int i = c_lo + k;
-        if (i >= wn || (w_key[i] >> ub) != sg) break;
-        seg_lo[i] = (unsigned short)s;  // only elements whose local run began at the chunk border
-      }
-    }
-  }
-  __syncthreads();
-  {
-    const int c_lo = tid * PER;
-    for (int k = 0; k < PER; k++) {
-      int i = c_lo + k;
-      if (i >= wn) break;
-      if (i + 1 >= wn || seg_lo[i + 1] != seg_lo[i]) seg_hi[seg_lo[i]] = (unsigned short)(i + 1);
-    }
-  }
-  __syncthreads();
-  // hash the members of the longer segments
-  for (int i = tid; i < wn; i += CU_THREADS) {
-    int s = seg_lo[i];
-    int n = (int)seg_hi[s] - s;
-    if (n > CU_SMALL || (s == 0 && cut_l) || ((int)seg_hi[s] == wn && cut_r)) {
-      uint32_t h = cu_hash(w_key[i]);
-      while (atomicCAS(&table[h], CU_EMPTY, (unsigned short)i) != CU_EMPTY) h = (h + 1) & (CU_SLOTS - 1);
-    }
-  }
-
-  unsigned long long n_corr = 0, n_corr_reads = 0;
+  // singletons are done; everything else goes to the work list (bit 15: the segment is cut)
   const int q_off = (int)(q_lo - w_lo);
   const int qn = (int)(q_hi - q_lo);
-  auto finish = [&](int i, const BestPick& bp, uint32_t own_c0) {
-    const uint64_t j = w_lo + i;
-    best[j] = bp.idx;
-    if (bp.idx != (uint32_t)j) {
-      atomicAdd(inc + bp.idx, (1ull << 40) | (unsigned long long)own_c0);
-      n_corr++;
-      n_corr_reads += own_c0;
-    }
-  };
-  // pass A: singletons, short segments (pairwise), cut segments (global); longer ones go to the work list
   for (int qi = tid; qi < qn; qi += CU_THREADS) {
     const int i = q_off + qi;
-    const uint64_t j = w_lo + i;
     const unsigned long long key = w_key[i];
+    const unsigned long long seg = key >> ub;
     const uint32_t lib = (uint32_t)(key >> kl.lib_shift) & lmask;
-    const int s = seg_lo[i];
-    const int e = seg_hi[s];
-    const int n = e - s;
-    const bool is_cut = (s == 0 && cut_l) || (e == wn && cut_r);
-    if (!((corr_mask >> lib) & 1u) || (n == 1 && !is_cut)) {
-      best[j] = (uint32_t)j;
-      continue;
-    }
-    if (is_cut) {
-      work[atomicAdd(&s_nwork, 1u)] = (unsigned short)(i | 0x8000);  // cut segment: more windows follow
-    } else if (n <= CU_SMALL) {
-      uint32_t hits = 0;  // neighbours are rare: find them first, fetch their counts only then
-      int first_hit = -1;
-      for (int k = s; k < e; k++) {
-        if (hamming1_2bit(w_key[k], key)) {
-          hits++;
-          if (first_hit < 0) first_hit = k;
-        }
-      }
-      if (hits == 0) {
-        best[j] = (uint32_t)j;
-      } else {
-        const uint32_t own = c0[j];
-        BestPick bp{own, key & umask, (uint32_t)j};
-        for (int k = first_hit; k < e; k++) {
-          unsigned long long o = w_key[k];
-          if (hamming1_2bit(o, key)) bp.consider(c0[w_lo + k], o & umask, (uint32_t)(w_lo + k));
-        }
-        finish(i, bp, own);
-      }
-    } else {
-      work[atomicAdd(&s_nwork, 1u)] = (unsigned short)i;
-    }
+    const bool is_cut = (cut_l && seg == seg_l) || (cut_r && seg == seg_r);
+    const bool alone = (i == 0 || (w_key[i - 1] >> ub) != seg) && (i + 1 >= wn || (w_key[i + 1] >> ub) != seg);
+    if (!((corr_mask >> lib) & 1u) || (alone && !is_cut))
+      best[w_lo + i] = (uint32_t)(w_lo + i);
+    else
+      work[atomicAdd(&s_nwork, 1u)] = (unsigned short)(i | (is_cut ? 0x8000 : 0));
   }
   __syncthreads();
-  // pass B: the work list, one thread per key, every lane busy
+
+  unsigned long long n_corr = 0, n_corr_reads = 0;
   const int nwork = (int)s_nwork;
   for (int w = tid; w < nwork; w += CU_THREADS) {
     const int i = work[w] & 0x7FFF;
     const bool is_cut = (work[w] & 0x8000) != 0;
     const uint64_t j = w_lo + i;
     const unsigned long long key = w_key[i];
-    uint32_t found[4];
-    int nfound = 0;
-    for (int sh = 0; sh < ub; sh += 2) {
-#pragma unroll
-      for (unsigned long long d = 1; d < 4; d++) {
-        const unsigned long long t = key ^ (d << sh);
-        uint32_t h = cu_hash(t);
-        while (true) {
-          unsigned short idx = table[h];
-          if (idx == CU_EMPTY) break;
-          if (w_key[idx] == t) {
-            if (nfound < 4) found[nfound] = idx;
-            nfound++;
-            break;
-          }
-          h = (h + 1) & (CU_SLOTS - 1);
-        }
+    BestPick bp{0u, key & umask, (uint32_t)j};
+    bool have_own = false;
+    cu_probe(w_key, table, bitmap, key, ub, [&](uint32_t idx) {
+      if (!have_own) {
+        bp.count = c0[j];
+        have_own = true;
       }
+      bp.consider(c0[w_lo + idx], w_key[idx] & umask, (uint32_t)(w_lo + idx));
+    });
+    best[j] = bp.idx;  // provisional for a cut segment: the rest of it is still to come
+    if (!is_cut && bp.idx != (uint32_t)j) {
+      const uint32_t own = c0[j];
+      atomicAdd(inc + bp.idx, (1ull << 40) | (unsigned long long)own);
+      n_corr++;
+      n_corr_reads += own;
     }
-    if (nfound == 0) {
-      best[j] = (uint32_t)j;
-      continue;
-    }
-    const uint32_t own = c0[j];
-    BestPick bp{own, key & umask, (uint32_t)j};
-    if (is_cut) nfound = 5;  // keep the code below simple: take the general path
-    if (nfound <= 4) {
-      for (int f = 0; f < nfound; f++) bp.consider(c0[w_lo + found[f]], w_key[found[f]] & umask, (uint32_t)(w_lo + found[f]));
-    } else {  // more neighbours than the register list holds: walk the mutants again
-      for (int sh = 0; sh < ub; sh += 2)
-        for (unsigned long long d = 1; d < 4; d++) {
-          const unsigned long long t = key ^ (d << sh);
-          uint32_t h = cu_hash(t);
-          while (true) {
-            unsigned short idx = table[h];
-            if (idx == CU_EMPTY) break;
-            if (w_key[idx] == t) {
-              bp.consider(c0[w_lo + idx], t & umask, (uint32_t)(w_lo + idx));
-              break;
-            }
-            h = (h + 1) & (CU_SLOTS - 1);
-          }
-        }
-    }
-    if (is_cut)
-      best[j] = bp.idx;  // provisional: the rest of the segment is still to come
-    else
-      finish(i, bp, own);
   }
   // further windows for the cut segments (block-uniform conditions)
   if (cut_l || cut_r) {
-    const unsigned long long seg_l = w_key[0] >> ub, seg_r = w_key[wn - 1] >> ub;
     const uint64_t home_lo = w_lo;
     for (int side = 0; side < 2; side++) {
       if (side == 0 ? !cut_l : !cut_r) continue;
       const unsigned long long seg_s = side == 0 ? seg_l : seg_r;
-      uint64_t edge = side == 0 ? w_lo : w_hi;  // the window grows away from the home window
+      uint64_t edge = side == 0 ? w_lo : w_hi;  // the window moves away from the home window
       bool more = true;
       while (more) {
         uint64_t a, b;
@@ -365,42 +291,22 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
         const int xn = (int)(b - a);
         __syncthreads();  // everyone is done with the previous window
         for (int i = tid; i < xn; i += CU_THREADS) w_key[i] = dkeys[a + i];
-        {
-          uint32_t* t32 = reinterpret_cast<uint32_t*>(table);
-          for (int i = tid; i < CU_SLOTS / 2; i += CU_THREADS) t32[i] = 0xFFFFFFFFu;
-        }
+        for (int i = tid; i < CU_SLOTS; i += CU_THREADS) table[i] = CU_EMPTY;
+        for (int i = tid; i < CU_BITS / 32; i += CU_THREADS) bitmap[i] = 0u;
         __syncthreads();
-        for (int i = tid; i < xn; i += CU_THREADS) {
-          if ((w_key[i] >> ub) != seg_s) continue;
-          uint32_t h = cu_hash(w_key[i]);
-          while (atomicCAS(&table[h], CU_EMPTY, (unsigned short)i) != CU_EMPTY) h = (h + 1) & (CU_SLOTS - 1);
-        }
+        cu_build(w_key, xn, table, bitmap, [=](unsigned long long k) { return (k >> ub) == seg_s; });
         __syncthreads();
         for (int w = tid; w < nwork; w += CU_THREADS) {
           if (!(work[w] & 0x8000)) continue;
           const uint64_t j = home_lo + (work[w] & 0x7FFF);
           const unsigned long long key = dkeys[j];
           if ((key >> ub) != seg_s) continue;
-          uint32_t cur = best[j];
+          const uint32_t cur = best[j];
           BestPick bp{c0[cur], dkeys[cur] & umask, cur};
-          bool changed = false;
-          for (int sh = 0; sh < ub; sh += 2)
-            for (unsigned long long d = 1; d < 4; d++) {
-              const unsigned long long t = key ^ (d << sh);
-              uint32_t h = cu_hash(t);
-              while (true) {
-                unsigned short idx = table[h];
-                if (idx == CU_EMPTY) break;
-                if (w_key[idx] == t) {
-                  uint32_t before = bp.idx;
-                  bp.consider(c0[a + idx], t & umask, (uint32_t)(a + idx));
-                  changed |= bp.idx != before;
-                  break;
-                }
-                h = (h + 1) & (CU_SLOTS - 1);
-              }
-            }
-          if (changed) best[j] = bp.idx;
+          cu_probe(w_key, table, bitmap, key, ub, [&](uint32_t idx) {
+            bp.consider(c0[a + idx], w_key[idx] & umask, (uint32_t)(a + idx));
+          });
+          if (bp.idx != cur) best[j] = bp.idx;
         }
       }
     }
@@ -642,7 +548,11 @@ int launch_order_violations(const unsigned long long* a, uint64_t n, int strict,
 int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
   int launches = 0;
   ScanScratch ss{b.lb_desc, b.tickets, 0};
+  auto mark = [&](const char* name) {
+    if (b.mark) b.mark(b.mark_user, name);
+  };
   cudaMemsetAsync(b.scalars, 0, 16 * 8, st);
+  mark("count.dedup.rle");
   // 1. run-length encode: distinct keys + raw counts (head positions parked in `best`)
   RleOp rle{b.sorted, 0, b.dkeys, b.best};
   launches += run_compact(rle, b.n_keys, ss, b.scalars + 0, st);
@@ -658,10 +568,11 @@ int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
     launches += launch_order_violations(b.dkeys, m, 1, b.scalars + 11, st);
   }
   // 2. UMI correction targets + incoming counts
+  mark("count.dedup.correct_umis");
   cudaMemsetAsync(b.inc, 0, m * 8, st);
   cudaMemsetAsync(b.low, 0, m, st);
   {
-    const size_t smem = (size_t)CU_WIN * 8 + (size_t)CU_SLOTS * 2 + (size_t)CU_WIN * 2 * 2 + (size_t)CU_TILE * 2;
+    const size_t smem = (size_t)CU_WIN * 8 + (size_t)CU_SLOTS * 4 + (size_t)CU_BITS / 8 + (size_t)CU_TILE * 2;
     static bool attr_set = false;
     if (!attr_set) {
       cudaFuncSetAttribute(correct_umis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -672,6 +583,7 @@ int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
                                                           b.inc, b.scalars);
     launches++;
   }
+  mark("count.dedup.low_support");
   // 3. low-support filter: candidates by hashing (rank, library, umi), exact regrouping of those only
   if (b.filter_umis) {
     int slot_bits = 16;
@@ -694,6 +606,7 @@ int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
       launches++;
     }
   }
+  mark("count.dedup.molecules");
   low_reads_kernel<<<grid_for(m), 256, 0, st>>>(b.c0, b.best, b.low, m, b.scalars);
   launches++;
   // 4. molecules = correction targets that are not low support (key2 now holds their keys)

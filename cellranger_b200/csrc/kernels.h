@@ -111,6 +111,8 @@ struct DedupBuffers {
   unsigned long long* scalars;  // device scalars: [0] n_distinct [1] nnz [2] n_molecules [3] corrected keys [4] low keys
   void* sort_temp;
   size_t sort_temp_bytes;
+  void (*mark)(void* user, const char* phase);  // optional: called at the start of each sub-phase
+  void* mark_user;
   int verify;          // CRGPU_VERIFY: count order violations after the sort and the run-length encoding
   uint32_t* slots;     // 2-bit hash slots of the low-support pre-filter
   size_t slots_bytes;
