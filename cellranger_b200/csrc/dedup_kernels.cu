@@ -132,12 +132,19 @@ constexpr int CU_TILE = 2048;
 constexpr int CU_HALO = 1024;
 constexpr int CU_WIN = CU_TILE + 2 * CU_HALO;  // 4096
 constexpr int CU_SLOTS = 8192;                 // 32-bit slots: native shared-memory CAS
-constexpr int CU_BITS = 65536;                 // presence bitmap
+constexpr int CU_BITS = 1 << 18;               // presence bitmap (32 KB)
 constexpr uint32_t CU_EMPTY = 0xFFFFFFFFu;
 
-__device__ __forceinline__ unsigned long long cu_mix(unsigned long long k) { return k * 0x9E3779B97F4A7C15ull; }
-__device__ __forceinline__ uint32_t cu_slot(unsigned long long h) { return (uint32_t)(h >> 51) & (CU_SLOTS - 1); }
-__device__ __forceinline__ uint32_t cu_bit(unsigned long long h) { return (uint32_t)(h >> 32) & (CU_BITS - 1); }
+// 32-bit hash of a 64-bit key: only the low word changes between a key and its UMI mutants, so the
+// contribution of the high word is computed once per key (hi_mix) and each mutant costs one multiply.
+__device__ __forceinline__ uint32_t cu_hi_mix(unsigned long long k) { return (uint32_t)(k >> 32) * 0x85EBCA77u; }
+__device__ __forceinline__ uint32_t cu_mix(uint32_t lo, uint32_t hi_mix) {
+  uint32_t h = (lo * 0x9E3779B1u) ^ hi_mix;
+  return h ^ (h >> 15);
+}
+__device__ __forceinline__ uint32_t cu_slot(uint32_t h) { return (h * 0x2C1B3C6Du) >> 19; }  // 13 bits
+__device__ __forceinline__ uint32_t cu_bit(uint32_t h) { return h >> 14; }                    // 18 bits
+static_assert(CU_SLOTS == 8192 && CU_BITS == (1 << 18), "hash field widths");
 
 // insert the keys w_key[0..n) that pass `take` into the hash set and the bitmap (tables already cleared)
 template <typename Take>
@@ -145,8 +152,8 @@ __device__ __forceinline__ void cu_build(const unsigned long long* w_key, int n,
                                          Take take) {
   for (int i = threadIdx.x; i < n; i += CU_THREADS) {
     const unsigned long long k = w_key[i];
-    if (!take(k)) continue;
-    const unsigned long long h = cu_mix(k);
+    if (!take(i, k)) continue;
+    const uint32_t h = cu_mix((uint32_t)k, cu_hi_mix(k));
     const uint32_t b = cu_bit(h);
     atomicOr(&bitmap[b >> 5], 1u << (b & 31));
     uint32_t sl = cu_slot(h);
@@ -161,20 +168,22 @@ __device__ __forceinline__ void cu_build(const unsigned long long* w_key, int n,
 template <typename Hit>
 __device__ __forceinline__ void cu_probe(const unsigned long long* w_key, const uint32_t* table,
                                          const uint32_t* bitmap, unsigned long long key, int ub, Hit hit) {
+  const uint32_t lo = (uint32_t)key, hm = cu_hi_mix(key);
   unsigned long long cand = 0ull;
   int m_idx = 0;
   for (int sh = 0; sh < ub; sh += 2) {
 #pragma unroll
-    for (unsigned long long d = 1; d < 4; d++, m_idx++) {
-      const uint32_t b = cu_bit(cu_mix(key ^ (d << sh)));
+    for (uint32_t d = 1; d < 4; d++, m_idx++) {
+      const uint32_t b = cu_bit(cu_mix(lo ^ (d << sh), hm));
       cand |= (unsigned long long)((bitmap[b >> 5] >> (b & 31)) & 1u) << m_idx;
     }
   }
   while (cand) {
     const int mi = __ffsll((long long)cand) - 1;
     cand &= cand - 1ull;
-    const unsigned long long t = key ^ ((unsigned long long)(mi % 3 + 1) << (2 * (mi / 3)));
-    uint32_t sl = cu_slot(cu_mix(t));
+    const uint32_t tlo = lo ^ ((uint32_t)(mi % 3 + 1) << (2 * (mi / 3)));
+    const unsigned long long t = (key & 0xFFFFFFFF00000000ull) | tlo;
+    uint32_t sl = cu_slot(cu_mix(tlo, hm));
     while (true) {
       const uint32_t idx = table[sl];
       if (idx == CU_EMPTY) break;
@@ -198,7 +207,6 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
   uint32_t* table = reinterpret_cast<uint32_t*>(w_key + CU_WIN);                // CU_SLOTS
   uint32_t* bitmap = table + CU_SLOTS;                                          // CU_BITS / 32
   unsigned short* work = reinterpret_cast<unsigned short*>(bitmap + CU_BITS / 32);  // CU_TILE
-  __shared__ unsigned long long s_corr, s_corr_reads;
   __shared__ uint32_t s_nwork;
 
   const int ub = kl.umi_bits;
@@ -211,11 +219,7 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
   const uint64_t w_hi = q_hi + CU_HALO < m ? q_hi + CU_HALO : m;
   const int wn = (int)(w_hi - w_lo);
 
-  if (tid == 0) {
-    s_corr = 0;
-    s_corr_reads = 0;
-    s_nwork = 0;
-  }
+  if (tid == 0) s_nwork = 0;
   for (int i = tid; i < wn; i += CU_THREADS) w_key[i] = dkeys[w_lo + i];
   for (int i = tid; i < CU_SLOTS; i += CU_THREADS) table[i] = CU_EMPTY;
   for (int i = tid; i < CU_BITS / 32; i += CU_THREADS) bitmap[i] = 0u;
@@ -224,7 +228,12 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
   const unsigned long long seg_l = w_key[0] >> ub, seg_r = w_key[wn - 1] >> ub;
   const bool cut_l = w_lo > 0 && (dkeys[w_lo - 1] >> ub) == seg_l;
   const bool cut_r = w_hi < m && (dkeys[w_hi] >> ub) == seg_r;
-  cu_build(w_key, wn, table, bitmap, [](unsigned long long) { return true; });
+  // keys that are alone in their segment can be nobody's neighbour: they stay out of the tables
+  cu_build(w_key, wn, table, bitmap, [&](int i, unsigned long long k) {
+    const unsigned long long sg = k >> ub;
+    const bool alone = (i == 0 ? !cut_l : (w_key[i - 1] >> ub) != sg) && (i + 1 >= wn ? !cut_r : (w_key[i + 1] >> ub) != sg);
+    return !alone;
+  });
 
   // singletons are done; everything else goes to the work list (bit 15: the segment is cut)
   const int q_off = (int)(q_lo - w_lo);
@@ -294,7 +303,7 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
         for (int i = tid; i < CU_SLOTS; i += CU_THREADS) table[i] = CU_EMPTY;
         for (int i = tid; i < CU_BITS / 32; i += CU_THREADS) bitmap[i] = 0u;
         __syncthreads();
-        cu_build(w_key, xn, table, bitmap, [=](unsigned long long k) { return (k >> ub) == seg_s; });
+        cu_build(w_key, xn, table, bitmap, [=](int, unsigned long long k) { return (k >> ub) == seg_s; });
         __syncthreads();
         for (int w = tid; w < nwork; w += CU_THREADS) {
           if (!(work[w] & 0x8000)) continue;
@@ -324,14 +333,15 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
       }
     }
   }
-  if (n_corr) {
-    atomicAdd(&s_corr, n_corr);
-    atomicAdd(&s_corr_reads, n_corr_reads);
+  // statistics: warp reduction, then one global atomic per warp (64-bit shared-memory atomics are a
+  // compare-and-swap loop on this hardware: never use them on a hot address)
+  for (int d = 16; d > 0; d >>= 1) {
+    n_corr += __shfl_xor_sync(0xFFFFFFFFu, n_corr, d);
+    n_corr_reads += __shfl_xor_sync(0xFFFFFFFFu, n_corr_reads, d);
   }
-  __syncthreads();
-  if (tid == 0 && s_corr) {
-    atomicAdd(scalars + 3, s_corr);
-    atomicAdd(scalars + 5, s_corr_reads);
+  if ((tid & 31) == 0 && n_corr) {
+    atomicAdd(scalars + 3, n_corr);
+    atomicAdd(scalars + 5, n_corr_reads);
   }
 }
 
