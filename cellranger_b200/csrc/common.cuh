@@ -5,6 +5,7 @@
 
 #define CRGPU_MAX_ORD 8
 #define CRGPU_MAX_LIBS 4
+#define CRGPU_MAX_PARTS 16
 
 // bc_out word: state in the top 2 bits, content rank below (CRGPU_NO_RANK when invalid)
 #define BC_STATE_SHIFT 30

@@ -333,7 +333,7 @@ int crgpu_ctx_create(int device, crgpu_ctx** out) {
   CU(cudaStreamSynchronize(c->stream));
   int rc;
   if ((rc = c->counters.ensure(8 * 1024))) return rc;
-  if ((rc = c->scalars.ensure(8 * 16))) return rc;
+  if ((rc = c->scalars.ensure(8 * 64))) return rc;
   if ((rc = c->tickets.ensure(64))) return rc;
   *out = c;
   return CRGPU_OK;
@@ -979,33 +979,14 @@ int crgpu_keys_partition(crgpu_ctx* c, int32_t n_parts, const uint32_t* bounds, 
   CU(cudaSetDevice(c->device));
   int rc;
   if ((rc = fetch_n_keys(c))) return rc;
-  // a full local sort groups the keys by rank; the parts are then contiguous ranges
-  if ((rc = c->sort_temp.ensure(sort_temp_bytes(c->n_keys)))) return rc;
-  unsigned long long* sorted = nullptr;
-  c->launches += sort_keys(c->keys.as<unsigned long long>(), c->keys_alt.as<unsigned long long>(), c->n_keys,
-                           c->kl.total_bits, c->sort_temp.p, c->sort_temp.cap, &sorted, c->stream);
+  if (n_parts > CRGPU_MAX_PARTS) return fail(CRGPU_E_LIMIT, "too many parts");
+  for (int p = 0; p < n_parts; p++)
+    if (bounds[p] > bounds[p + 1]) return fail(CRGPU_E_INVALID, "bounds must be non-decreasing");
+  c->launches += run_owner_partition(c->keys.as<unsigned long long>(), c->n_keys, c->kl.rank_shift, bounds, n_parts,
+                                     c->keys_alt.as<unsigned long long>(), c->scalars.as<unsigned long long>() + 16,
+                                     out_counts, c->stream);
   CHECK_KERNEL();
-  if (sorted != c->keys.as<unsigned long long>()) std::swap(c->keys, c->keys_alt);
-  // boundaries by binary search on the host over device memory would need many copies; fetch the rank
-  // column boundaries with a small kernel-free approach: copy the keys' rank bounds via lower_bound probes
-  std::vector<uint64_t> cut(n_parts + 1, 0);
-  cut[n_parts] = c->n_keys;
-  for (int p = 1; p < n_parts; p++) {
-    unsigned long long target = (unsigned long long)bounds[p] << c->kl.rank_shift;
-    uint64_t lo = 0, hi = c->n_keys;
-    while (lo < hi) {
-      uint64_t mid = (lo + hi) >> 1;
-      unsigned long long v;
-      CU(cudaMemcpyAsync(&v, c->keys.as<unsigned long long>() + mid, 8, cudaMemcpyDeviceToHost, c->stream));
-      CU(cudaStreamSynchronize(c->stream));
-      if (v < target)
-        lo = mid + 1;
-      else
-        hi = mid;
-    }
-    cut[p] = lo;
-  }
-  for (int p = 0; p < n_parts; p++) out_counts[p] = cut[p + 1] - cut[p];
+  std::swap(c->keys, c->keys_alt);
   return CRGPU_OK;
 }
 
@@ -1250,21 +1231,17 @@ int crgpu_sync(crgpu_ctx* c) {
 int crgpu_stats(crgpu_ctx* c, uint64_t out[CRGPU_STAT_COUNT]) {
   if (!c || !out) return fail(CRGPU_E_INVALID, "bad argument");
   CU(cudaSetDevice(c->device));
-  if (c->stage >= 2) {
-    // barcode state counts from the per-library histograms
-    uint64_t vb = 0, co = 0;
-    std::vector<uint32_t> h(c->content.size());
-    for (auto* l : c->libs) {
-      CU(cudaMemcpyAsync(h.data(), l->prior.p, h.size() * 4, cudaMemcpyDeviceToHost, c->stream));
-      CU(cudaStreamSynchronize(c->stream));
-      for (uint32_t v : h) vb += v;
-      CU(cudaMemcpyAsync(h.data(), l->corrected.p, h.size() * 4, cudaMemcpyDeviceToHost, c->stream));
-      CU(cudaStreamSynchronize(c->stream));
-      for (uint32_t v : h) co += v;
-    }
-    c->stats[CRGPU_STAT_VALID_BEFORE] = vb;
-    c->stats[CRGPU_STAT_CORRECTED] = co;
-    c->stats[CRGPU_STAT_INVALID] = c->n_reads - vb - co;
+  if (c->stage >= 1 && c->n_reads) {
+    // barcode states of this context's own reads (the histograms may hold all-reduced, global counts)
+    unsigned long long* d4 = c->scalars.as<unsigned long long>() + 48;
+    unsigned long long h4[4];
+    CU(cudaMemsetAsync(d4, 0, 32, c->stream));
+    c->launches += launch_state_counts(c->bc_out.as<uint32_t>(), c->n_reads, d4, c->stream);
+    CU(cudaMemcpyAsync(h4, d4, 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->stats[CRGPU_STAT_VALID_BEFORE] = h4[1];
+    c->stats[CRGPU_STAT_CORRECTED] = h4[2];
+    c->stats[CRGPU_STAT_INVALID] = h4[3];
   }
   c->stats[CRGPU_STAT_READS] = c->n_reads;
   c->stats[CRGPU_STAT_KERNEL_LAUNCHES] = c->launches;

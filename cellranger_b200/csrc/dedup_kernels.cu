@@ -537,6 +537,130 @@ __global__ void low_reads_kernel(const uint32_t* __restrict__ c0, const uint32_t
   if ((threadIdx.x & 31) == 0 && s) atomicAdd(scalars + 6, s);
 }
 
+// ---------------------------------------------------------------------------
+// barcode-owner partition of the local keys (multi-GPU): keys of owner p = content ranks
+// [bounds[p], bounds[p+1]) end up contiguous, in owner order; order inside an owner is irrelevant
+// (the receiver sorts). One counting pass, one scatter pass.
+// ---------------------------------------------------------------------------
+struct OwnerBounds {
+  uint32_t b[CRGPU_MAX_PARTS + 1];
+  int n;
+};
+__device__ __forceinline__ int owner_of(const OwnerBounds& ob, uint32_t rank) {
+  int p = 0;
+#pragma unroll
+  for (int i = 1; i < CRGPU_MAX_PARTS; i++)
+    if (i < ob.n && rank >= ob.b[i]) p = i;
+  return p;
+}
+__global__ void __launch_bounds__(256) owner_count_kernel(const unsigned long long* __restrict__ keys, uint64_t n,
+                                                          int rank_shift, OwnerBounds ob,
+                                                          unsigned long long* __restrict__ counts) {
+  __shared__ uint32_t s_cnt[CRGPU_MAX_PARTS];
+  if (threadIdx.x < CRGPU_MAX_PARTS) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    int p = owner_of(ob, (uint32_t)(keys[i] >> rank_shift));
+    uint32_t peers = __match_any_sync(__activemask(), p);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_cnt[p], (uint32_t)__popc(peers));
+  }
+  __syncthreads();
+  if (threadIdx.x < ob.n && s_cnt[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+}
+// cursors[p] starts at the exclusive prefix of counts; blocks claim ranges per owner
+__global__ void __launch_bounds__(256) owner_scatter_kernel(const unsigned long long* __restrict__ keys, uint64_t n,
+                                                            int rank_shift, OwnerBounds ob,
+                                                            unsigned long long* __restrict__ cursors,
+                                                            unsigned long long* __restrict__ out) {
+  __shared__ uint32_t s_cnt[CRGPU_MAX_PARTS];
+  __shared__ unsigned long long s_base[CRGPU_MAX_PARTS];
+  const uint64_t n_blocks_work = (n + 255) / 256;
+  for (uint64_t blk = blockIdx.x; blk < n_blocks_work; blk += gridDim.x) {
+    if (threadIdx.x < CRGPU_MAX_PARTS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t i = blk * 256 + threadIdx.x;
+    int p = -1;
+    uint32_t off = 0;
+    unsigned long long k = 0;
+    if (i < n) {
+      k = keys[i];
+      p = owner_of(ob, (uint32_t)(k >> rank_shift));
+    }
+    {
+      uint32_t peers = __match_any_sync(0xFFFFFFFFu, p);
+      int leader = __ffs(peers) - 1;
+      uint32_t base = 0;
+      if (p >= 0 && (int)(threadIdx.x & 31) == leader) base = atomicAdd(&s_cnt[p], (uint32_t)__popc(peers));
+      base = __shfl_sync(0xFFFFFFFFu, base, leader);
+      off = base + __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
+    }
+    __syncthreads();
+    if (threadIdx.x < ob.n)
+      s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(cursors + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]) : 0ull;
+    __syncthreads();
+    if (p >= 0) out[s_base[p] + off] = k;
+    __syncthreads();
+  }
+}
+
+// counts[0..n_parts) <- keys per owner; out <- keys grouped by owner. scratch: 2 * CRGPU_MAX_PARTS u64.
+int run_owner_partition(const unsigned long long* keys, uint64_t n, int rank_shift, const uint32_t* bounds, int n_parts,
+                        unsigned long long* out, unsigned long long* scratch, uint64_t* counts_host, cudaStream_t st) {
+  OwnerBounds ob;
+  ob.n = n_parts;
+  for (int i = 0; i <= CRGPU_MAX_PARTS; i++) ob.b[i] = i <= n_parts ? bounds[i] : 0xFFFFFFFFu;
+  unsigned long long* d_counts = scratch;
+  unsigned long long* d_cursors = scratch + CRGPU_MAX_PARTS;
+  cudaMemsetAsync(scratch, 0, 2 * CRGPU_MAX_PARTS * 8, st);
+  int launches = 0;
+  if (n) {
+    owner_count_kernel<<<grid_for(n), 256, 0, st>>>(keys, n, rank_shift, ob, d_counts);
+    launches++;
+  }
+  unsigned long long h[CRGPU_MAX_PARTS] = {0};
+  cudaMemcpyAsync(h, d_counts, n_parts * 8, cudaMemcpyDeviceToHost, st);
+  cudaStreamSynchronize(st);
+  unsigned long long cur[CRGPU_MAX_PARTS] = {0}, run = 0;
+  for (int p = 0; p < n_parts; p++) {
+    counts_host[p] = h[p];
+    cur[p] = run;
+    run += h[p];
+  }
+  cudaMemcpyAsync(d_cursors, cur, n_parts * 8, cudaMemcpyHostToDevice, st);
+  if (n) {
+    owner_scatter_kernel<<<grid_for(n), 256, 0, st>>>(keys, n, rank_shift, ob, d_cursors, out);
+    launches++;
+  }
+  cudaStreamSynchronize(st);  // `cur` is a local
+  return launches;
+}
+
+// per-read barcode states of a batch (local statistics; the histograms may hold global counts)
+__global__ void state_counts_kernel(const uint32_t* __restrict__ bc_out, uint64_t n, unsigned long long* out4) {
+  unsigned long long c1 = 0, c2 = 0, c3 = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t st = bc_out[i] >> BC_STATE_SHIFT;
+    c1 += st == ST_VALID_BEFORE;
+    c2 += st == ST_VALID_AFTER;
+    c3 += st == ST_INVALID;
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    c1 += __shfl_xor_sync(0xFFFFFFFFu, c1, d);
+    c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, d);
+    c3 += __shfl_xor_sync(0xFFFFFFFFu, c3, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (c1) atomicAdd(out4 + 1, c1);
+    if (c2) atomicAdd(out4 + 2, c2);
+    if (c3) atomicAdd(out4 + 3, c3);
+  }
+}
+int launch_state_counts(const uint32_t* bc_out, uint64_t n, unsigned long long* out4, cudaStream_t st) {
+  if (!n) return 0;
+  state_counts_kernel<<<grid_for(n), 256, 0, st>>>(bc_out, n, out4);
+  return 1;
+}
+
 // debug verification (CRGPU_VERIFY=1): order violations in a key array; strict = equal neighbours count too
 __global__ void order_violations_kernel(const unsigned long long* __restrict__ a, uint64_t n, int strict,
                                         unsigned long long* out) {

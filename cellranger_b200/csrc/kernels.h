@@ -137,6 +137,10 @@ struct MatrixArgs {
 int run_matrix(DedupBuffers& b, MatrixArgs& m, uint64_t nnz, uint64_t n_mol, uint64_t* n_barcodes_host,
                cudaStream_t st);
 
+int run_owner_partition(const unsigned long long* keys, uint64_t n, int rank_shift, const uint32_t* bounds, int n_parts,
+                        unsigned long long* out, unsigned long long* scratch, uint64_t* counts_host, cudaStream_t st);
+int launch_state_counts(const uint32_t* bc_out, uint64_t n, unsigned long long* out4, cudaStream_t st);
+
 struct AnnotateArgs {
   uint64_t n;
   const uint32_t* bc_out;
