@@ -23,6 +23,7 @@ struct Pass1Args {
   uint32_t lib;
   int emit_keys;
   int have_qual;  // 0: qualities absent (crgpu_correct_barcodes with qual == NULL)
+  int debug_flags;  // profiling ablations (CRGPU_P1_DBG); 0 in production
 };
 
 struct Pass2Args {

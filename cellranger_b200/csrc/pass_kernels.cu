@@ -466,6 +466,258 @@ __global__ void __launch_bounds__(256) pass1_generic_kernel(const Pass1Args a) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Pass 1 split in two (standard layouts): pack_kernel streams the reads once at HBM speed (no table
+// look-ups, no atomics), match_kernel works on the 8-byte packed records with many look-ups in flight.
+// ---------------------------------------------------------------------------
+#define UMI_BCN_BIT 0x20000000u  // umi_out word, between the two kernels: the barcode holds a non-ACGT base
+
+template <int R1_LEN, int UMI_LEN, int THREADS, int RPT, int STAGES>
+__global__ void __launch_bounds__(THREADS) pack_kernel(const Pass1Args a) {
+  constexpr int TILE = THREADS * RPT;
+  constexpr int SEQ_BYTES = TILE * R1_LEN;
+  constexpr int REC_PAD = 16;
+  constexpr int STAGE_BYTES = 2 * (SEQ_BYTES + REC_PAD);
+  constexpr int NWARPS = THREADS / 32;
+  static_assert(SEQ_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t mbar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint64_t n_tiles = (a.n + TILE - 1) / TILE;
+  const unsigned long long policy = make_evict_first_policy();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&mbar[s], 1);
+      mbar_init(&empty_bar[s], NWARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto stage_seq = [&](int s) { return smem + (size_t)s * STAGE_BYTES; };
+  auto stage_qual = [&](int s) { return smem + (size_t)s * STAGE_BYTES + SEQ_BYTES + REC_PAD; };
+  auto issue = [&](uint64_t tile, int s) {
+    uint64_t first = tile * TILE;
+    if (first + TILE <= a.n) {
+      mbar_expect_tx(&mbar[s], 2 * SEQ_BYTES);
+      bulk_g2s_hint(stage_seq(s), a.seq + first * R1_LEN, SEQ_BYTES, &mbar[s], policy);
+      bulk_g2s_hint(stage_qual(s), a.qual + first * R1_LEN, SEQ_BYTES, &mbar[s], policy);
+    }
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) {
+      uint64_t tile = blockIdx.x + (uint64_t)s * gridDim.x;
+      if (tile < n_tiles) issue(tile, s);
+    }
+  }
+  uint32_t it = 0;
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+    const int s = it % STAGES;
+    const uint32_t parity = (it / STAGES) & 1u;
+    const uint64_t first = tile * TILE;
+    const int cnt = (int)((a.n - first) < (uint64_t)TILE ? (a.n - first) : (uint64_t)TILE);
+    if (cnt == TILE) {
+      mbar_wait(&mbar[s], parity);
+    } else {
+      const uint8_t* gs = a.seq + first * R1_LEN;
+      const uint8_t* gq = a.qual + first * R1_LEN;
+      for (int b = tid; b < cnt * R1_LEN; b += THREADS) {
+        stage_seq(s)[b] = gs[b];
+        stage_qual(s)[b] = gq[b];
+      }
+      __syncthreads();
+    }
+    uint32_t bcw[RPT], umw[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
+      const int j = tid + k * THREADS;
+      if (j < cnt) {
+        Packed pk;
+        pack_record<R1_LEN, UMI_LEN>(stage_seq(s), stage_qual(s), j, &pk);
+        const uint32_t rep = 0x55555555u & mask_bits(2 * UMI_LEN);
+        bool homopolymer = pk.umi == (pk.umi & 3u) * rep;
+        bool umi_valid = !(pk.umi_has_n || homopolymer || pk.umi_lowq);
+        bcw[k] = pk.bc;
+        umw[k] = (pk.umi & 0x1FFFFFFFu) | (umi_valid ? UMI_VALID_BIT : 0u) | (pk.umi_has_n ? UMI_HASN_BIT : 0u) |
+                 (pk.nmask ? UMI_BCN_BIT : 0u);
+      }
+    }
+    // the stage may be refilled once every warp has read it (see pass1_staged_kernel for why not bar.sync)
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+    if (tid == 0) {
+      uint64_t next = tile + (uint64_t)STAGES * gridDim.x;
+      if (next < n_tiles) {
+        mbar_wait(&empty_bar[s], parity);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(next, s);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
+      const int j = tid + k * THREADS;
+      if (j < cnt) {
+        a.bc_out[first + j] = bcw[k];
+        a.umi_out[first + j] = umw[k];
+      }
+    }
+  }
+}
+
+// 16 bytes at an arbitrary address (needs 4 readable bytes past the end at most)
+__device__ __forceinline__ uint4 load_bytes16(const uint8_t* p) {
+  const uintptr_t addr = (uintptr_t)p;
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(addr & 3) * 8u;
+  uint32_t x0 = __ldg(q), x1 = __ldg(q + 1), x2 = __ldg(q + 2), x3 = __ldg(q + 3);
+  uint32_t x4 = sh ? __ldg(q + 4) : 0u;
+  return make_uint4(__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), __funnelshift_r(x2, x3, sh),
+                    __funnelshift_r(x3, x4, sh));
+}
+
+template <int THREADS, int RPT>
+__global__ void __launch_bounds__(THREADS) match_kernel(const Pass1Args a) {
+  constexpr int TILE = THREADS * RPT;
+  constexpr int NWARPS = THREADS / 32;
+  __shared__ uint32_t warp_tot[2][NWARPS];
+  __shared__ unsigned long long base_bcast[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t n_tiles = (a.n + TILE - 1) / TILE;
+  const bool have_feat = a.feature != nullptr;
+  const uint32_t umask = mask_bits(a.kl.umi_bits);
+  uint32_t it = 0;
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+    const uint64_t first = tile * TILE;
+    uint32_t bc[RPT], uw[RPT], feat[RPT];
+    bool live[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
+      const uint64_t gi = first + tid + k * THREADS;
+      live[k] = gi < a.n;
+      bc[k] = live[k] ? a.bc_out[gi] : 0u;
+      uw[k] = live[k] ? a.umi_out[gi] : UMI_BCN_BIT;
+      feat[k] = (live[k] && have_feat) ? __ldcs(a.feature + gi) : NO_FEATURE;
+    }
+    uint32_t st0[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; k++) st0[k] = wl_find_begin(a.wl, bc[k]);
+    WlProbe pr[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; k++) pr[k] = wl_find_probe(a.wl, st0[k]);
+    uint32_t bcw[RPT];
+    unsigned long long key[RPT];
+    bool emit[RPT], inval[RPT];
+    uint32_t n_key = 0, n_inv = 0;
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
+      const bool bcn = (uw[k] & UMI_BCN_BIT) != 0;
+      int idx = bcn ? -1 : wl_find_end(a.wl, pr[k], bc[k]);
+      emit[k] = false;
+      inval[k] = false;
+      key[k] = 0ull;
+      if (idx >= 0) {
+        uint32_t rank = wl_rank_of(a.wl, idx);
+        if (a.prior && !(a.debug_flags & 1)) atomicAdd(a.prior + rank, 1u);
+        bcw[k] = (ST_VALID_BEFORE << BC_STATE_SHIFT) | rank;
+        if (a.emit_keys && (uw[k] & UMI_VALID_BIT) && feat[k] != NO_FEATURE) {
+          emit[k] = true;
+          key[k] = make_key(a.kl, rank, feat[k], a.lib, uw[k] & umask);
+        }
+      } else {
+        bcw[k] = (ST_INVALID << BC_STATE_SHIFT) | BC_RANK_MASK;
+        inval[k] = live[k];
+      }
+      n_key += emit[k];
+      n_inv += inval[k];
+    }
+    const uint32_t v = n_key | (n_inv << 16);
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    const int par = it & 1;
+    if (lane == 31) warp_tot[par][warp] = inc;
+    __syncthreads();
+    uint32_t wsum = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < NWARPS; w++) {
+      uint32_t c = warp_tot[par][w];
+      if (w < warp) wsum += c;
+      tot += c;
+    }
+    const uint32_t excl = wsum + inc - v;
+    if (tid == 0)
+      base_bcast[par] = tot ? atomicAdd(a.counters, (unsigned long long)(tot & 0xFFFFu) |
+                                                        ((unsigned long long)(tot >> 16) << 32))
+                            : 0ull;
+    __syncthreads();
+    const unsigned long long base = base_bcast[par];
+    uint64_t kpos = (base & 0xFFFFFFFFull) + (excl & 0xFFFFu);
+    uint64_t ipos = (base >> 32) + (excl >> 16);
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
+      if (live[k]) {
+        const uint64_t gi = first + tid + k * THREADS;
+        a.bc_out[gi] = bcw[k];
+        if (uw[k] & UMI_BCN_BIT) a.umi_out[gi] = uw[k] & ~UMI_BCN_BIT;
+        if (emit[k] && !(a.debug_flags & 2)) __stcs(a.keys + kpos++, key[k]);
+        if (inval[k]) {
+          uint32_t nmask = 0;
+          if (uw[k] & UMI_BCN_BIT) {  // rare: recompute which bases are not A,C,G,T
+            uint4 sq = load_bytes16(a.seq + gi * a.r1_len + a.bc_off);
+            const uint32_t w4[4] = {sq.x, sq.y, sq.z, sq.w};
+#pragma unroll
+            for (int wd = 0; wd < 4; wd++) {
+              uint32_t bad;
+              pack4(w4[wd], &bad);
+#pragma unroll
+              for (int by = 0; by < 4; by++)
+                if (bad & (0x80u << (8 * by))) nmask |= 1u << (wd * 4 + by);
+            }
+          }
+          a.inv_idx[ipos] = (uint32_t)gi;
+          a.inv_bc[ipos] = bc[k];
+          a.inv_nmask[ipos] = nmask;
+          a.inv_qual[ipos] = load_bytes16(a.qual + gi * a.r1_len + a.bc_off);
+          ipos++;
+        }
+      }
+    }
+  }
+}
+
+template <int R1_LEN, int UMI_LEN>
+static int launch_split(const Pass1Args& a_in, int n_sms, cudaStream_t st) {
+  Pass1Args a = a_in;
+  a.debug_flags = getenv("CRGPU_P1_DBG") ? atoi(getenv("CRGPU_P1_DBG")) : 0;
+  const bool only_pack = a.debug_flags & 4, only_match = a.debug_flags & 8;
+  if (!only_match) {
+    constexpr int THREADS = 256, RPT = 2, STAGES = 3, TILE = THREADS * RPT;
+    auto kern = pack_kernel<R1_LEN, UMI_LEN, THREADS, RPT, STAGES>;
+    size_t smem = (size_t)STAGES * 2 * (TILE * R1_LEN + 16);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
+    uint64_t tiles = (a.n + TILE - 1) / TILE;
+    int grid = (int)std::min<uint64_t>(tiles, (uint64_t)n_sms * (per_sm > 0 ? per_sm : 1));
+    kern<<<grid, THREADS, smem, st>>>(a);
+  }
+  if (!only_pack) {
+    constexpr int THREADS = 256, RPT = 4, TILE = THREADS * RPT;
+    auto kern = match_kernel<THREADS, RPT>;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, 0);
+    uint64_t tiles = (a.n + TILE - 1) / TILE;
+    int grid = (int)std::min<uint64_t>(tiles, (uint64_t)n_sms * (per_sm > 0 ? per_sm : 1));
+    kern<<<grid, THREADS, 0, st>>>(a);
+  }
+  return 2;
+}
+
 template <int R1_LEN, int UMI_LEN, int THREADS, int RPT, int STAGES>
 static int launch_staged(const Pass1Args& a, int n_sms, cudaStream_t st) {
   constexpr int TILE = THREADS * RPT;
@@ -498,8 +750,11 @@ int launch_pass1(const Pass1Args& a, int n_sms, cudaStream_t st) {
   const bool std_layout = a.bc_off == 0 && a.bc_len == 16 && a.umi_off == 16 && a.have_qual &&
                           ((uintptr_t)a.seq % 16 == 0) && ((uintptr_t)a.qual % 16 == 0) &&
                           (a.feature == nullptr || (uintptr_t)a.feature % 16 == 0);
-  if (std_layout && a.r1_len == 28 && a.umi_len == 12) return launch_staged_cfg<28, 12>(a, n_sms, st);
-  if (std_layout && a.r1_len == 26 && a.umi_len == 10) return launch_staged_cfg<26, 10>(a, n_sms, st);
+  const bool split = getenv("CRGPU_P1_MODE") && atoi(getenv("CRGPU_P1_MODE")) == 2;  // default: fused kernel
+  if (std_layout && a.r1_len == 28 && a.umi_len == 12)
+    return split ? launch_split<28, 12>(a, n_sms, st) : launch_staged_cfg<28, 12>(a, n_sms, st);
+  if (std_layout && a.r1_len == 26 && a.umi_len == 10)
+    return split ? launch_split<26, 10>(a, n_sms, st) : launch_staged_cfg<26, 10>(a, n_sms, st);
   uint64_t blocks = (a.n + 255) / 256;
   int grid = (int)std::min<uint64_t>(blocks, (uint64_t)n_sms * 8);
   pass1_generic_kernel<<<grid, 256, 0, st>>>(a);

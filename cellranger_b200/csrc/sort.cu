@@ -3,9 +3,9 @@
 // Least-significant-digit radix sort, 8 bits per pass, restricted to the bits the key layout really
 // uses (KeyLayout::total_bits), so a 3' v2 key (55 bits) takes 7 passes and a 3' v3 key (62 bits) 8.
 // One upfront kernel builds the digit histograms of every pass; each pass is then a single "onesweep"
-// kernel: a tile of keys is ranked inside the block, the tile's digit counts are published through a
-// chained (decoupled look-back) scan, and the keys are scattered through shared memory so every digit
-// bin is written as one contiguous run.
+// kernel: a tile of keys is ranked inside the block (warp match-any, warp-private digit counters), the
+// tile's digit counts are published through a chained (decoupled look-back) scan, and the keys are
+// scattered through shared memory so every digit bin is written as one contiguous run.
 #include <algorithm>
 #include <cstdlib>
 
@@ -54,71 +54,50 @@ __global__ void radix_scan_hist_kernel(unsigned long long* hist) {
 
 // ---- one onesweep pass ----
 // desc[tile * RADIX + digit]: {status:2 | count:62} chained-scan descriptors of this pass.
-template <int SORT_THREADS, int SORT_ITEMS, int MIN_BLOCKS, int RANK_ATOMIC>
-__global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) radix_onesweep_kernel(const unsigned long long* __restrict__ in,
-                                                                      unsigned long long* __restrict__ out, uint64_t n,
-                                                                      int shift,
-                                                                      const unsigned long long* __restrict__ bin_base,
-                                                                      unsigned long long* __restrict__ desc,
-                                                                      uint32_t* __restrict__ ticket) {
+// One tile of one pass. FULL = the tile holds SORT_TILE keys (no bounds checks in the hot loops).
+template <int SORT_THREADS, int SORT_ITEMS, bool FULL>
+__device__ __forceinline__ void onesweep_tile(const unsigned long long* __restrict__ in,
+                                              unsigned long long* __restrict__ out, int cnt, uint64_t tile_first,
+                                              uint32_t tile, int shift,
+                                              const unsigned long long* __restrict__ bin_base,
+                                              unsigned long long* __restrict__ desc, unsigned char* smem_raw) {
   constexpr int WARPS = SORT_THREADS / 32;
   constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_raw);         // SORT_TILE keys
-  uint32_t* s_warp_hist = reinterpret_cast<uint32_t*>(smem_raw + SORT_TILE * 8);         // WARPS * RADIX
-  uint32_t* s_bin_off = s_warp_hist + WARPS * RADIX;                                     // RADIX: tile-local exclusive
-  unsigned long long* s_bin_glob = reinterpret_cast<unsigned long long*>(s_bin_off + RADIX);  // RADIX
-  uint32_t* s_bin_cnt = reinterpret_cast<uint32_t*>(s_bin_glob + RADIX);                       // RADIX: tile counts
-  __shared__ uint32_t tile_s;
-
+  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_raw);               // SORT_TILE keys
+  uint32_t* s_warp_hist = reinterpret_cast<uint32_t*>(smem_raw + SORT_TILE * 8);               // WARPS * RADIX
+  uint32_t* s_bin_off = s_warp_hist + WARPS * RADIX;                                           // RADIX
+  unsigned long long* s_delta = reinterpret_cast<unsigned long long*>(s_bin_off + RADIX);      // RADIX
+  uint32_t* s_bin_cnt = reinterpret_cast<uint32_t*>(s_delta + RADIX);                          // RADIX
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) tile_s = atomicAdd(ticket, 1u);
-  for (int i = tid; i < WARPS * RADIX; i += SORT_THREADS) s_warp_hist[i] = 0;
-  __syncthreads();
-  const uint32_t tile = tile_s;
-  const uint64_t tile_first = (uint64_t)tile * SORT_TILE;
-  const int cnt = (n - tile_first) < (uint64_t)SORT_TILE ? (int)(n - tile_first) : SORT_TILE;
 
   // warp-striped load: warp w owns items [w*32*ITEMS, (w+1)*32*ITEMS), lane-strided
   unsigned long long key[SORT_ITEMS];
-  uint32_t rank_in_warp[SORT_ITEMS];
+  uint32_t dr[SORT_ITEMS];  // digit (low 8 bits... 9 with the invalid marker) | rank in warp << 16
   const int warp_first = warp * 32 * SORT_ITEMS;
 #pragma unroll
   for (int k = 0; k < SORT_ITEMS; k++) {
-    int idx = warp_first + k * 32 + lane;
-    key[k] = idx < cnt ? in[tile_first + idx] : ~0ull;
+    const int idx = warp_first + k * 32 + lane;
+    key[k] = (FULL || idx < cnt) ? __ldcs(in + tile_first + idx) : ~0ull;
   }
-  // rank each key among the keys of the same digit that precede it in this warp: the match masks of all
-  // items are computed first (independent), then the lowest peer lane claims the warp-private counter
-  // with one shared-memory atomic per (item, digit) and hands the old value to its peers by shuffle.
+  // rank each key among the keys of the same digit that precede it in this warp. The lowest peer lane
+  // alone reads and bumps the warp-private counter and hands the old value to its peers by shuffle.
   uint32_t* my_hist = s_warp_hist + warp * RADIX;
-  uint32_t peers[SORT_ITEMS];
+  const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
   for (int k = 0; k < SORT_ITEMS; k++) {
-    int idx = warp_first + k * 32 + lane;
-    uint32_t digit = idx < cnt ? (uint32_t)((key[k] >> shift) & (RADIX - 1)) : (uint32_t)RADIX;
-    peers[k] = __match_any_sync(0xFFFFFFFFu, digit);
-  }
-#pragma unroll
-  for (int k = 0; k < SORT_ITEMS; k++) {
-    int idx = warp_first + k * 32 + lane;
-    bool valid = idx < cnt;
-    uint32_t digit = (uint32_t)((key[k] >> shift) & (RADIX - 1));
-    uint32_t before = __popc(peers[k] & ((1u << lane) - 1u));
-    if constexpr (RANK_ATOMIC) {
-      int leader = __ffs(peers[k]) - 1;
-      uint32_t base = 0;
-      if (valid && lane == leader) base = atomicAdd(&my_hist[digit], (uint32_t)__popc(peers[k]));
-      base = __shfl_sync(0xFFFFFFFFu, base, leader);
-      rank_in_warp[k] = base + before;
-    } else {
-      uint32_t base = 0;
-      if (valid) base = my_hist[digit];
-      __syncwarp();
-      if (valid && before == 0) my_hist[digit] = base + __popc(peers[k]);
-      __syncwarp();
-      rank_in_warp[k] = base + before;
+    const int idx = warp_first + k * 32 + lane;
+    const bool valid = FULL || idx < cnt;
+    const uint32_t digit = valid ? (uint32_t)((key[k] >> shift) & (RADIX - 1)) : (uint32_t)RADIX;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, digit);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (lane == leader && valid) {
+      base = my_hist[digit];
+      my_hist[digit] = base + (uint32_t)__popc(peers);
     }
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    __syncwarp();  // the next item may have another leader for the same digit
+    dr[k] = digit | ((base + (uint32_t)__popc(peers & lt_mask)) << 16);
   }
   __syncthreads();
   // per digit: exclusive scan over the warps, tile total
@@ -130,15 +109,10 @@ __global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) radix_onesweep_kerne
       s_warp_hist[w * RADIX + d] = run;
       run += c;
     }
-    s_bin_off[d] = run;  // tile count of digit d (turned into an exclusive offset below)
-  }
-  __syncthreads();
-  // Publish this tile's digit counts right away (AGGREGATE), so that successors can already add them up
-  // while this block is still scattering; the walk back over the predecessors comes as late as possible.
-  for (int d = tid; d < RADIX; d += SORT_THREADS) {
-    const unsigned long long mine = s_bin_off[d];
-    s_bin_cnt[d] = (uint32_t)mine;
-    lb_store(desc + (size_t)tile * RADIX + d, tile == 0 ? LB_PREFIX : LB_AGGREGATE, mine);
+    s_bin_off[d] = run;
+    s_bin_cnt[d] = run;
+    // publish this tile's digit counts right away, so that successors can add them up while we scatter
+    lb_store(desc + (size_t)tile * RADIX + d, tile == 0 ? LB_PREFIX : LB_AGGREGATE, (unsigned long long)run);
   }
   __syncthreads();
   // tile-local exclusive offsets of the digits (one warp, shuffles)
@@ -158,15 +132,13 @@ __global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) radix_onesweep_kerne
     }
   }
   __syncthreads();
-  // scatter into shared memory in digit order
+  // fold the digit offsets into the per-warp offsets: one shared load per key in the scatter
+  for (int i = tid; i < WARPS * RADIX; i += SORT_THREADS) s_warp_hist[i] += s_bin_off[i & (RADIX - 1)];
+  __syncthreads();
 #pragma unroll
   for (int k = 0; k < SORT_ITEMS; k++) {
-    int idx = warp_first + k * 32 + lane;
-    if (idx < cnt) {
-      uint32_t digit = (uint32_t)((key[k] >> shift) & (RADIX - 1));
-      uint32_t p = s_bin_off[digit] + s_warp_hist[warp * RADIX + digit] + rank_in_warp[k];
-      s_keys[p] = key[k];
-    }
+    const uint32_t digit = dr[k] & 0x1FFu;
+    if (FULL || digit < RADIX) s_keys[my_hist[digit] + (dr[k] >> 16)] = key[k];
   }
   // chained scan over tiles (decoupled look-back), one descriptor per digit
   for (int d = tid; d < RADIX; d += SORT_THREADS) {
@@ -182,15 +154,39 @@ __global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) radix_onesweep_kerne
       }
       lb_store(desc + (size_t)tile * RADIX + d, LB_PREFIX, excl + (unsigned long long)s_bin_cnt[d]);
     }
-    s_bin_glob[d] = bin_base[d] + excl;
+    s_delta[d] = bin_base[d] + excl - (unsigned long long)s_bin_off[d];  // global position of s_keys[p] = delta + p
   }
   __syncthreads();
   // write out: consecutive threads write consecutive keys of a digit run
-  for (int p = tid; p < cnt; p += SORT_THREADS) {
-    unsigned long long k = s_keys[p];
-    uint32_t digit = (uint32_t)((k >> shift) & (RADIX - 1));
-    out[s_bin_glob[digit] + (uint32_t)(p - s_bin_off[digit])] = k;
+#pragma unroll 4
+  for (int p = tid; p < (FULL ? SORT_TILE : cnt); p += SORT_THREADS) {
+    const unsigned long long k = s_keys[p];
+    const uint32_t digit = (uint32_t)((k >> shift) & (RADIX - 1));
+    out[s_delta[digit] + (unsigned long long)p] = k;
   }
+}
+
+template <int SORT_THREADS, int SORT_ITEMS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) radix_onesweep_kernel(
+    const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, uint64_t n, int shift,
+    const unsigned long long* __restrict__ bin_base, unsigned long long* __restrict__ desc,
+    uint32_t* __restrict__ ticket) {
+  constexpr int WARPS = SORT_THREADS / 32;
+  constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* s_warp_hist = reinterpret_cast<uint32_t*>(smem_raw + SORT_TILE * 8);
+  __shared__ uint32_t tile_s;
+  const int tid = threadIdx.x;
+  if (tid == 0) tile_s = atomicAdd(ticket, 1u);
+  for (int i = tid; i < WARPS * RADIX; i += SORT_THREADS) s_warp_hist[i] = 0;
+  __syncthreads();
+  const uint32_t tile = tile_s;
+  const uint64_t tile_first = (uint64_t)tile * SORT_TILE;
+  const int cnt = (n - tile_first) < (uint64_t)SORT_TILE ? (int)(n - tile_first) : SORT_TILE;
+  if (cnt == SORT_TILE)
+    onesweep_tile<SORT_THREADS, SORT_ITEMS, true>(in, out, cnt, tile_first, tile, shift, bin_base, desc, smem_raw);
+  else
+    onesweep_tile<SORT_THREADS, SORT_ITEMS, false>(in, out, cnt, tile_first, tile, shift, bin_base, desc, smem_raw);
 }
 
 }  // namespace
@@ -222,7 +218,7 @@ int sort_histograms(const unsigned long long* keys, uint64_t n, int end_bit, voi
   return 2;
 }
 
-template <int THREADS, int ITEMS, int MIN_BLOCKS, int RANK_ATOMIC>
+template <int THREADS, int ITEMS, int MIN_BLOCKS>
 static int run_passes(unsigned long long* keys, unsigned long long* alt, uint64_t n, int n_passes, void* temp,
                       unsigned long long** out, cudaStream_t st) {
   constexpr int TILE = THREADS * ITEMS;
@@ -233,7 +229,7 @@ static int run_passes(unsigned long long* keys, unsigned long long* alt, uint64_
   unsigned long long* desc = reinterpret_cast<unsigned long long*>(t + (size_t)MAX_PASSES * RADIX * 8);
   uint32_t* ticket = reinterpret_cast<uint32_t*>(t + (size_t)MAX_PASSES * RADIX * 8 + (size_t)(max_tiles + 1) * RADIX * 8);
   const size_t smem = (size_t)TILE * 8 + (size_t)(THREADS / 32) * RADIX * 4 + RADIX * 4 + RADIX * 8 + RADIX * 4;
-  auto kern = radix_onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS, RANK_ATOMIC>;
+  auto kern = radix_onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int launches = 0;
   unsigned long long* src = keys;
@@ -256,18 +252,11 @@ int sort_passes(unsigned long long* keys, unsigned long long* alt, uint64_t n, i
   if (n <= 1) return 0;
   const int np = plan_passes(end_bit);
   const int cfg = getenv("CRGPU_SORT_CFG") ? atoi(getenv("CRGPU_SORT_CFG")) : 0;
-  switch (cfg) {
-    case 1: return run_passes<512, 12, 2, 1>(keys, alt, n, np, temp, out, st);
-    case 2: return run_passes<256, 16, 4, 0>(keys, alt, n, np, temp, out, st);
-    case 3: return run_passes<256, 24, 3, 0>(keys, alt, n, np, temp, out, st);
-    case 4: return run_passes<384, 16, 2, 0>(keys, alt, n, np, temp, out, st);
-    case 5: return run_passes<128, 16, 8, 0>(keys, alt, n, np, temp, out, st);
-    case 6: return run_passes<256, 12, 4, 0>(keys, alt, n, np, temp, out, st);
-    case 7: return run_passes<256, 8, 6, 0>(keys, alt, n, np, temp, out, st);
-    case 8: return run_passes<512, 16, 1, 0>(keys, alt, n, np, temp, out, st);
-    case 9: return run_passes<1024, 12, 1, 0>(keys, alt, n, np, temp, out, st);
-    case 10: return run_passes<512, 20, 1, 0>(keys, alt, n, np, temp, out, st);
-    default: return run_passes<512, 12, 2, 0>(keys, alt, n, np, temp, out, st);
+  switch (cfg) {  // CRGPU_SORT_CFG: tile shapes kept for profiling; 0 = the measured best on B200
+    case 1: return run_passes<512, 12, 2>(keys, alt, n, np, temp, out, st);
+    case 2: return run_passes<384, 16, 2>(keys, alt, n, np, temp, out, st);
+    case 3: return run_passes<384, 12, 3>(keys, alt, n, np, temp, out, st);
+    default: return run_passes<256, 16, 4>(keys, alt, n, np, temp, out, st);
   }
 }
 
