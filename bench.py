@@ -274,7 +274,7 @@ def run_ours(args):
             gw.clear_reads()
             gw.add_reads(libs[0], host["r1_seq"], host["r1_qual"], host["feature"])
             step_device()
-            m = gw.count_matrix()  # device→host read of the step's result
+            m = gw.count_matrix(pinned=True)  # device→host read of the step's result
             d2h = m.indptr.nbytes + m.indices.nbytes + m.data.nbytes + m.barcode_rank.nbytes
             return m
 

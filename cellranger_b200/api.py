@@ -165,20 +165,29 @@ class FeatureReference:
         return self.n_features - 1
 
 
-@dataclass
 class CountMatrix:
     """Feature x barcode matrix in CSC, as write_matrix_h5_helper lays it out
-    (cr_h5/src/count_matrix.rs:382-448): data i32, indices = feature index, indptr i64 per barcode."""
-    barcodes: np.ndarray       # (n_barcodes, L) ASCII, sorted
-    barcode_rank: np.ndarray   # uint32 content rank of each column
-    indptr: np.ndarray         # int64[n_barcodes + 1]
-    indices: np.ndarray        # uint32[nnz]
-    data: np.ndarray           # int32[nnz]
-    n_features: int
+    (cr_h5/src/count_matrix.rs:382-448): data i32, indices = feature index, indptr i64 per barcode.
+    `barcodes` ((n_barcodes, L) ASCII, sorted) is materialised on first use from the content ranks."""
+
+    def __init__(self, barcode_rank, indptr, indices, data, n_features, resolve_barcodes=None, barcodes=None):
+        self.barcode_rank = barcode_rank   # uint32 content rank of each column
+        self.indptr = indptr               # int64[n_barcodes + 1]
+        self.indices = indices             # uint32[nnz]
+        self.data = data                   # int32[nnz]
+        self.n_features = n_features
+        self._resolve = resolve_barcodes
+        self._barcodes = barcodes
+
+    @property
+    def barcodes(self) -> np.ndarray:
+        if self._barcodes is None:
+            self._barcodes = self._resolve(self.barcode_rank)
+        return self._barcodes
 
     @property
     def shape(self):
-        return (self.n_features, self.barcodes.shape[0])
+        return (self.n_features, self.barcode_rank.shape[0])
 
     def barcode_strings(self, gem_group: int = 1):
         return [f"{bytes(b).decode()}-{gem_group}" for b in self.barcodes]
@@ -186,7 +195,7 @@ class CountMatrix:
     def mtx_lines(self):
         """`feature barcode count` triplets, 1-based, in file order
         (MtxWriter::write_matrix_mtx, cr_lib/src/stages/write_matrix_market.rs:81-120)."""
-        cols = np.repeat(np.arange(self.barcodes.shape[0], dtype=np.int64), np.diff(self.indptr))
+        cols = np.repeat(np.arange(self.barcode_rank.shape[0], dtype=np.int64), np.diff(self.indptr))
         return [f"{int(f) + 1} {int(c) + 1} {int(v)}" for f, c, v in zip(self.indices, cols, self.data)]
 
 
@@ -202,6 +211,7 @@ class GemWell:
         check(self.L.crgpu_set_params(self._ctx, C.c_double(self.posterior.bc_confidence_threshold),
                                       C.c_double(self.posterior.max_expected_barcode_errors), int(filter_umis)))
         self._keep = []
+        self._pinned_bufs = {}
         self._whitelists = []
         self._libs = []
         self._batches = []
@@ -212,6 +222,9 @@ class GemWell:
     # ---- lifecycle ----
     def close(self):
         if getattr(self, "_ctx", None):
+            for p, _ in self._pinned_bufs.values():
+                self.L.crgpu_host_free_pinned(C.c_void_p(p))
+            self._pinned_bufs = {}
             self.L.crgpu_ctx_destroy(self._ctx)
             self._ctx = None
 
@@ -441,15 +454,33 @@ class GemWell:
               "crgpu_reads_get")
         return dict(bc_rank=bc_rank, state=state, umi=umi, flags=flags, feature=feature)
 
-    def count_matrix(self) -> CountMatrix:
+    def _pinned(self, name: str, shape, dtype) -> np.ndarray:
+        """A numpy view of a grow-only page-locked host buffer owned by this GemWell."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        cur = self._pinned_bufs.get(name)
+        if cur is None or cur[1] < nbytes:
+            if cur is not None:
+                self.L.crgpu_host_free_pinned(C.c_void_p(cur[0]))
+            p = C.c_void_p()
+            cap = max(nbytes + nbytes // 8, 4096)
+            check(self.L.crgpu_host_alloc_pinned(C.c_uint64(cap), C.byref(p)), "crgpu_host_alloc_pinned")
+            cur = (p.value, cap)
+            self._pinned_bufs[name] = cur
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(cur[0])
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def count_matrix(self, pinned: bool = False) -> CountMatrix:
+        """The CSC arrays. pinned=True reads them into page-locked buffers that this GemWell reuses on
+        the next call (the arrays of an earlier call are then overwritten)."""
         nb, nnz, nf = C.c_uint64(), C.c_uint64(), C.c_uint64()
         check(self.L.crgpu_matrix_dims(self._ctx, C.byref(nb), C.byref(nnz), C.byref(nf)), "crgpu_matrix_dims")
-        rank = np.zeros(nb.value, dtype=np.uint32)
-        indptr = np.zeros(nb.value + 1, dtype=np.int64)
-        indices = np.zeros(nnz.value, dtype=np.uint32)
-        data = np.zeros(nnz.value, dtype=np.int32)
+        mk = (lambda nm, sh, dt: self._pinned(nm, sh, dt)) if pinned else (lambda nm, sh, dt: np.zeros(sh, dtype=dt))
+        rank = mk("rank", (nb.value,), np.uint32)
+        indptr = mk("indptr", (nb.value + 1,), np.int64)
+        indices = mk("indices", (nnz.value,), np.uint32)
+        data = mk("data", (nnz.value,), np.int32)
         check(self.L.crgpu_matrix_get(self._ctx, ptr(rank), ptr(indptr), ptr(indices), ptr(data)), "crgpu_matrix_get")
-        return CountMatrix(self.barcode_seqs(rank), rank, indptr, indices, data, int(nf.value))
+        return CountMatrix(rank, indptr, indices, data, int(nf.value), resolve_barcodes=self.barcode_seqs)
 
     def molecules(self) -> np.ndarray:
         """UmiCount rows: (barcode column, library, feature, umi 2-bit, read_count)."""

@@ -378,25 +378,31 @@ __global__ void make_key2_kernel(const unsigned long long* __restrict__ dkeys, u
 // features, which is rare. Each distinct key hashes its (rank, library, umi) into a table of 2-bit
 // slots: the first visitor sets bit 0, any later visitor sets bit 1. Keys whose slot has bit 1 are the
 // candidates (all true groups plus hash collisions); only they are sorted and regrouped exactly.
-__device__ __forceinline__ unsigned long long group_hash(unsigned long long key, const KeyLayout& kl,
-                                                         const FieldMasks& fm) {
+// Slot of a key's (rank, library, umi) group. The table is split into regions of 2^17 slots (32 KB): the
+// region is chosen by the barcode rank alone, so the keys of one barcode - which are neighbours in the
+// sorted table and therefore processed together - stay inside one L2-resident region.
+#define LS_REGION_BITS 17
+__device__ __forceinline__ unsigned long long group_slot(unsigned long long key, const KeyLayout& kl,
+                                                         const FieldMasks& fm, int slot_bits) {
   unsigned long long umi = key & ((1ull << fm.ubits) - 1ull);
   unsigned long long lib = (key >> kl.lib_shift) & ((1ull << fm.lbits) - 1ull);
   unsigned long long rank = key >> kl.rank_shift;
-  unsigned long long g = ((rank << fm.lbits | lib) << fm.ubits) | umi;
-  g ^= g >> 31;
+  unsigned long long g = (lib << fm.ubits) | umi;
+  g ^= g >> 15;
   g *= 0x9E3779B97F4A7C15ull;
   g ^= g >> 29;
-  g *= 0xBF58476D1CE4E5B9ull;
-  g ^= g >> 32;
-  return g;
+  unsigned long long r = (rank + 0x632BE59BD9B4E019ull) * 0xBF58476D1CE4E5B9ull;
+  r ^= r >> 31;
+  if (slot_bits <= LS_REGION_BITS) return (g ^ r) >> (64 - slot_bits);
+  const int rbits = slot_bits - LS_REGION_BITS;
+  return ((r >> (64 - rbits)) << LS_REGION_BITS) | ((g ^ (r << 7)) >> (64 - LS_REGION_BITS));
 }
 
 __global__ void __launch_bounds__(256) ls_mark_kernel(const unsigned long long* __restrict__ dkeys, uint64_t m,
                                                       KeyLayout kl, uint32_t* __restrict__ slots, int slot_bits) {
   const FieldMasks fm = field_masks(kl);
   for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < m; j += (uint64_t)gridDim.x * blockDim.x) {
-    unsigned long long h = group_hash(dkeys[j], kl, fm) >> (64 - slot_bits);
+    unsigned long long h = group_slot(dkeys[j], kl, fm, slot_bits);
     uint32_t bit = 1u << (2 * (h & 15));
     uint32_t old = atomicOr(slots + (h >> 4), bit);
     if (old & bit) atomicOr(slots + (h >> 4), bit << 1);
@@ -417,7 +423,7 @@ __global__ void __launch_bounds__(256) ls_collect_kernel(const unsigned long lon
     unsigned long long k2 = 0;
     if (j < m) {
       unsigned long long k = dkeys[j];
-      unsigned long long h = group_hash(k, kl, fm) >> (64 - slot_bits);
+      unsigned long long h = group_slot(k, kl, fm, slot_bits);
       hit = (slots[h >> 4] >> (2 * (h & 15) + 1)) & 1u;
       if (hit) {
         unsigned long long umi = k & ((1ull << fm.ubits) - 1ull);
