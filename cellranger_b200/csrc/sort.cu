@@ -55,7 +55,20 @@ __global__ void radix_scan_hist_kernel(unsigned long long* hist) {
 // ---- one onesweep pass ----
 // desc[tile * RADIX + digit]: {status:2 | count:62} chained-scan descriptors of this pass.
 // One tile of one pass. FULL = the tile holds SORT_TILE keys (no bounds checks in the hot loops).
-template <int SORT_THREADS, int SORT_ITEMS, bool FULL>
+// lanes of the warp holding the same 9-bit value: eight ballots instead of match.any, whose cost grows with
+// the number of distinct values in the warp (about 30 for a uniformly distributed digit)
+__device__ __forceinline__ uint32_t match_digit(uint32_t digit) {
+  uint32_t peers = 0xFFFFFFFFu;
+#pragma unroll
+  for (int b = 0; b < RADIX_BITS + 1; b++) {
+    const bool bit = (digit >> b) & 1u;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
+    peers &= bit ? m : ~m;
+  }
+  return peers;
+}
+
+template <int SORT_THREADS, int SORT_ITEMS, bool FULL, bool BALLOT>
 __device__ __forceinline__ void onesweep_tile(const unsigned long long* __restrict__ in,
                                               unsigned long long* __restrict__ out, int cnt, uint64_t tile_first,
                                               uint32_t tile, int shift,
@@ -88,7 +101,7 @@ __device__ __forceinline__ void onesweep_tile(const unsigned long long* __restri
     const int idx = warp_first + k * 32 + lane;
     const bool valid = FULL || idx < cnt;
     const uint32_t digit = valid ? (uint32_t)((key[k] >> shift) & (RADIX - 1)) : (uint32_t)RADIX;
-    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, digit);
+    const uint32_t peers = BALLOT ? match_digit(digit) : __match_any_sync(0xFFFFFFFFu, digit);
     const int leader = __ffs(peers) - 1;
     uint32_t base = 0;
     if (lane == leader && valid) {
@@ -166,7 +179,7 @@ __device__ __forceinline__ void onesweep_tile(const unsigned long long* __restri
   }
 }
 
-template <int SORT_THREADS, int SORT_ITEMS, int MIN_BLOCKS>
+template <int SORT_THREADS, int SORT_ITEMS, int MIN_BLOCKS, bool BALLOT>
 __global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) radix_onesweep_kernel(
     const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, uint64_t n, int shift,
     const unsigned long long* __restrict__ bin_base, unsigned long long* __restrict__ desc,
@@ -184,9 +197,9 @@ __global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) radix_onesweep_kerne
   const uint64_t tile_first = (uint64_t)tile * SORT_TILE;
   const int cnt = (n - tile_first) < (uint64_t)SORT_TILE ? (int)(n - tile_first) : SORT_TILE;
   if (cnt == SORT_TILE)
-    onesweep_tile<SORT_THREADS, SORT_ITEMS, true>(in, out, cnt, tile_first, tile, shift, bin_base, desc, smem_raw);
+    onesweep_tile<SORT_THREADS, SORT_ITEMS, true, BALLOT>(in, out, cnt, tile_first, tile, shift, bin_base, desc, smem_raw);
   else
-    onesweep_tile<SORT_THREADS, SORT_ITEMS, false>(in, out, cnt, tile_first, tile, shift, bin_base, desc, smem_raw);
+    onesweep_tile<SORT_THREADS, SORT_ITEMS, false, BALLOT>(in, out, cnt, tile_first, tile, shift, bin_base, desc, smem_raw);
 }
 
 }  // namespace
@@ -218,7 +231,7 @@ int sort_histograms(const unsigned long long* keys, uint64_t n, int end_bit, voi
   return 2;
 }
 
-template <int THREADS, int ITEMS, int MIN_BLOCKS>
+template <int THREADS, int ITEMS, int MIN_BLOCKS, bool BALLOT>
 static int run_passes(unsigned long long* keys, unsigned long long* alt, uint64_t n, int n_passes, void* temp,
                       unsigned long long** out, cudaStream_t st) {
   constexpr int TILE = THREADS * ITEMS;
@@ -229,7 +242,7 @@ static int run_passes(unsigned long long* keys, unsigned long long* alt, uint64_
   unsigned long long* desc = reinterpret_cast<unsigned long long*>(t + (size_t)MAX_PASSES * RADIX * 8);
   uint32_t* ticket = reinterpret_cast<uint32_t*>(t + (size_t)MAX_PASSES * RADIX * 8 + (size_t)(max_tiles + 1) * RADIX * 8);
   const size_t smem = (size_t)TILE * 8 + (size_t)(THREADS / 32) * RADIX * 4 + RADIX * 4 + RADIX * 8 + RADIX * 4;
-  auto kern = radix_onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS>;
+  auto kern = radix_onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS, BALLOT>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int launches = 0;
   unsigned long long* src = keys;
@@ -252,11 +265,11 @@ int sort_passes(unsigned long long* keys, unsigned long long* alt, uint64_t n, i
   if (n <= 1) return 0;
   const int np = plan_passes(end_bit);
   const int cfg = getenv("CRGPU_SORT_CFG") ? atoi(getenv("CRGPU_SORT_CFG")) : 0;
-  switch (cfg) {  // CRGPU_SORT_CFG: tile shapes kept for profiling; 0 = the measured best on B200
-    case 1: return run_passes<512, 12, 2>(keys, alt, n, np, temp, out, st);
-    case 2: return run_passes<384, 16, 2>(keys, alt, n, np, temp, out, st);
-    case 3: return run_passes<384, 12, 3>(keys, alt, n, np, temp, out, st);
-    default: return run_passes<256, 16, 4>(keys, alt, n, np, temp, out, st);
+  switch (cfg) {  // CRGPU_SORT_CFG: variants kept for profiling; 0 = the measured best on B200
+    case 1: return run_passes<256, 16, 4, false>(keys, alt, n, np, temp, out, st);  // match.any instead of ballots
+    case 2: return run_passes<512, 12, 2, true>(keys, alt, n, np, temp, out, st);
+    case 3: return run_passes<384, 12, 3, true>(keys, alt, n, np, temp, out, st);
+    default: return run_passes<256, 16, 4, true>(keys, alt, n, np, temp, out, st);
   }
 }
 
