@@ -38,10 +38,12 @@ struct DevWhitelist {
   const uint32_t* offs[CRGPU_MAX_ORD];  // (1 << p) + 1 bucket starts
   int rot[CRGPU_MAX_ORD];
   uint32_t resp[CRGPU_MAX_ORD];  // bit `pos` set: this ordering answers for mutations at base `pos`
-  // exact membership: a finer bucket table over ordering 0 (about 1.5 entries per bucket): start index of
-  // the bucket q >> exact_shift. keys[0] carries four 0xFFFFFFFF sentinels past its end.
-  const uint32_t* exact_offs;
-  int exact_shift;
+  // exact membership: one 16-byte slot per bucket of the top (2L - slot_shift) key bits, fetched with a
+  // single 128-bit load: .x = index of the bucket's first entry in keys[0] (low 29 bits) | entry count
+  // (top 3 bits, 7 = more than six: search keys[0]); .y/.z/.w = up to six 16-bit key suffixes (the low
+  // slot_shift bits), 0xFFFF-padded.
+  const uint4* slots;
+  int slot_shift;
 };
 
 // how the 64-bit dedup key is laid out: rank | feature | library | umi
@@ -57,53 +59,54 @@ __device__ __forceinline__ uint32_t rotr_bits(uint32_t q, int r, int nbits) {
   return ((q >> r) | (q << (nbits - r))) & mask_bits(nbits);
 }
 
-// exact membership through ordering 0 (rot 0). Returns the entry index or -1.
-// Split in two so that callers can issue the loads of several independent lookups before resolving any:
-// wl_find_begin() loads the bucket start, wl_find_probe() the first two entries, wl_find_end() decides.
+// exact membership. Returns the index of the entry in keys[0] (sorted, rot 0) or -1.
+// Split in three so that callers can issue the loads of several independent lookups before resolving any.
 struct WlProbe {
-  uint32_t start, e0, e1, e2, e3;
+  uint4 slot;
 };
 __device__ __forceinline__ uint32_t wl_find_begin(const DevWhitelist& wl, uint32_t q) {
-  uint32_t b = wl.exact_shift >= 32 ? 0u : (q >> wl.exact_shift);
-  return __ldg(wl.exact_offs + b);
+  return wl.slot_shift >= 32 ? 0u : (q >> wl.slot_shift);  // bucket
 }
-__device__ __forceinline__ WlProbe wl_find_probe(const DevWhitelist& wl, uint32_t start) {
+__device__ __forceinline__ WlProbe wl_find_probe(const DevWhitelist& wl, uint32_t bucket) {
   WlProbe p;
-  p.start = start;
-  const uint32_t* __restrict__ k = wl.keys[0] + start;  // four sentinels follow the last key
-  p.e0 = __ldg(k);
-  p.e1 = __ldg(k + 1);
-  p.e2 = __ldg(k + 2);
-  p.e3 = __ldg(k + 3);
+  p.slot = __ldg(wl.slots + bucket);
   return p;
 }
 __device__ __forceinline__ int wl_find_end(const DevWhitelist& wl, const WlProbe& p, uint32_t q) {
-  uint32_t idx;
-  if (p.e0 >= q) {
-    if (p.e0 != q) return -1;
-    idx = p.start;
-  } else if (p.e1 >= q) {
-    if (p.e1 != q) return -1;
-    idx = p.start + 1;
-  } else if (p.e2 >= q) {
-    if (p.e2 != q) return -1;
-    idx = p.start + 2;
-  } else if (p.e3 >= q) {
-    if (p.e3 != q) return -1;
-    idx = p.start + 3;
-  } else {
-    const uint32_t* __restrict__ keys = wl.keys[0];
-    idx = p.start + 4;
-    while (true) {  // the keys are sorted and end with 0xFFFFFFFF sentinels
-      uint32_t e = __ldg(keys + idx);
-      if (e >= q) {
-        if (e != q) return -1;
-        break;
-      }
-      idx++;
-    }
+  const uint32_t cnt = p.slot.x >> 29, base = p.slot.x & 0x1FFFFFFFu;
+  if (cnt == 0u) return -1;
+  const uint32_t qs = q & mask_bits(wl.slot_shift);
+  if (cnt < 7u) {
+    const uint32_t qq = qs | (qs << 16);
+    const uint32_t x0 = p.slot.y ^ qq, x1 = p.slot.z ^ qq, x2 = p.slot.w ^ qq;
+    int j = -1;
+    if (!(x2 >> 16)) j = 5;
+    if (!(x2 & 0xFFFFu)) j = 4;
+    if (!(x1 >> 16)) j = 3;
+    if (!(x1 & 0xFFFFu)) j = 2;
+    if (!(x0 >> 16)) j = 1;
+    if (!(x0 & 0xFFFFu)) j = 0;
+    return (j >= 0 && (uint32_t)j < cnt) ? (int)(base + (uint32_t)j) : -1;
   }
-  return idx < wl.W ? (int)idx : -1;  // a hit on a sentinel is a miss
+  // crowded bucket (more than six entries): the first six are inline, the rest follow in the sorted keys
+  // (which end with 0xFFFFFFFF sentinels)
+  {
+    const uint32_t qq = qs | (qs << 16);
+    const uint32_t x0 = p.slot.y ^ qq, x1 = p.slot.z ^ qq, x2 = p.slot.w ^ qq;
+    if (!(x0 & 0xFFFFu)) return (int)base;
+    if (!(x0 >> 16)) return (int)base + 1;
+    if (!(x1 & 0xFFFFu)) return (int)base + 2;
+    if (!(x1 >> 16)) return (int)base + 3;
+    if (!(x2 & 0xFFFFu)) return (int)base + 4;
+    if (!(x2 >> 16)) return (int)base + 5;
+  }
+  const uint32_t* __restrict__ keys = wl.keys[0];
+  uint32_t idx = base + 6;
+  while (true) {
+    uint32_t e = __ldg(keys + idx);
+    if (e >= q) return (e == q && idx < wl.W) ? (int)idx : -1;
+    idx++;
+  }
 }
 __device__ __forceinline__ int wl_find(const DevWhitelist& wl, uint32_t q) {
   return wl_find_end(wl, wl_find_probe(wl, wl_find_begin(wl, q)), q);

@@ -464,21 +464,40 @@ int crgpu_whitelist_add(crgpu_ctx* c, const uint8_t* seqs, uint64_t n, int L, co
     CU(cudaMemcpy(dk.p, keys.data(), (size_t)(W + 4) * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dof.p, offs.data(), (n_buckets + 1) * 4, cudaMemcpyHostToDevice));
     if (o == 0) {
-      // finer table for exact membership: about 1.5 entries per bucket
+      // exact-membership slots: about 3 entries per bucket on average, six at most inline; the suffix kept in a
+      // slot must fit 16 bits
       int pe = 0;
       while (pe < nbits && (1ull << pe) < (uint64_t)W) pe++;  // ceil(log2 W)
-      if (pe > 0) pe -= 1;                                     // 1..2 entries per bucket
+      pe = pe > 2 ? pe - 2 : 0;  // about 3 entries per bucket: the table stays small enough for L2
+      if (pe < nbits - 16) pe = nbits - 16;
       if (pe > 26) pe = 26;
-      const int eshift = nbits - pe;
+      if (pe > nbits) pe = nbits;
+      const int sshift = nbits - pe;
       const uint64_t nb = 1ull << pe;
-      std::vector<uint32_t> eo(nb + 1, 0);
-      for (uint32_t i = 0; i < W; i++) eo[(eshift >= 32 ? 0 : (keys[i] >> eshift)) + 1]++;
-      for (uint64_t b = 0; b < nb; b++) eo[b + 1] += eo[b];
+      std::vector<uint4> slots(nb, make_uint4(0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu));
+      {
+        uint32_t i = 0;
+        while (i < W) {
+          const uint64_t b = sshift >= 32 ? 0 : (keys[i] >> sshift);
+          uint32_t j = i;
+          while (j < W && (sshift >= 32 ? 0 : (keys[j] >> sshift)) == b) j++;
+          const uint32_t cnt = j - i;
+          uint16_t suf[6] = {0xFFFF, 0xFFFF, 0xFFFF, 0xFFFF, 0xFFFF, 0xFFFF};
+          for (uint32_t k = 0; k < cnt && k < 6; k++) suf[k] = (uint16_t)(keys[i + k] & ((sshift >= 32) ? 0xFFFFFFFFu : ((1u << sshift) - 1u)));
+          uint4 v;
+          v.x = i | ((cnt <= 6 ? cnt : 7u) << 29);
+          v.y = suf[0] | ((uint32_t)suf[1] << 16);
+          v.z = suf[2] | ((uint32_t)suf[3] << 16);
+          v.w = suf[4] | ((uint32_t)suf[5] << 16);
+          slots[b] = v;
+          i = j;
+        }
+      }
       DevBuf de;
-      if ((rc = de.ensure((nb + 1) * 4))) return rc;
-      CU(cudaMemcpy(de.p, eo.data(), (nb + 1) * 4, cudaMemcpyHostToDevice));
-      w->dev.exact_offs = de.as<uint32_t>();
-      w->dev.exact_shift = eshift;
+      if ((rc = de.ensure(nb * sizeof(uint4)))) return rc;
+      CU(cudaMemcpy(de.p, slots.data(), nb * sizeof(uint4), cudaMemcpyHostToDevice));
+      w->dev.slots = de.as<uint4>();
+      w->dev.slot_shift = sshift;
       w->bufs.push_back(de);
     }
     w->dev.keys[o] = dk.as<uint32_t>();
