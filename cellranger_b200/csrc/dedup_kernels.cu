@@ -165,19 +165,36 @@ __device__ __forceinline__ void cu_build(const unsigned long long* w_key, int n,
 // Two phases so that a warp does not diverge on every mutant: first all mutants are tested against the
 // bitmap (straight-line code, one shared load each) into a candidate mask, then only the few candidates
 // (bitmap false positives and true neighbours) are looked up in the hash set.
-template <typename Hit>
+// UB > 0: the UMI width in bits is a compile-time constant and the mutant loop is fully unrolled
+// (constant shifts, constant mask bits); UB == 0: generic width `ub`.
+template <int UB, typename Hit>
 __device__ __forceinline__ void cu_probe(const unsigned long long* w_key, const uint32_t* table,
                                          const uint32_t* bitmap, unsigned long long key, int ub, Hit hit) {
   const uint32_t lo = (uint32_t)key, hm = cu_hi_mix(key);
-  unsigned long long cand = 0ull;
-  int m_idx = 0;
-  for (int sh = 0; sh < ub; sh += 2) {
+  uint32_t cand_lo = 0u, cand_hi = 0u;  // bit m = mutant m (3 per base, base 0 = least significant)
+  if constexpr (UB > 0) {
 #pragma unroll
-    for (uint32_t d = 1; d < 4; d++, m_idx++) {
-      const uint32_t b = cu_bit(cu_mix(lo ^ (d << sh), hm));
-      cand |= (unsigned long long)((bitmap[b >> 5] >> (b & 31)) & 1u) << m_idx;
+    for (int m = 0; m < 3 * (UB / 2); m++) {
+      const uint32_t b = cu_bit(cu_mix(lo ^ ((uint32_t)(m % 3 + 1) << (2 * (m / 3))), hm));
+      const uint32_t bit = (bitmap[b >> 5] >> (b & 31)) & 1u;
+      if (m < 32)
+        cand_lo |= bit << (m & 31);
+      else
+        cand_hi |= bit << (m & 31);
     }
+  } else {
+    int m = 0;
+    for (int sh = 0; sh < ub; sh += 2)
+      for (uint32_t d = 1; d < 4; d++, m++) {
+        const uint32_t b = cu_bit(cu_mix(lo ^ (d << sh), hm));
+        const uint32_t bit = (bitmap[b >> 5] >> (b & 31)) & 1u;
+        if (m < 32)
+          cand_lo |= bit << (m & 31);
+        else
+          cand_hi |= bit << (m & 31);
+      }
   }
+  unsigned long long cand = ((unsigned long long)cand_hi << 32) | cand_lo;
   while (cand) {
     const int mi = __ffsll((long long)cand) - 1;
     cand &= cand - 1ull;
@@ -196,6 +213,7 @@ __device__ __forceinline__ void cu_probe(const unsigned long long* w_key, const 
   }
 }
 
+template <int UB>
 __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsigned long long* __restrict__ dkeys,
                                                                      const uint32_t* __restrict__ c0, uint64_t m,
                                                                      KeyLayout kl, uint32_t corr_mask,
@@ -261,7 +279,7 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
     const unsigned long long key = w_key[i];
     BestPick bp{0u, key & umask, (uint32_t)j};
     bool have_own = false;
-    cu_probe(w_key, table, bitmap, key, ub, [&](uint32_t idx) {
+    cu_probe<UB>(w_key, table, bitmap, key, ub, [&](uint32_t idx) {
       if (!have_own) {
         bp.count = c0[j];
         have_own = true;
@@ -312,7 +330,7 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
           if ((key >> ub) != seg_s) continue;
           const uint32_t cur = best[j];
           BestPick bp{c0[cur], dkeys[cur] & umask, cur};
-          cu_probe(w_key, table, bitmap, key, ub, [&](uint32_t idx) {
+          cu_probe<UB>(w_key, table, bitmap, key, ub, [&](uint32_t idx) {
             bp.consider(c0[a + idx], w_key[idx] & umask, (uint32_t)(a + idx));
           });
           if (bp.idx != cur) best[j] = bp.idx;
@@ -713,14 +731,11 @@ int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
   cudaMemsetAsync(b.low, 0, m, st);
   {
     const size_t smem = (size_t)CU_WIN * 8 + (size_t)CU_SLOTS * 4 + (size_t)CU_BITS / 8 + (size_t)CU_TILE * 2;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(correct_umis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr_set = true;
-    }
+    auto kern = b.kl.umi_bits == 24 ? correct_umis_kernel<24>
+                : b.kl.umi_bits == 20 ? correct_umis_kernel<20> : correct_umis_kernel<0>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const unsigned blocks = (unsigned)((m + CU_TILE - 1) / CU_TILE);
-    correct_umis_kernel<<<blocks, CU_THREADS, smem, st>>>(b.dkeys, b.c0, m, b.kl, b.umi_correction_mask, b.best,
-                                                          b.inc, b.scalars);
+    kern<<<blocks, CU_THREADS, smem, st>>>(b.dkeys, b.c0, m, b.kl, b.umi_correction_mask, b.best, b.inc, b.scalars);
     launches++;
   }
   mark("count.dedup.low_support");
