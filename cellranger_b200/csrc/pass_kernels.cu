@@ -879,70 +879,122 @@ __device__ __forceinline__ int fb_find(const uint32_t* __restrict__ keys, int n,
   return -1;
 }
 
-__global__ void __launch_bounds__(256) fb_kernel(const FbArgs a) {
-  extern __shared__ uint32_t s_fb[];  // keys[n_fb] | index[n_fb]
-  uint32_t* s_keys = s_fb;
-  uint32_t* s_index = s_fb + a.n_fb;
-  for (int i = threadIdx.x; i < a.n_fb; i += blockDim.x) {
+constexpr int FB_THREADS = 256;
+constexpr int FB_RPT = 8;
+constexpr int FB_TILE = FB_THREADS * FB_RPT;
+
+// Phase A of a tile: every read's capture is packed and looked up exactly; the captures that miss (and may
+// be corrected) are compacted into a shared-memory work list. Phase B corrects the list densely - otherwise
+// every warp would walk the 3L mutants because one of its lanes has to.
+__global__ void __launch_bounds__(FB_THREADS) fb_kernel(const FbArgs a) {
+  extern __shared__ __align__(16) uint32_t s_fb[];
+  uint32_t* s_keys = s_fb;                   // n_fb sorted packed feature sequences
+  uint32_t* s_index = s_fb + a.n_fb;         // n_fb feature indices
+  uint32_t* s_cnt = s_fb + 2 * a.n_fb;       // n_fb exact-hit counters
+  uint32_t* w_q = s_fb + 3 * a.n_fb;         // FB_TILE: packed capture of a work item
+  uint32_t* w_meta = w_q + FB_TILE;          // FB_TILE: index in tile | (non-ACGT position + 1) << 16
+  uint4* w_qual = reinterpret_cast<uint4*>(s_fb + ((3 * a.n_fb + 2 * FB_TILE + 3) & ~3));  // FB_TILE quality words
+  __shared__ uint32_t s_nwork;
+  for (int i = threadIdx.x; i < a.n_fb; i += FB_THREADS) {
     s_keys[i] = a.fb_keys[i];
     s_index[i] = a.fb_index[i];
+    s_cnt[i] = 0;
   }
-  __syncthreads();
-  for (uint64_t gi = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; gi < a.n; gi += (uint64_t)gridDim.x * blockDim.x) {
-    uint32_t out = NO_FEATURE;
-    if (a.r2_len >= a.fb_off + a.fb_len) {
-      const uint8_t* s = a.r2_seq + gi * a.r2_len + a.fb_off;
-      const uint8_t* qp = a.r2_qual + gi * a.r2_len + a.fb_off;
-      uint32_t q = 0, nmask = 0;
-      for (int i = 0; i < a.fb_len; i++) {
-        uint8_t c = s[i];
-        uint32_t code = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
-        if (code == 4u) {
-          nmask |= 1u << i;
-          code = 0u;
+  const uint64_t n_tiles = (a.n + FB_TILE - 1) / FB_TILE;
+  const bool fits = a.r2_len >= a.fb_off + a.fb_len;
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (threadIdx.x == 0) s_nwork = 0;
+    __syncthreads();
+    const uint64_t first = tile * FB_TILE;
+#pragma unroll 2
+    for (int k = 0; k < FB_RPT; k++) {
+      const uint64_t gi = first + (uint64_t)k * FB_THREADS + threadIdx.x;
+      if (gi >= a.n) break;
+      uint32_t out = NO_FEATURE;
+      if (fits) {
+        const uint4 sq = load_bytes16(a.r2_seq + gi * a.r2_len + a.fb_off);
+        const uint32_t sw[4] = {sq.x, sq.y, sq.z, sq.w};
+        uint32_t q = 0, nmask = 0;
+#pragma unroll
+        for (int wd = 0; wd < 4; wd++) {
+          const int left = a.fb_len - 4 * wd;  // bases of the capture in this word
+          if (left <= 0) break;
+          uint32_t w = sw[wd];
+          const uint32_t bmask = left >= 4 ? 0xFFFFFFFFu : ((1u << (8 * left)) - 1u);
+          w = (w & bmask) | (0x41414141u & ~bmask);
+          uint32_t bad;
+          uint32_t pk = pack4(w, &bad);
+          bad &= bmask;
+          if (bad) {
+#pragma unroll
+            for (int by = 0; by < 4; by++)
+              if (bad & (0x80u << (8 * by))) nmask |= 1u << (wd * 4 + by);
+          }
+          q = left >= 4 ? ((q << 8) | pk) : ((q << (2 * left)) | (pk >> (2 * (4 - left))));
         }
-        q = (q << 2) | code;
+        int hit = nmask ? -1 : fb_find(s_keys, a.n_fb, q);
+        if (hit >= 0) {
+          out = s_index[hit];
+          if (a.exact_counts) atomicAdd(&s_cnt[hit], 1u);  // a few hundred hot features: count per block
+        } else if (a.feat_dist && (nmask & (nmask - 1u)) == 0u) {
+          const uint32_t slot = atomicAdd(&s_nwork, 1u);
+          w_q[slot] = q;
+          w_meta[slot] = (uint32_t)(k * FB_THREADS + threadIdx.x) | ((nmask ? (uint32_t)__ffs(nmask) : 0u) << 16);
+          w_qual[slot] = load_bytes16(a.r2_qual + gi * a.r2_len + a.fb_off);
+        }
       }
-      int hit = nmask ? -1 : fb_find(s_keys, a.n_fb, q);
-      if (hit >= 0) {
-        out = s_index[hit];
-      } else if (a.feat_dist && (nmask & (nmask - 1u)) == 0u) {
-        // correct_feature_barcode for a single candidate: trials in (position, A,C,G,T) order
-        double sum = 0.0, best = -1.0;
-        uint32_t best_f = NO_FEATURE;
-        for (int i = 0; i < a.fb_len; i++) {
-          if (nmask && !((nmask >> i) & 1u)) continue;  // other positions keep the N and cannot match
-          int sh = 2 * (a.fb_len - 1 - i);
-          uint32_t orig = nmask ? 4u : ((q >> sh) & 3u);
-          for (uint32_t b = 0; b < 4; b++) {
-            if (b == orig) continue;
-            uint32_t trial = (q & ~(3u << sh)) | (b << sh);
-            int h = fb_find(s_keys, a.n_fb, trial);
-            if (h < 0) continue;
-            uint32_t f = s_index[h];
-            uint32_t qv = (uint8_t)(qp[i] - 33);
-            if (qv > 33u) qv = 33u;  // FEATURE_MAX_QV
-            double lik = __dmul_rn(a.feat_dist[f], c_fb_prob[qv]);
-            sum = __dadd_rn(sum, lik);
-            if (lik > best) {
-              best = lik;
-              best_f = f;
-            }
+      if (a.feature_out) a.feature_out[gi] = out;
+    }
+    __syncthreads();
+    // phase B: correct_feature_barcode for a single candidate, trials in (position, A,C,G,T) order
+    const uint32_t nwork = s_nwork;
+    for (uint32_t wi = threadIdx.x; wi < nwork; wi += FB_THREADS) {
+      const uint32_t q = w_q[wi];
+      const uint32_t meta = w_meta[wi];
+      const int npos = (int)(meta >> 16) - 1;  // position of the single non-ACGT base, or -1
+      const uint4 qq = w_qual[wi];
+      const uint32_t qw[4] = {qq.x, qq.y, qq.z, qq.w};
+      double sum = 0.0, best = -1.0;
+      uint32_t best_f = NO_FEATURE;
+      for (int i = 0; i < a.fb_len; i++) {
+        if (npos >= 0 && i != npos) continue;  // the other positions keep the N and cannot match
+        const int sh = 2 * (a.fb_len - 1 - i);
+        const uint32_t orig = npos >= 0 ? 4u : ((q >> sh) & 3u);
+        for (uint32_t b = 0; b < 4; b++) {
+          if (b == orig) continue;
+          const uint32_t trial = (q & ~(3u << sh)) | (b << sh);
+          const int h = fb_find(s_keys, a.n_fb, trial);
+          if (h < 0) continue;
+          const uint32_t f = s_index[h];
+          uint32_t qv = (uint8_t)((uint8_t)(qw[i >> 2] >> (8 * (i & 3))) - 33);
+          if (qv > 33u) qv = 33u;  // FEATURE_MAX_QV
+          const double lik = __dmul_rn(a.feat_dist[f], c_fb_prob[qv]);
+          sum = __dadd_rn(sum, lik);
+          if (lik > best) {
+            best = lik;
+            best_f = f;
           }
         }
-        if (best_f != NO_FEATURE && __ddiv_rn(best, sum) >= a.threshold) out = best_f;
       }
-      if (a.exact_counts && hit >= 0) atomicAdd(a.exact_counts + out, 1ull);
+      if (best_f != NO_FEATURE && __ddiv_rn(best, sum) >= a.threshold && a.feature_out)
+        a.feature_out[first + (meta & 0xFFFFu)] = best_f;
     }
-    if (a.feature_out) a.feature_out[gi] = out;
+    __syncthreads();
+  }
+  if (a.exact_counts) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.n_fb; i += FB_THREADS)
+      if (s_cnt[i]) atomicAdd(a.exact_counts + s_index[i], (unsigned long long)s_cnt[i]);
   }
 }
 
 int launch_fb(const FbArgs& a, cudaStream_t st) {
   if (a.n == 0) return 0;
-  uint64_t blocks = (a.n + 255) / 256;
-  int grid = (int)std::min<uint64_t>(blocks, 148ull * 8);
-  fb_kernel<<<grid, 256, (size_t)a.n_fb * 8, st>>>(a);
+  uint64_t tiles = (a.n + FB_TILE - 1) / FB_TILE;
+  int grid = (int)std::min<uint64_t>(tiles, 148ull * 3);
+  size_t smem = (((size_t)3 * a.n_fb + 2 * FB_TILE + 3) & ~(size_t)3) * 4 + (size_t)FB_TILE * 16;
+  cudaFuncSetAttribute(fb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  fb_kernel<<<grid, FB_THREADS, smem, st>>>(a);
   return 1;
 }
 
