@@ -203,6 +203,8 @@ def run_ours(args):
     reads_dev = synth_device.generate_device(gw, tables, rank * n_per, n_per, "gex")
     ext = torch.cuda.ExternalStream(gw.stream(), device=dev)
     engine = crdist.TorchEngine(gw, len(libs))
+    if world > 1 and not os.environ.get("CRGPU_NO_P2P"):
+        engine.setup_peer_exchange(rank, world, capacity_keys=int(n_per * 1.25))
     sharded = crdist.ShardedGemWell(engine, rank, world)
 
     def barrier():

@@ -408,6 +408,30 @@ class GemWell:
     def keys_set(self, dev_ptr: int, n: int):
         check(self.L.crgpu_keys_set(self._ctx, C.c_void_p(dev_ptr), C.c_uint64(n)), "crgpu_keys_set")
 
+    # ---- fused key exchange over peer memory (CUDA IPC + NVLink stores) ----
+    def exchange_init(self, capacity_keys: int) -> bytes:
+        h = (C.c_uint8 * 128)()
+        check(self.L.crgpu_exchange_init(self._ctx, C.c_uint64(capacity_keys), h), "crgpu_exchange_init")
+        return bytes(h)
+
+    def exchange_connect(self, n_ranks: int, my_rank: int, handles: bytes):
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        check(self.L.crgpu_exchange_connect(self._ctx, n_ranks, my_rank, buf), "crgpu_exchange_connect")
+
+    def exchange_reset(self):
+        check(self.L.crgpu_exchange_reset(self._ctx), "crgpu_exchange_reset")
+
+    def keys_scatter_peers(self, bounds) -> np.ndarray:
+        b = np.ascontiguousarray(bounds, dtype=np.uint32)
+        out = np.zeros(b.shape[0] - 1, dtype=np.uint64)
+        check(self.L.crgpu_keys_scatter_peers(self._ctx, b.shape[0] - 1, ptr(b), ptr(out)), "crgpu_keys_scatter_peers")
+        return out
+
+    def exchange_finish(self) -> int:
+        n = C.c_uint64()
+        check(self.L.crgpu_exchange_finish(self._ctx, C.byref(n)), "crgpu_exchange_finish")
+        return int(n.value)
+
     def set_owned_range(self, lo: int, hi: int):
         check(self.L.crgpu_set_owned_range(self._ctx, C.c_uint32(lo), C.c_uint32(hi)))
 

@@ -147,6 +147,15 @@ struct crgpu_ctx {
   uint32_t own_lo = 0, own_hi = 0xFFFFFFFFu;
   bool annotated = false;
 
+  // fused exchange over peer memory
+  void* xchg_buf = nullptr;     // this rank's receive buffer (cudaMalloc, exported through CUDA IPC)
+  void* xchg_cursor = nullptr;  // u64[2]: keys received, overflow flag
+  uint64_t xchg_capacity = 0;
+  int xchg_ranks = 0, xchg_rank = -1;
+  unsigned long long* peer_buf[CRGPU_MAX_PARTS] = {nullptr};
+  unsigned long long* peer_cursor[CRGPU_MAX_PARTS] = {nullptr};
+  bool peer_opened[CRGPU_MAX_PARTS] = {false};
+
   uint64_t stats[CRGPU_STAT_COUNT] = {0};
   uint64_t launches = 0;
 
@@ -368,6 +377,13 @@ void crgpu_ctx_destroy(crgpu_ctx* c) {
     cudaEventDestroy(p.second.first);
     cudaEventDestroy(p.second.second);
   }
+  for (int r = 0; r < CRGPU_MAX_PARTS; r++)
+    if (c->peer_opened[r]) {
+      cudaIpcCloseMemHandle(c->peer_buf[r]);
+      cudaIpcCloseMemHandle(c->peer_cursor[r]);
+    }
+  if (c->xchg_buf) cudaFree(c->xchg_buf);
+  if (c->xchg_cursor) cudaFree(c->xchg_cursor);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1045,6 +1061,97 @@ int crgpu_valid_counts_refresh(crgpu_ctx* c) {
                                        c->content.size(), c->stream);
     CHECK_KERNEL();
   }
+  return CRGPU_OK;
+}
+
+int crgpu_exchange_init(crgpu_ctx* c, uint64_t capacity_keys, void* out_handle) {
+  if (!c || !out_handle || capacity_keys == 0) return fail(CRGPU_E_INVALID, "bad argument");
+  if (c->xchg_buf) return fail(CRGPU_E_INVALID, "exchange already initialised");
+  CU(cudaSetDevice(c->device));
+  cudaError_t e = cudaMalloc(&c->xchg_buf, capacity_keys * 8);
+  if (e != cudaSuccess) return fail(CRGPU_E_NOMEM, std::string("exchange buffer: ") + cudaGetErrorString(e));
+  e = cudaMalloc(&c->xchg_cursor, 16);
+  if (e != cudaSuccess) return fail(CRGPU_E_NOMEM, std::string("exchange cursor: ") + cudaGetErrorString(e));
+  CU(cudaMemset(c->xchg_cursor, 0, 16));
+  c->xchg_capacity = capacity_keys;
+  cudaIpcMemHandle_t h[2];
+  CU(cudaIpcGetMemHandle(&h[0], c->xchg_buf));
+  CU(cudaIpcGetMemHandle(&h[1], c->xchg_cursor));
+  static_assert(sizeof(h) == CRGPU_IPC_HANDLE_BYTES, "IPC handle size");
+  memcpy(out_handle, h, sizeof(h));
+  return CRGPU_OK;
+}
+
+int crgpu_exchange_connect(crgpu_ctx* c, int32_t n_ranks, int32_t my_rank, const void* handles) {
+  if (!c || !handles || n_ranks < 1 || n_ranks > CRGPU_MAX_PARTS || my_rank < 0 || my_rank >= n_ranks)
+    return fail(CRGPU_E_INVALID, "bad argument");
+  if (!c->xchg_buf) return fail(CRGPU_E_INVALID, "crgpu_exchange_init must run first");
+  CU(cudaSetDevice(c->device));
+  const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(handles);
+  for (int r = 0; r < n_ranks; r++) {
+    if (r == my_rank) {
+      c->peer_buf[r] = static_cast<unsigned long long*>(c->xchg_buf);
+      c->peer_cursor[r] = static_cast<unsigned long long*>(c->xchg_cursor);
+      continue;
+    }
+    void *pb = nullptr, *pc = nullptr;
+    CU(cudaIpcOpenMemHandle(&pb, h[2 * r], cudaIpcMemLazyEnablePeerAccess));
+    CU(cudaIpcOpenMemHandle(&pc, h[2 * r + 1], cudaIpcMemLazyEnablePeerAccess));
+    c->peer_buf[r] = static_cast<unsigned long long*>(pb);
+    c->peer_cursor[r] = static_cast<unsigned long long*>(pc);
+    c->peer_opened[r] = true;
+  }
+  c->xchg_ranks = n_ranks;
+  c->xchg_rank = my_rank;
+  return CRGPU_OK;
+}
+
+int crgpu_exchange_reset(crgpu_ctx* c) {
+  if (!c || !c->xchg_cursor) return fail(CRGPU_E_INVALID, "exchange not initialised");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemsetAsync(c->xchg_cursor, 0, 16, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return CRGPU_OK;
+}
+
+int crgpu_keys_scatter_peers(crgpu_ctx* c, int32_t n_parts, const uint32_t* bounds, uint64_t* out_sent) {
+  if (!c || !bounds || n_parts != c->xchg_ranks) return fail(CRGPU_E_INVALID, "bad argument / exchange not connected");
+  if (c->stage < 2) return fail(CRGPU_E_INVALID, "crgpu_pass2 must run first");
+  CU(cudaSetDevice(c->device));
+  int rc;
+  if ((rc = fetch_n_keys(c))) return rc;
+  for (int p = 0; p < n_parts; p++)
+    if (bounds[p] > bounds[p + 1]) return fail(CRGPU_E_INVALID, "bounds must be non-decreasing");
+  unsigned long long* d_sent = c->scalars.as<unsigned long long>() + 16;
+  c->launches += run_owner_scatter_peers(c->keys.as<unsigned long long>(), c->n_keys, c->kl.rank_shift, bounds, n_parts,
+                                         c->peer_buf, c->peer_cursor, c->xchg_capacity, d_sent, c->stream);
+  CHECK_KERNEL();
+  unsigned long long h[CRGPU_MAX_PARTS] = {0};
+  CU(cudaMemcpyAsync(h, d_sent, n_parts * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));  // this rank's peer stores are complete
+  if (out_sent)
+    for (int p = 0; p < n_parts; p++) out_sent[p] = h[p];
+  return CRGPU_OK;
+}
+
+int crgpu_exchange_finish(crgpu_ctx* c, uint64_t* out_received) {
+  if (!c || !c->xchg_cursor) return fail(CRGPU_E_INVALID, "exchange not initialised");
+  CU(cudaSetDevice(c->device));
+  unsigned long long h[2] = {0, 0};
+  CU(cudaMemcpyAsync(h, c->xchg_cursor, 16, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (h[1] || h[0] > c->xchg_capacity)
+    return fail(CRGPU_E_LIMIT, "exchange buffer overflow: " + std::to_string(h[0]) + " keys for a capacity of " +
+                                   std::to_string(c->xchg_capacity));
+  int rc;
+  if ((rc = ensure_layout(c))) return rc;
+  if ((rc = c->keys.ensure(h[0] * 8 + 16))) return rc;
+  if ((rc = c->keys_alt.ensure(h[0] * 8 + 16))) return rc;
+  if (h[0]) CU(cudaMemcpyAsync(c->keys.p, c->xchg_buf, h[0] * 8, cudaMemcpyDeviceToDevice, c->stream));
+  c->n_keys = h[0];
+  c->keys_external = true;
+  if (c->stage < 2) c->stage = 2;
+  if (out_received) *out_received = h[0];
   return CRGPU_OK;
 }
 

@@ -659,6 +659,114 @@ int run_owner_partition(const unsigned long long* keys, uint64_t n, int rank_shi
   return launches;
 }
 
+// ---------------------------------------------------------------------------
+// Fused exchange: the same grouping by owner, but every key is stored straight into the owner GPU's
+// receive buffer over NVLink (peer pointers mapped through CUDA IPC). A block takes a chunk of PX_CHUNK
+// keys, orders it by owner in shared memory, claims one range per owner with a single remote atomicAdd
+// on that owner's cursor and writes each owner's run with coalesced peer stores.
+// ---------------------------------------------------------------------------
+constexpr int PX_THREADS = 256;
+constexpr int PX_ITEMS = 16;
+constexpr int PX_CHUNK = PX_THREADS * PX_ITEMS;  // 4096 keys = 32 KB
+
+struct PeerTargets {
+  unsigned long long* buf[CRGPU_MAX_PARTS];
+  unsigned long long* cursor[CRGPU_MAX_PARTS];  // [0] keys received so far, [1] overflow flag
+  unsigned long long capacity;
+};
+
+__global__ void __launch_bounds__(PX_THREADS) owner_scatter_peers_kernel(const unsigned long long* __restrict__ keys,
+                                                                        uint64_t n, int rank_shift, OwnerBounds ob,
+                                                                        PeerTargets pt,
+                                                                        unsigned long long* __restrict__ sent) {
+  __shared__ unsigned long long s_keys[PX_CHUNK];
+  __shared__ uint32_t s_cnt[CRGPU_MAX_PARTS], s_off[CRGPU_MAX_PARTS + 1], s_fill[CRGPU_MAX_PARTS];
+  __shared__ unsigned long long s_base[CRGPU_MAX_PARTS];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint64_t n_chunks = (n + PX_CHUNK - 1) / PX_CHUNK;
+  for (uint64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    if (tid < CRGPU_MAX_PARTS) {
+      s_cnt[tid] = 0;
+      s_fill[tid] = 0;
+    }
+    __syncthreads();
+    const uint64_t first = chunk * PX_CHUNK;
+    unsigned long long k[PX_ITEMS];
+    int own[PX_ITEMS];
+#pragma unroll
+    for (int i = 0; i < PX_ITEMS; i++) {
+      const uint64_t g = first + (uint64_t)i * PX_THREADS + tid;
+      own[i] = -1;
+      if (g < n) {
+        k[i] = __ldcs(keys + g);
+        own[i] = owner_of(ob, (uint32_t)(k[i] >> rank_shift));
+      }
+      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, own[i]);
+      if (own[i] >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[own[i]], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t run = 0;
+      for (int p = 0; p < ob.n; p++) {
+        s_off[p] = run;
+        run += s_cnt[p];
+      }
+      s_off[ob.n] = run;
+    }
+    // one remote claim per owner and chunk
+    if (tid < ob.n && s_cnt[tid]) {
+      unsigned long long b = atomicAdd(pt.cursor[tid], (unsigned long long)s_cnt[tid]);
+      if (b + s_cnt[tid] > pt.capacity) {
+        atomicExch(pt.cursor[tid] + 1, 1ull);  // the receiver reports the overflow
+        b = ~0ull;
+      }
+      s_base[tid] = b;
+      atomicAdd(sent + tid, (unsigned long long)s_cnt[tid]);
+    }
+    __syncthreads();
+    // order the chunk by owner in shared memory
+#pragma unroll
+    for (int i = 0; i < PX_ITEMS; i++) {
+      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, own[i]);
+      const int leader = __ffs(peers) - 1;
+      uint32_t base = 0;
+      if (own[i] >= 0 && lane == leader) base = atomicAdd(&s_fill[own[i]], (uint32_t)__popc(peers));
+      base = __shfl_sync(0xFFFFFFFFu, base, leader);
+      if (own[i] >= 0) s_keys[s_off[own[i]] + base + __popc(peers & ((1u << lane) - 1u))] = k[i];
+    }
+    __syncthreads();
+    // coalesced peer stores, one owner run after the other
+    const uint32_t total = s_off[ob.n];
+    for (uint32_t p = tid; p < total; p += PX_THREADS) {
+      int o = 0;
+      while (p >= s_off[o + 1]) o++;
+      const unsigned long long b = s_base[o];
+      if (b != ~0ull) pt.buf[o][b + (p - s_off[o])] = s_keys[p];
+    }
+    __syncthreads();
+  }
+}
+
+int run_owner_scatter_peers(const unsigned long long* keys, uint64_t n, int rank_shift, const uint32_t* bounds,
+                            int n_parts, unsigned long long* const* peer_buf, unsigned long long* const* peer_cursor,
+                            unsigned long long capacity, unsigned long long* d_sent, cudaStream_t st) {
+  OwnerBounds ob;
+  ob.n = n_parts;
+  for (int i = 0; i <= CRGPU_MAX_PARTS; i++) ob.b[i] = i <= n_parts ? bounds[i] : 0xFFFFFFFFu;
+  PeerTargets pt;
+  for (int i = 0; i < CRGPU_MAX_PARTS; i++) {
+    pt.buf[i] = i < n_parts ? peer_buf[i] : nullptr;
+    pt.cursor[i] = i < n_parts ? peer_cursor[i] : nullptr;
+  }
+  pt.capacity = capacity;
+  cudaMemsetAsync(d_sent, 0, CRGPU_MAX_PARTS * 8, st);
+  if (!n) return 0;
+  uint64_t chunks = (n + PX_CHUNK - 1) / PX_CHUNK;
+  int grid = (int)std::min<uint64_t>(chunks, 148ull * 4);
+  owner_scatter_peers_kernel<<<grid, PX_THREADS, 0, st>>>(keys, n, rank_shift, ob, pt, d_sent);
+  return 1;
+}
+
 // per-read barcode states of a batch (local statistics; the histograms may hold global counts)
 __global__ void state_counts_kernel(const uint32_t* __restrict__ bc_out, uint64_t n, unsigned long long* out4) {
   unsigned long long c1 = 0, c2 = 0, c3 = 0;

@@ -140,6 +140,9 @@ int run_matrix(DedupBuffers& b, MatrixArgs& m, uint64_t nnz, uint64_t n_mol, uin
 
 int run_owner_partition(const unsigned long long* keys, uint64_t n, int rank_shift, const uint32_t* bounds, int n_parts,
                         unsigned long long* out, unsigned long long* scratch, uint64_t* counts_host, cudaStream_t st);
+int run_owner_scatter_peers(const unsigned long long* keys, uint64_t n, int rank_shift, const uint32_t* bounds,
+                            int n_parts, unsigned long long* const* peer_buf, unsigned long long* const* peer_cursor,
+                            unsigned long long capacity, unsigned long long* d_sent, cudaStream_t st);
 int launch_state_counts(const uint32_t* bc_out, uint64_t n, unsigned long long* out4, cudaStream_t st);
 
 struct AnnotateArgs {

@@ -11,7 +11,9 @@ stages/align_and_count.rs:519-524); priors are summed over every chunk in the MA
   3. every rank corrects its own invalid reads                    (local)
   4. all-reduce(sum) of the corrected-read counts; prior + corrected = the valid-barcode counts
      (barcode index) → owner ranges of contiguous content ranks balanced by read count
-  5. one all-to-all of the packed 64-bit keys to the rank that owns their barcode
+  5. the packed 64-bit keys go to the rank that owns their barcode: fused scatter into the owner's
+     receive buffer through peer memory (NVLink stores, CUDA IPC mapping), or - when the GPUs have no peer
+     access - grouping by owner plus one NCCL all-to-all
   6. dedup + counting, shard-local; the matrix is the concatenation of the ranks' column blocks
 
 `ShardedGemWell` only talks to an *engine* (the GPU GemWell through TorchEngine below); the host
@@ -47,6 +49,34 @@ class TorchEngine:
         self.n_libs = n_libs
         self.device = torch.device("cuda", gw.device)
         self._recv = None
+        self.p2p = False
+
+    def setup_peer_exchange(self, rank: int, world: int, capacity_keys: int, group=None) -> bool:
+        """Map every rank's receive buffer into every other rank (CUDA IPC). Returns False - and leaves the
+        NCCL all-to-all in place - when the GPUs cannot reach each other's memory."""
+        if world < 2 or self.p2p:
+            return self.p2p
+        ok = all(torch.cuda.can_device_access_peer(self.gw.device, d) for d in range(torch.cuda.device_count())
+                 if d != self.gw.device)
+        flag = torch.tensor([1 if ok else 0], device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            return False
+        mine = torch.frombuffer(bytearray(self.gw.exchange_init(capacity_keys)), dtype=torch.uint8).to(self.device)
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine, group=group)
+        self.gw.exchange_connect(world, rank, b"".join(bytes(x.cpu().numpy()) for x in every))
+        self.p2p = True
+        return True
+
+    def exchange_reset(self):
+        self.gw.exchange_reset()
+
+    def keys_scatter_peers(self, bounds: np.ndarray) -> np.ndarray:
+        return self.gw.keys_scatter_peers(bounds)
+
+    def exchange_finish(self) -> int:
+        return self.gw.exchange_finish()
 
     def make_shard(self):
         self.gw.make_shard()
@@ -126,6 +156,9 @@ class ShardedGemWell:
 
     def run(self):
         e = self.e
+        p2p = self.world > 1 and getattr(e, "p2p", False)
+        if p2p:
+            e.exchange_reset()  # ordered before every peer's scatter by the all-reduces below
         e.make_shard()
         for t in e.prior_tensors():
             self._allreduce(t)
@@ -140,7 +173,13 @@ class ShardedGemWell:
         for t in valid[1:]:
             total = total + t.to(torch.int64)
         self.bounds = owner_bounds(total, self.world)
-        if self.world > 1:
+        if p2p:
+            # fused: one pass writes every key into its owner's receive buffer over NVLink
+            sent = e.keys_scatter_peers(self.bounds)
+            self.exchange_bytes = int(sent.sum() - sent[self.rank]) * 8
+            dist.barrier(group=self.group)  # every rank's stores have landed
+            e.exchange_finish()
+        elif self.world > 1:
             keys, send_counts = e.keys_partition(self.bounds)
             sc = torch.as_tensor(send_counts, dtype=torch.int64, device=keys.device)
             rc = torch.empty_like(sc)

@@ -155,6 +155,22 @@ int crgpu_valid_counts_dev(crgpu_ctx* ctx, int library, uint32_t** out_dev_u32, 
  * recomputation valid = prior + corrected after both have been made global */
 int crgpu_corrected_dev(crgpu_ctx* ctx, int library, uint32_t** out_dev_u32, uint64_t* out_n);
 int crgpu_valid_counts_refresh(crgpu_ctx* ctx);
+/* Fused key exchange over peer memory (NVLink / NVSwitch) instead of partition + all-to-all: every context
+ * owns a receive buffer that its peers map through CUDA IPC, and crgpu_keys_scatter_peers() writes each key
+ * straight into the buffer of the rank that owns its barcode (one pass over the keys, block-aggregated remote
+ * cursor claims, coalesced peer stores). Protocol per step, on every rank:
+ *   crgpu_exchange_reset            (before the first collective of the step)
+ *   ... pass1, all-reduces, pass2 ...
+ *   crgpu_keys_scatter_peers        (returns when this rank's stores are complete)
+ *   <any cross-rank barrier>
+ *   crgpu_exchange_finish           (adopts the received keys as this context's key set)
+ * handle: 2 * 64 bytes (cudaIpcMemHandle_t of the buffer and of its cursor). */
+#define CRGPU_IPC_HANDLE_BYTES 128
+int crgpu_exchange_init(crgpu_ctx* ctx, uint64_t capacity_keys, void* out_handle);
+int crgpu_exchange_connect(crgpu_ctx* ctx, int32_t n_ranks, int32_t my_rank, const void* handles);
+int crgpu_exchange_reset(crgpu_ctx* ctx);
+int crgpu_keys_scatter_peers(crgpu_ctx* ctx, int32_t n_parts, const uint32_t* bounds, uint64_t* out_sent);
+int crgpu_exchange_finish(crgpu_ctx* ctx, uint64_t* out_received);
 /* restrict the matrix columns this context owns to content ranks [lo, hi) */
 int crgpu_set_owned_range(crgpu_ctx* ctx, uint32_t lo, uint32_t hi);
 

@@ -1,0 +1,69 @@
+"""Host-side pieces of cellranger_b200.api that need no GPU."""
+import gzip
+
+import numpy as np
+import pytest
+
+from cellranger_b200 import api
+
+
+def test_tethered_offset_follows_compile_pattern_rules():
+    # FeatureExtractor::compile_pattern — lib/rust/cr_types/src/reference/feature_extraction.rs:306-342
+    assert api.tethered_offset("5PNNNNNNNNNN(BC)") == 10
+    assert api.tethered_offset("5P(BC)") == 0
+    assert api.tethered_offset("^(BC)") == 0
+    assert api.tethered_offset("5p-NN(BC)") == 2
+    for bad in ("(BC)", "5PAGT(BC)", "5PNN(BC)TTT", "NN(BC)", "5PNN(BC)(BC)"):
+        with pytest.raises(ValueError):
+            api.tethered_offset(bad)
+
+
+def test_whitelist_from_txt_plain_and_translation(tmp_path):
+    p = tmp_path / "wl.txt"
+    p.write_text("ACGT\nTTTT\n")
+    wl = api.Whitelist.from_txt(str(p))
+    assert wl.translated is None and wl.length == 4 and wl.seqs.shape == (2, 4)
+    g = tmp_path / "tr.txt.gz"
+    with gzip.open(g, "wt") as f:
+        f.write("ACGT\tAAAA\nTTTT\tCCCC\n")
+    tr = api.Whitelist.from_txt(str(g))
+    assert bytes(tr.translated[1]) == b"CCCC" and bytes(tr.seqs[0]) == b"ACGT"
+    with pytest.raises(ValueError):
+        api.Whitelist.trans(["ACGT"], ["AAAA", "CCCC"])
+
+
+def test_ascii_matrix_and_unpack_roundtrip():
+    m = api.ascii_matrix(["ACGT", "TTGA"])
+    assert m.shape == (2, 4) and bytes(m[1]) == b"TTGA"
+    with pytest.raises(ValueError):
+        api.ascii_matrix(["ACGT", "AC"])
+    packed = np.array([27, 0b11110010], dtype=np.uint32)  # ACGT, TTAG
+    assert [bytes(r) for r in api.unpack_2bit(packed, 4)] == [b"ACGT", b"TTAG"]
+
+
+def test_count_matrix_mtx_lines_and_lazy_barcodes():
+    calls = []
+
+    def resolve(ranks):
+        calls.append(1)
+        return np.frombuffer(b"AAAACCCC", dtype=np.uint8).reshape(2, 4)[: len(ranks)]
+
+    m = api.CountMatrix(np.array([3, 9], dtype=np.uint32), np.array([0, 2, 3], dtype=np.int64),
+                        np.array([0, 5, 2], dtype=np.uint32), np.array([1, 4, 7], dtype=np.int32), 10,
+                        resolve_barcodes=resolve)
+    assert m.shape == (10, 2) and not calls
+    # MtxWriter::write_matrix_mtx: `feature+1 barcode+1 count`
+    assert m.mtx_lines() == ["1 1 1", "6 1 4", "3 2 7"]
+    assert m.barcode_strings() == ["AAAA-1", "CCCC-1"] and len(calls) == 1
+    m.barcodes
+    assert len(calls) == 1
+
+
+def test_feature_reference_and_chemistry_presets():
+    fr = api.FeatureReference(3)
+    assert fr.add_feature_barcode("CD3", "ACGTACGTACGTACG", 1) == 3 and fr.n_features == 4
+    with pytest.raises(ValueError):
+        fr.add_feature_barcode("x", "ACGT", 0)
+    # lib/python/cellranger/chemistry_defs.json: SC3Pv2 UMI 10 @16, SC3Pv3 UMI 12 @16
+    assert (api.ChemistryDef.SC3Pv2().umi_length, api.ChemistryDef.SC3Pv3().umi_length) == (10, 12)
+    assert api.Posterior().bc_confidence_threshold == 0.975

@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, outdir, name, n_reads, kw):
+def _worker(rank, world, port, outdir, name, n_reads, kw, p2p):
     import torch
     import torch.distributed as dist
 
@@ -41,7 +41,10 @@ def _worker(rank, world, port, outdir, name, n_reads, kw):
         gw.set_feature_reference(cb.FeatureReference(cfg.n_genes))
         g = prob["gex"]
         gw.add_reads(lib, g["r1_seq"][lo:hi], g["r1_qual"][lo:hi], g["feature"][lo:hi])
-        sh = ShardedGemWell(TorchEngine(gw, 1), rank, world)
+        eng = TorchEngine(gw, 1)
+        if p2p:
+            assert eng.setup_peer_exchange(rank, world, capacity_keys=n_reads), "no peer access between the GPUs"
+        sh = ShardedGemWell(eng, rank, world)
         for _ in range(2):  # twice: the second run reuses every buffer
             sh.run()
         m = gw.count_matrix()
@@ -55,8 +58,9 @@ def _worker(rank, world, port, outdir, name, n_reads, kw):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("p2p", [True, False], ids=["peer-stores", "nccl-all-to-all"])
 @pytest.mark.parametrize("name,n,kw", [("cfg1", 400_000, {}), ("cfg2", 300_000, {"n_whitelist": 300_000, "n_cells": 300})])
-def test_two_gpu_sharded_matches_oracle(name, n, kw):
+def test_two_gpu_sharded_matches_oracle(name, n, kw, p2p):
     import torch
     import torch.multiprocessing as mp
 
@@ -64,7 +68,7 @@ def test_two_gpu_sharded_matches_oracle(name, n, kw):
         pytest.skip("needs two GPUs")
     world = 2
     with tempfile.TemporaryDirectory() as d:
-        mp.spawn(_worker, args=(world, _free_port(), d, name, n, kw), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), d, name, n, kw, p2p), nprocs=world, join=True)
         parts = [dict(np.load(os.path.join(d, f"rank{r}.npz"))) for r in range(world)]
     prob = helpers.make_problem(name, n, **kw)
     o = helpers.run_oracle(prob, threads=8)
