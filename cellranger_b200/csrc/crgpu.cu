@@ -139,6 +139,7 @@ struct crgpu_ctx {
   unsigned long long* sorted = nullptr;
   uint64_t n_keys = 0;
   bool keys_external = false;
+  unsigned long long* key_src = nullptr;  // where crgpu_count finds the keys (nullptr = the keys buffer)
 
   // dedup
   DevBuf dkeys, c0, best, inc, low, key2, key2_alt, lb_desc, tickets, scalars, ent_rank, ent_feature, ent_count, mol;
@@ -749,6 +750,7 @@ int crgpu_pass1(crgpu_ctx* c) {
   if ((rc = phase_end(c))) return rc;
   c->stage = 1;
   c->keys_external = false;
+  c->key_src = nullptr;
   c->annotated = false;
   return CRGPU_OK;
 }
@@ -1034,6 +1036,7 @@ int crgpu_keys_set(crgpu_ctx* c, const unsigned long long* dev_keys, uint64_t n)
   if ((rc = c->keys_alt.ensure(n * 8 + 16))) return rc;
   if (n) CU(cudaMemcpyAsync(c->keys.p, dev_keys, n * 8, cudaMemcpyDeviceToDevice, c->stream));
   c->n_keys = n;
+  c->key_src = nullptr;
   c->keys_external = true;
   if (c->stage < 2) c->stage = 2;
   return CRGPU_OK;
@@ -1145,9 +1148,10 @@ int crgpu_exchange_finish(crgpu_ctx* c, uint64_t* out_received) {
                                    std::to_string(c->xchg_capacity));
   int rc;
   if ((rc = ensure_layout(c))) return rc;
-  if ((rc = c->keys.ensure(h[0] * 8 + 16))) return rc;
   if ((rc = c->keys_alt.ensure(h[0] * 8 + 16))) return rc;
-  if (h[0]) CU(cudaMemcpyAsync(c->keys.p, c->xchg_buf, h[0] * 8, cudaMemcpyDeviceToDevice, c->stream));
+  // the receive buffer itself is the sort input (and one of its two ping-pong buffers): no copy. Peers
+  // write into it again only after the next step's collectives, i.e. after this context's count.
+  c->key_src = static_cast<unsigned long long*>(c->xchg_buf);
   c->n_keys = h[0];
   c->keys_external = true;
   if (c->stage < 2) c->stage = 2;
@@ -1173,15 +1177,16 @@ int crgpu_count(crgpu_ctx* c) {
   const uint64_t cap = std::max<uint64_t>(nk, 1);
   if ((rc = c->sort_temp.ensure(sort_temp_bytes(cap)))) return rc;
   if ((rc = phase_begin(c, "count.sort.hist"))) return rc;
-  c->launches += sort_histograms(c->keys.as<unsigned long long>(), nk, c->kl.total_bits, c->sort_temp.p, c->stream);
+  unsigned long long* key_src = c->key_src ? c->key_src : c->keys.as<unsigned long long>();
+  c->launches += sort_histograms(key_src, nk, c->kl.total_bits, c->sort_temp.p, c->stream);
   CHECK_KERNEL();
   if ((rc = phase_end(c))) return rc;
   {
     std::string nm = "count.sort.onesweep_x" + std::to_string(sort_num_passes(c->kl.total_bits));
     if ((rc = phase_begin(c, nm.c_str()))) return rc;
   }
-  unsigned long long* sorted = c->keys.as<unsigned long long>();
-  c->launches += sort_passes(c->keys.as<unsigned long long>(), c->keys_alt.as<unsigned long long>(), nk,
+  unsigned long long* sorted = key_src;
+  c->launches += sort_passes(key_src, c->keys_alt.as<unsigned long long>(), nk,
                              c->kl.total_bits, c->sort_temp.p, &sorted, c->stream);
   CHECK_KERNEL();
   if ((rc = phase_end(c))) return rc;

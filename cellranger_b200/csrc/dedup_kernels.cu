@@ -70,19 +70,86 @@ static int run_compact(const Op& op, uint64_t n, ScanScratch s, unsigned long lo
 }
 
 // ---- run-length encoding of sorted 64-bit keys (shifted right by `shift`) ----
-struct RleOp {
-  const unsigned long long* keys;
-  int shift;
-  unsigned long long* out_keys;  // un-shifted key of each run head (may be nullptr)
-  uint32_t* out_pos;             // index of each run head
-  __device__ bool flag(uint64_t i) const {
-    return i == 0 || (keys[i] >> shift) != (keys[i - 1] >> shift);
+
+// ---- specialised single-pass compactions (vector loads, flags in registers) ----
+constexpr int CP_THREADS = 256;
+constexpr int CP_ITEMS = 8;
+constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
+
+// ticket + block scan + look-back shared by the specialised kernels; returns the output position of the
+// thread's first flagged item and writes the grand total once
+__device__ __forceinline__ uint64_t cp_place(uint32_t cnt, uint32_t tile, uint64_t n_tiles, unsigned long long* desc,
+                                             unsigned long long* total_out, uint32_t* scan_s,
+                                             unsigned long long* bcast) {
+  uint32_t total;
+  uint32_t off = block_exclusive_scan<CP_THREADS>(cnt, &total, scan_s);
+  unsigned long long excl = lookback_exclusive(desc, tile, (unsigned long long)total, bcast);
+  if (tile == n_tiles - 1 && threadIdx.x == 0) *total_out = excl + total;
+  return excl + off;
+}
+
+// run-length encoding of sorted keys compared after `>> shift`; heads go to out_pos (and out_keys)
+template <bool WRITE_KEYS>
+__global__ void __launch_bounds__(CP_THREADS) rle_kernel(const unsigned long long* __restrict__ keys, uint64_t n,
+                                                         int shift, unsigned long long* __restrict__ out_keys,
+                                                         uint32_t* __restrict__ out_pos, unsigned long long* desc,
+                                                         uint32_t* ticket, unsigned long long* total_out) {
+  __shared__ uint32_t scan_s[CP_THREADS / 32 + 1];
+  __shared__ unsigned long long bcast;
+  __shared__ uint32_t tile_s;
+  if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = tile_s;
+  const uint64_t first = (uint64_t)tile * CP_TILE + (uint64_t)threadIdx.x * CP_ITEMS;
+  unsigned long long k[CP_ITEMS];
+  if (first + CP_ITEMS <= n) {
+    const ulonglong2* v = reinterpret_cast<const ulonglong2*>(keys + first);  // 64-byte aligned
+#pragma unroll
+    for (int i = 0; i < CP_ITEMS / 2; i++) {
+      ulonglong2 t = __ldcs(v + i);
+      k[2 * i] = t.x;
+      k[2 * i + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < CP_ITEMS; i++) k[i] = first + i < n ? keys[first + i] : 0ull;
   }
-  __device__ void emit(uint64_t i, uint64_t pos) const {
-    if (out_keys) out_keys[pos] = keys[i];
-    out_pos[pos] = (uint32_t)i;
+  // the key before this thread's first: the neighbour lane's last key, or one global load for lane 0
+  unsigned long long prev = __shfl_up_sync(0xFFFFFFFFu, k[CP_ITEMS - 1], 1);
+  if ((threadIdx.x & 31) == 0 && first > 0 && first < n) prev = keys[first - 1];
+  bool f[CP_ITEMS];
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int i = 0; i < CP_ITEMS; i++) {
+    const unsigned long long before = i == 0 ? prev : k[i - 1];
+    f[i] = first + i < n && ((first + i == 0) || (k[i] >> shift) != (before >> shift));
+    cnt += f[i];
   }
-};
+  const uint64_t n_tiles = (n + CP_TILE - 1) / CP_TILE;
+  uint64_t pos = cp_place(cnt, tile, n_tiles, desc, total_out, scan_s, &bcast);
+#pragma unroll
+  for (int i = 0; i < CP_ITEMS; i++)
+    if (f[i]) {
+      if (WRITE_KEYS) out_keys[pos] = k[i];
+      out_pos[pos] = (uint32_t)(first + i);
+      pos++;
+    }
+}
+
+template <bool WRITE_KEYS>
+static int run_rle(const unsigned long long* keys, uint64_t n, int shift, unsigned long long* out_keys,
+                   uint32_t* out_pos, unsigned long long* desc, uint32_t* ticket, unsigned long long* total_out,
+                   cudaStream_t st) {
+  if (n == 0) {
+    cudaMemsetAsync(total_out, 0, 8, st);
+    return 0;
+  }
+  uint64_t tiles = (n + CP_TILE - 1) / CP_TILE;
+  cudaMemsetAsync(desc, 0, tiles * 8, st);
+  cudaMemsetAsync(ticket, 0, 4, st);
+  rle_kernel<WRITE_KEYS><<<(unsigned)tiles, CP_THREADS, 0, st>>>(keys, n, shift, out_keys, out_pos, desc, ticket, total_out);
+  return 1;
+}
 
 __global__ void run_lengths_kernel(const uint32_t* pos, uint64_t n_runs, uint64_t n_items, uint32_t* len) {
   for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < n_runs; j += (uint64_t)gridDim.x * blockDim.x) {
@@ -520,23 +587,66 @@ __global__ void __launch_bounds__(256) low_support_kernel(const unsigned long lo
 // ---------------------------------------------------------------------------
 // molecules (UmiCount rows) and matrix entries
 // ---------------------------------------------------------------------------
-struct MolOp {
-  const unsigned long long* dkeys;
-  const uint32_t* c0;
-  const uint32_t* best;
-  const unsigned long long* inc;
-  const uint8_t* low;
-  unsigned long long* mol_key;  // packed key of the molecule (corrected UMI)
-  uint32_t* mol_reads;          // c2
-  __device__ bool flag(uint64_t j) const {
-    bool is_target = best[j] == (uint32_t)j || (inc[j] >> 40) != 0ull;
-    return is_target && !low[j];
+// molecules = correction targets that are not low support: key + read count (c2), compacted in order
+__global__ void __launch_bounds__(CP_THREADS) molecules_compact_kernel(
+    const unsigned long long* __restrict__ dkeys, const uint32_t* __restrict__ c0, const uint32_t* __restrict__ best,
+    const unsigned long long* __restrict__ inc, const uint8_t* __restrict__ low, uint64_t m,
+    unsigned long long* __restrict__ mol_key, uint32_t* __restrict__ mol_reads, unsigned long long* desc,
+    uint32_t* ticket, unsigned long long* total_out) {
+  __shared__ uint32_t scan_s[CP_THREADS / 32 + 1];
+  __shared__ unsigned long long bcast;
+  __shared__ uint32_t tile_s;
+  if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = tile_s;
+  const uint64_t first = (uint64_t)tile * CP_TILE + (uint64_t)threadIdx.x * CP_ITEMS;
+  uint32_t b[CP_ITEMS];
+  unsigned long long in[CP_ITEMS];
+  uint8_t lw[CP_ITEMS];
+  if (first + CP_ITEMS <= m) {
+    const uint4* vb = reinterpret_cast<const uint4*>(best + first);
+    const ulonglong2* vi = reinterpret_cast<const ulonglong2*>(inc + first);
+    const uint2 vl = *reinterpret_cast<const uint2*>(low + first);
+#pragma unroll
+    for (int i = 0; i < CP_ITEMS / 4; i++) {
+      uint4 t = vb[i];
+      b[4 * i] = t.x, b[4 * i + 1] = t.y, b[4 * i + 2] = t.z, b[4 * i + 3] = t.w;
+    }
+#pragma unroll
+    for (int i = 0; i < CP_ITEMS / 2; i++) {
+      ulonglong2 t = vi[i];
+      in[2 * i] = t.x, in[2 * i + 1] = t.y;
+    }
+#pragma unroll
+    for (int i = 0; i < CP_ITEMS; i++) lw[i] = (uint8_t)((i < 4 ? vl.x : vl.y) >> (8 * (i & 3)));
+  } else {
+#pragma unroll
+    for (int i = 0; i < CP_ITEMS; i++) {
+      const bool ok = first + i < m;
+      b[i] = ok ? best[first + i] : 0u;
+      in[i] = ok ? inc[first + i] : 0ull;
+      lw[i] = ok ? low[first + i] : (uint8_t)1;
+    }
   }
-  __device__ void emit(uint64_t j, uint64_t pos) const {
-    mol_key[pos] = dkeys[j];
-    mol_reads[pos] = (uint32_t)((best[j] == (uint32_t)j ? c0[j] : 0u) + (inc[j] & INC_READS_MASK));
+  bool f[CP_ITEMS];
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int i = 0; i < CP_ITEMS; i++) {
+    const bool is_target = b[i] == (uint32_t)(first + i) || (in[i] >> 40) != 0ull;
+    f[i] = first + i < m && is_target && !lw[i];
+    cnt += f[i];
   }
-};
+  const uint64_t n_tiles = (m + CP_TILE - 1) / CP_TILE;
+  uint64_t pos = cp_place(cnt, tile, n_tiles, desc, total_out, scan_s, &bcast);
+#pragma unroll
+  for (int i = 0; i < CP_ITEMS; i++)
+    if (f[i]) {
+      const uint64_t j = first + i;
+      mol_key[pos] = dkeys[j];
+      mol_reads[pos] = (uint32_t)((b[i] == (uint32_t)j ? c0[j] : 0u) + (in[i] & INC_READS_MASK));
+      pos++;
+    }
+}
 
 __global__ void entries_kernel(const unsigned long long* __restrict__ mol_key, const uint32_t* __restrict__ pos,
                                uint64_t n_ent, uint64_t n_mol, KeyLayout kl, uint32_t* __restrict__ ent_rank,
@@ -820,8 +930,7 @@ int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
   cudaMemsetAsync(b.scalars, 0, 16 * 8, st);
   mark("count.dedup.rle");
   // 1. run-length encode: distinct keys + raw counts (head positions parked in `best`)
-  RleOp rle{b.sorted, 0, b.dkeys, b.best};
-  launches += run_compact(rle, b.n_keys, ss, b.scalars + 0, st);
+  launches += run_rle<true>(b.sorted, b.n_keys, 0, b.dkeys, b.best, ss.desc, ss.ticket, b.scalars + 0, st);
   unsigned long long m = 0;
   cudaMemcpyAsync(&m, b.scalars + 0, 8, cudaMemcpyDeviceToHost, st);
   cudaStreamSynchronize(st);
@@ -873,8 +982,14 @@ int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
   low_reads_kernel<<<grid_for(m), 256, 0, st>>>(b.c0, b.best, b.low, m, b.scalars);
   launches++;
   // 4. molecules = correction targets that are not low support (key2 now holds their keys)
-  MolOp mol{b.dkeys, b.c0, b.best, b.inc, b.low, b.key2, b.mol};
-  launches += run_compact(mol, m, ss, b.scalars + 2, st);
+  {
+    uint64_t tiles = (m + CP_TILE - 1) / CP_TILE;
+    cudaMemsetAsync(ss.desc, 0, tiles * 8, st);
+    cudaMemsetAsync(ss.ticket, 0, 4, st);
+    molecules_compact_kernel<<<(unsigned)tiles, CP_THREADS, 0, st>>>(b.dkeys, b.c0, b.best, b.inc, b.low, m, b.key2,
+                                                                    b.mol, ss.desc, ss.ticket, b.scalars + 2);
+    launches++;
+  }
   return launches;
 }
 
@@ -980,8 +1095,7 @@ int run_matrix(DedupBuffers& b, MatrixArgs& ma, uint64_t /*nnz_unused*/, uint64_
   launches += run_compact(seen, ma.n_content, ss, b.scalars + 7, st);
   // entries = runs of (rank, feature) among the molecules
   uint32_t* run_pos = reinterpret_cast<uint32_t*>(b.key2_alt);
-  RleOp rle{b.key2, b.kl.feature_shift, nullptr, run_pos};
-  launches += run_compact(rle, n_mol, ss, b.scalars + 1, st);
+  launches += run_rle<false>(b.key2, n_mol, b.kl.feature_shift, nullptr, run_pos, ss.desc, ss.ticket, b.scalars + 1, st);
   unsigned long long h[2] = {0, 0};
   cudaMemcpyAsync(&h[0], b.scalars + 1, 8, cudaMemcpyDeviceToHost, st);
   cudaMemcpyAsync(&h[1], b.scalars + 7, 8, cudaMemcpyDeviceToHost, st);
