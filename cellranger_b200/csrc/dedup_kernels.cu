@@ -76,16 +76,20 @@ constexpr int CP_THREADS = 256;
 constexpr int CP_ITEMS = 8;
 constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
 
-// ticket + block scan + look-back shared by the specialised kernels; returns the output position of the
-// thread's first flagged item and writes the grand total once
-__device__ __forceinline__ uint64_t cp_place(uint32_t cnt, uint32_t tile, uint64_t n_tiles, unsigned long long* desc,
-                                             unsigned long long* total_out, uint32_t* scan_s,
-                                             unsigned long long* bcast) {
-  uint32_t total;
-  uint32_t off = block_exclusive_scan<CP_THREADS>(cnt, &total, scan_s);
-  unsigned long long excl = lookback_exclusive(desc, tile, (unsigned long long)total, bcast);
-  if (tile == n_tiles - 1 && threadIdx.x == 0) *total_out = excl + total;
-  return excl + off;
+// ticket + block scan + look-back shared by the specialised kernels: the thread's offset inside the tile's
+// output, the tile's exclusive prefix and its total; writes the grand total once
+struct CpPlace {
+  uint32_t off, total;
+  uint64_t excl;
+};
+__device__ __forceinline__ CpPlace cp_place(uint32_t cnt, uint32_t tile, uint64_t n_tiles, unsigned long long* desc,
+                                            unsigned long long* total_out, uint32_t* scan_s,
+                                            unsigned long long* bcast) {
+  CpPlace r;
+  r.off = block_exclusive_scan<CP_THREADS>(cnt, &r.total, scan_s);
+  r.excl = lookback_exclusive(desc, tile, (unsigned long long)r.total, bcast);
+  if (tile == n_tiles - 1 && threadIdx.x == 0) *total_out = r.excl + r.total;
+  return r;
 }
 
 // run-length encoding of sorted keys compared after `>> shift`; heads go to out_pos (and out_keys)
@@ -126,14 +130,24 @@ __global__ void __launch_bounds__(CP_THREADS) rle_kernel(const unsigned long lon
     cnt += f[i];
   }
   const uint64_t n_tiles = (n + CP_TILE - 1) / CP_TILE;
-  uint64_t pos = cp_place(cnt, tile, n_tiles, desc, total_out, scan_s, &bcast);
+  const CpPlace pl = cp_place(cnt, tile, n_tiles, desc, total_out, scan_s, &bcast);
+  // stage the tile's heads in shared memory so the global stores are contiguous
+  __shared__ unsigned long long st_k[WRITE_KEYS ? CP_TILE : 1];
+  __shared__ uint16_t st_p[CP_TILE];
+  uint32_t o = pl.off;
 #pragma unroll
   for (int i = 0; i < CP_ITEMS; i++)
     if (f[i]) {
-      if (WRITE_KEYS) out_keys[pos] = k[i];
-      out_pos[pos] = (uint32_t)(first + i);
-      pos++;
+      if (WRITE_KEYS) st_k[o] = k[i];
+      st_p[o] = (uint16_t)(threadIdx.x * CP_ITEMS + i);
+      o++;
     }
+  __syncthreads();
+  const uint64_t tile_base = (uint64_t)tile * CP_TILE;
+  for (uint32_t i = threadIdx.x; i < pl.total; i += CP_THREADS) {
+    if (WRITE_KEYS) out_keys[pl.excl + i] = st_k[i];
+    out_pos[pl.excl + i] = (uint32_t)(tile_base + st_p[i]);
+  }
 }
 
 template <bool WRITE_KEYS>
@@ -637,15 +651,23 @@ __global__ void __launch_bounds__(CP_THREADS) molecules_compact_kernel(
     cnt += f[i];
   }
   const uint64_t n_tiles = (m + CP_TILE - 1) / CP_TILE;
-  uint64_t pos = cp_place(cnt, tile, n_tiles, desc, total_out, scan_s, &bcast);
+  const CpPlace pl = cp_place(cnt, tile, n_tiles, desc, total_out, scan_s, &bcast);
+  __shared__ unsigned long long st_k[CP_TILE];
+  __shared__ uint32_t st_r[CP_TILE];
+  uint32_t o = pl.off;
 #pragma unroll
   for (int i = 0; i < CP_ITEMS; i++)
     if (f[i]) {
       const uint64_t j = first + i;
-      mol_key[pos] = dkeys[j];
-      mol_reads[pos] = (uint32_t)((b[i] == (uint32_t)j ? c0[j] : 0u) + (in[i] & INC_READS_MASK));
-      pos++;
+      st_k[o] = dkeys[j];
+      st_r[o] = (uint32_t)((b[i] == (uint32_t)j ? c0[j] : 0u) + (in[i] & INC_READS_MASK));
+      o++;
     }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < pl.total; i += CP_THREADS) {
+    mol_key[pl.excl + i] = st_k[i];
+    mol_reads[pl.excl + i] = st_r[i];
+  }
 }
 
 __global__ void entries_kernel(const unsigned long long* __restrict__ mol_key, const uint32_t* __restrict__ pos,
