@@ -57,18 +57,30 @@ __global__ void radix_scan_hist_kernel(unsigned long long* hist) {
 // One tile of one pass. FULL = the tile holds SORT_TILE keys (no bounds checks in the hot loops).
 // lanes of the warp holding the same 9-bit value: eight ballots instead of match.any, whose cost grows with
 // the number of distinct values in the warp (about 30 for a uniformly distributed digit)
+template <int NBITS>
 __device__ __forceinline__ uint32_t match_digit(uint32_t digit) {
   uint32_t peers = 0xFFFFFFFFu;
 #pragma unroll
-  for (int b = 0; b < RADIX_BITS + 1; b++) {
-    const bool bit = (digit >> b) & 1u;
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
-    peers &= bit ? m : ~m;
+  for (int b = 0; b < NBITS; b++) {
+    // one predicate, one vote, one conditional complement, one AND per bit (the C++ form compiled to seven)
+    uint32_t m;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+        "and.b32 t, %1, %2;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+        "@!p not.b32 %0, %0;\n\t}"
+        : "=r"(m)
+        : "r"(digit), "r"(1u << b));
+    peers &= m;
   }
   return peers;
 }
 
-template <int SORT_THREADS, int SORT_ITEMS, bool FULL, bool BALLOT>
+// RANK = 0: the lowest peer lane bumps the counter and shuffles the old value to its peers;
+// RANK = 1: the lowest peer lane bumps the counter and the peers read the new value back from shared memory
+// (one POPC per key instead of POPC + POPC + BREV + FLO + SHFL). LBK = descriptors fetched per look-back step.
+template <int SORT_THREADS, int SORT_ITEMS, bool FULL, bool BALLOT, int RANK, int LBK>
 __device__ __forceinline__ void onesweep_tile(const unsigned long long* __restrict__ in,
                                               unsigned long long* __restrict__ out, int cnt, uint64_t tile_first,
                                               uint32_t tile, int shift,
@@ -96,21 +108,34 @@ __device__ __forceinline__ void onesweep_tile(const unsigned long long* __restri
   // alone reads and bumps the warp-private counter and hands the old value to its peers by shuffle.
   uint32_t* my_hist = s_warp_hist + warp * RADIX;
   const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t gt_mask = lane == 31 ? 0u : (0xFFFFFFFEu << lane);
 #pragma unroll
   for (int k = 0; k < SORT_ITEMS; k++) {
     const int idx = warp_first + k * 32 + lane;
     const bool valid = FULL || idx < cnt;
     const uint32_t digit = valid ? (uint32_t)((key[k] >> shift) & (RADIX - 1)) : (uint32_t)RADIX;
-    const uint32_t peers = BALLOT ? match_digit(digit) : __match_any_sync(0xFFFFFFFFu, digit);
-    const int leader = __ffs(peers) - 1;
-    uint32_t base = 0;
-    if (lane == leader && valid) {
-      base = my_hist[digit];
-      my_hist[digit] = base + (uint32_t)__popc(peers);
+    // a full tile has no invalid marker, so eight ballots tell the digits apart
+    const uint32_t peers = BALLOT ? match_digit<FULL ? RADIX_BITS : RADIX_BITS + 1>(digit)
+                                  : __match_any_sync(0xFFFFFFFFu, digit);
+    if (RANK == 0) {
+      const int leader = __ffs(peers) - 1;
+      uint32_t base = 0;
+      if (lane == leader && valid) {
+        base = my_hist[digit];
+        my_hist[digit] = base + (uint32_t)__popc(peers);
+      }
+      base = __shfl_sync(0xFFFFFFFFu, base, leader);
+      __syncwarp();  // the next item may have another leader for the same digit
+      dr[k] = digit | ((base + (uint32_t)__popc(peers & lt_mask)) << 16);
+    } else {
+      const uint32_t above = (uint32_t)__popc(peers & gt_mask);  // peers in higher lanes
+      if ((peers & lt_mask) == 0u && valid) my_hist[digit] += above + 1u;
+      __syncwarp();
+      // shared-memory accesses of one warp are performed in program order: this read sees the bump of this
+      // item and none of the later ones
+      const uint32_t after = valid ? my_hist[digit] : 0u;
+      dr[k] = digit | ((after - 1u - above) << 16);
     }
-    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    __syncwarp();  // the next item may have another leader for the same digit
-    dr[k] = digit | ((base + (uint32_t)__popc(peers & lt_mask)) << 16);
   }
   __syncthreads();
   // per digit: exclusive scan over the warps, tile total
@@ -146,24 +171,49 @@ __device__ __forceinline__ void onesweep_tile(const unsigned long long* __restri
   }
   __syncthreads();
   // fold the digit offsets into the per-warp offsets: one shared load per key in the scatter
-  for (int i = tid; i < WARPS * RADIX; i += SORT_THREADS) s_warp_hist[i] += s_bin_off[i & (RADIX - 1)];
+  {
+    static_assert(WARPS * RADIX == SORT_THREADS * 8 || WARPS * RADIX % (SORT_THREADS * 4) == 0, "fold layout");
+    uint4* h4 = reinterpret_cast<uint4*>(s_warp_hist);
+    const uint4* o4 = reinterpret_cast<const uint4*>(s_bin_off);
+    for (int i = tid; i < WARPS * RADIX / 4; i += SORT_THREADS) {
+      uint4 h = h4[i];
+      const uint4 o = o4[i & (RADIX / 4 - 1)];
+      h.x += o.x, h.y += o.y, h.z += o.z, h.w += o.w;
+      h4[i] = h;
+    }
+  }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < SORT_ITEMS; k++) {
     const uint32_t digit = dr[k] & 0x1FFu;
     if (FULL || digit < RADIX) s_keys[my_hist[digit] + (dr[k] >> 16)] = key[k];
   }
-  // chained scan over tiles (decoupled look-back), one descriptor per digit
+  // chained scan over tiles (decoupled look-back), one descriptor per digit; LBK predecessors are fetched
+  // per step so that a walk of depth D costs D / LBK memory round trips
   for (int d = tid; d < RADIX; d += SORT_THREADS) {
     unsigned long long excl = 0;
     if (tile != 0) {
-      for (int64_t t = (int64_t)tile - 1; t >= 0; t--) {
-        unsigned long long w;
-        do {
-          w = lb_load(desc + (size_t)t * RADIX + d);
-        } while ((w >> 62) == LB_INVALID);
-        excl += w & 0x3FFFFFFFFFFFFFFFull;
-        if ((w >> 62) == LB_PREFIX) break;
+      int64_t left = (int64_t)tile;  // predecessors not yet looked at
+      const unsigned long long* p = desc + (size_t)(tile - 1) * RADIX + d;
+      bool done = false;
+      while (!done) {
+        unsigned long long w[LBK];
+#pragma unroll
+        for (int i = 0; i < LBK; i++) w[i] = i < left ? lb_load(p - (size_t)i * RADIX) : (LB_PREFIX << 62);
+#pragma unroll
+        for (int i = 0; i < LBK; i++) {
+          if (!done) {
+            unsigned long long x = w[i];
+            while ((x >> 62) == LB_INVALID) {
+              __nanosleep(40);
+              x = lb_load(p - (size_t)i * RADIX);
+            }
+            excl += x & 0x3FFFFFFFFFFFFFFFull;
+            done = (x >> 62) == LB_PREFIX;
+          }
+        }
+        p -= (size_t)LBK * RADIX;
+        left -= LBK;
       }
       lb_store(desc + (size_t)tile * RADIX + d, LB_PREFIX, excl + (unsigned long long)s_bin_cnt[d]);
     }
@@ -179,7 +229,7 @@ __device__ __forceinline__ void onesweep_tile(const unsigned long long* __restri
   }
 }
 
-template <int SORT_THREADS, int SORT_ITEMS, int MIN_BLOCKS, bool BALLOT>
+template <int SORT_THREADS, int SORT_ITEMS, int MIN_BLOCKS, bool BALLOT, int RANK, int LBK>
 __global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) radix_onesweep_kernel(
     const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, uint64_t n, int shift,
     const unsigned long long* __restrict__ bin_base, unsigned long long* __restrict__ desc,
@@ -191,15 +241,16 @@ __global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) radix_onesweep_kerne
   __shared__ uint32_t tile_s;
   const int tid = threadIdx.x;
   if (tid == 0) tile_s = atomicAdd(ticket, 1u);
-  for (int i = tid; i < WARPS * RADIX; i += SORT_THREADS) s_warp_hist[i] = 0;
+  for (int i = tid; i < WARPS * RADIX / 4; i += SORT_THREADS)
+    reinterpret_cast<uint4*>(s_warp_hist)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
   const uint32_t tile = tile_s;
   const uint64_t tile_first = (uint64_t)tile * SORT_TILE;
   const int cnt = (n - tile_first) < (uint64_t)SORT_TILE ? (int)(n - tile_first) : SORT_TILE;
   if (cnt == SORT_TILE)
-    onesweep_tile<SORT_THREADS, SORT_ITEMS, true, BALLOT>(in, out, cnt, tile_first, tile, shift, bin_base, desc, smem_raw);
+    onesweep_tile<SORT_THREADS, SORT_ITEMS, true, BALLOT, RANK, LBK>(in, out, cnt, tile_first, tile, shift, bin_base, desc, smem_raw);
   else
-    onesweep_tile<SORT_THREADS, SORT_ITEMS, false, BALLOT>(in, out, cnt, tile_first, tile, shift, bin_base, desc, smem_raw);
+    onesweep_tile<SORT_THREADS, SORT_ITEMS, false, BALLOT, RANK, LBK>(in, out, cnt, tile_first, tile, shift, bin_base, desc, smem_raw);
 }
 
 }  // namespace
@@ -231,7 +282,7 @@ int sort_histograms(const unsigned long long* keys, uint64_t n, int end_bit, voi
   return 2;
 }
 
-template <int THREADS, int ITEMS, int MIN_BLOCKS, bool BALLOT>
+template <int THREADS, int ITEMS, int MIN_BLOCKS, bool BALLOT, int RANK, int LBK>
 static int run_passes(unsigned long long* keys, unsigned long long* alt, uint64_t n, int n_passes, void* temp,
                       unsigned long long** out, cudaStream_t st) {
   constexpr int TILE = THREADS * ITEMS;
@@ -242,7 +293,7 @@ static int run_passes(unsigned long long* keys, unsigned long long* alt, uint64_
   unsigned long long* desc = reinterpret_cast<unsigned long long*>(t + (size_t)MAX_PASSES * RADIX * 8);
   uint32_t* ticket = reinterpret_cast<uint32_t*>(t + (size_t)MAX_PASSES * RADIX * 8 + (size_t)(max_tiles + 1) * RADIX * 8);
   const size_t smem = (size_t)TILE * 8 + (size_t)(THREADS / 32) * RADIX * 4 + RADIX * 4 + RADIX * 8 + RADIX * 4;
-  auto kern = radix_onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS, BALLOT>;
+  auto kern = radix_onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS, BALLOT, RANK, LBK>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int launches = 0;
   unsigned long long* src = keys;
@@ -266,10 +317,13 @@ int sort_passes(unsigned long long* keys, unsigned long long* alt, uint64_t n, i
   const int np = plan_passes(end_bit);
   const int cfg = getenv("CRGPU_SORT_CFG") ? atoi(getenv("CRGPU_SORT_CFG")) : 0;
   switch (cfg) {  // CRGPU_SORT_CFG: variants kept for profiling; 0 = the measured best on B200
-    case 1: return run_passes<256, 16, 4, false>(keys, alt, n, np, temp, out, st);  // match.any instead of ballots
-    case 2: return run_passes<512, 12, 2, true>(keys, alt, n, np, temp, out, st);
-    case 3: return run_passes<384, 12, 3, true>(keys, alt, n, np, temp, out, st);
-    default: return run_passes<256, 16, 4, true>(keys, alt, n, np, temp, out, st);
+    case 1: return run_passes<256, 16, 4, false, 0, 4>(keys, alt, n, np, temp, out, st);  // match.any, not ballots
+    case 2: return run_passes<512, 12, 2, true, 0, 4>(keys, alt, n, np, temp, out, st);
+    case 3: return run_passes<384, 16, 3, true, 0, 4>(keys, alt, n, np, temp, out, st);
+    case 4: return run_passes<256, 16, 4, true, 1, 4>(keys, alt, n, np, temp, out, st);  // peers re-read the counter
+    case 5: return run_passes<256, 16, 4, true, 0, 1>(keys, alt, n, np, temp, out, st);  // one descriptor per step
+    case 6: return run_passes<256, 16, 4, true, 0, 8>(keys, alt, n, np, temp, out, st);
+    default: return run_passes<256, 16, 4, true, 0, 4>(keys, alt, n, np, temp, out, st);
   }
 }
 
