@@ -38,10 +38,11 @@ struct DevWhitelist {
   const uint32_t* offs[CRGPU_MAX_ORD];  // (1 << p) + 1 bucket starts
   int rot[CRGPU_MAX_ORD];
   uint32_t resp[CRGPU_MAX_ORD];  // bit `pos` set: this ordering answers for mutations at base `pos`
-  // exact membership: one 16-byte slot per bucket of the top (2L - slot_shift) key bits, fetched with a
-  // single 128-bit load: .x = index of the bucket's first entry in keys[0] (low 29 bits) | entry count
-  // (top 3 bits, 7 = more than six: search keys[0]); .y/.z/.w = up to six 16-bit key suffixes (the low
-  // slot_shift bits), 0xFFFF-padded.
+  // exact membership: one 32-byte slot (one L2 sector) per bucket of the top (2L - slot_shift) key bits,
+  // fetched with two 128-bit loads: word 0 = index of the bucket's first entry in keys[0] (low 27 bits) |
+  // entry count (top 5 bits, 31 = more than WL_SLOT_CAP: the rest follows in keys[0]); words 1..7 = up to
+  // fourteen 16-bit key suffixes (the low slot_shift bits), 0xFFFF-padded. About 6.5 entries per bucket, so
+  // that fewer than 1 % of the lookups leave the slot.
   const uint4* slots;
   int slot_shift;
 };
@@ -61,47 +62,38 @@ __device__ __forceinline__ uint32_t rotr_bits(uint32_t q, int r, int nbits) {
 
 // exact membership. Returns the index of the entry in keys[0] (sorted, rot 0) or -1.
 // Split in three so that callers can issue the loads of several independent lookups before resolving any.
+constexpr int WL_SLOT_CAP = 14;
 struct WlProbe {
-  uint4 slot;
+  uint4 s0, s1;
 };
 __device__ __forceinline__ uint32_t wl_find_begin(const DevWhitelist& wl, uint32_t q) {
   return wl.slot_shift >= 32 ? 0u : (q >> wl.slot_shift);  // bucket
 }
 __device__ __forceinline__ WlProbe wl_find_probe(const DevWhitelist& wl, uint32_t bucket) {
   WlProbe p;
-  p.slot = __ldg(wl.slots + bucket);
+  p.s0 = __ldg(wl.slots + 2 * (size_t)bucket);
+  p.s1 = __ldg(wl.slots + 2 * (size_t)bucket + 1);
   return p;
 }
 __device__ __forceinline__ int wl_find_end(const DevWhitelist& wl, const WlProbe& p, uint32_t q) {
-  const uint32_t cnt = p.slot.x >> 29, base = p.slot.x & 0x1FFFFFFFu;
+  const uint32_t cnt = p.s0.x >> 27, base = p.s0.x & 0x07FFFFFFu;
   if (cnt == 0u) return -1;
   const uint32_t qs = q & mask_bits(wl.slot_shift);
-  if (cnt < 7u) {
-    const uint32_t qq = qs | (qs << 16);
-    const uint32_t x0 = p.slot.y ^ qq, x1 = p.slot.z ^ qq, x2 = p.slot.w ^ qq;
-    int j = -1;
-    if (!(x2 >> 16)) j = 5;
-    if (!(x2 & 0xFFFFu)) j = 4;
-    if (!(x1 >> 16)) j = 3;
-    if (!(x1 & 0xFFFFu)) j = 2;
-    if (!(x0 >> 16)) j = 1;
-    if (!(x0 & 0xFFFFu)) j = 0;
-    return (j >= 0 && (uint32_t)j < cnt) ? (int)(base + (uint32_t)j) : -1;
+  const uint32_t qq = qs | (qs << 16);
+  const uint32_t w[7] = {p.s0.y, p.s0.z, p.s0.w, p.s1.x, p.s1.y, p.s1.z, p.s1.w};
+  int j = -1;
+#pragma unroll
+  for (int i = 6; i >= 0; i--) {
+    const uint32_t x = w[i] ^ qq;
+    if (!(x >> 16)) j = 2 * i + 1;
+    if (!(x & 0xFFFFu)) j = 2 * i;
   }
-  // crowded bucket (more than six entries): the first six are inline, the rest follow in the sorted keys
-  // (which end with 0xFFFFFFFF sentinels)
-  {
-    const uint32_t qq = qs | (qs << 16);
-    const uint32_t x0 = p.slot.y ^ qq, x1 = p.slot.z ^ qq, x2 = p.slot.w ^ qq;
-    if (!(x0 & 0xFFFFu)) return (int)base;
-    if (!(x0 >> 16)) return (int)base + 1;
-    if (!(x1 & 0xFFFFu)) return (int)base + 2;
-    if (!(x1 >> 16)) return (int)base + 3;
-    if (!(x2 & 0xFFFFu)) return (int)base + 4;
-    if (!(x2 >> 16)) return (int)base + 5;
-  }
+  if (cnt <= (uint32_t)WL_SLOT_CAP) return (j >= 0 && (uint32_t)j < cnt) ? (int)(base + (uint32_t)j) : -1;
+  // crowded bucket: the first fourteen entries are inline, the rest follow in the sorted keys (which end
+  // with 0xFFFFFFFF sentinels)
+  if (j >= 0) return (int)(base + (uint32_t)j);
   const uint32_t* __restrict__ keys = wl.keys[0];
-  uint32_t idx = base + 6;
+  uint32_t idx = base + WL_SLOT_CAP;
   while (true) {
     uint32_t e = __ldg(keys + idx);
     if (e >= q) return (e == q && idx < wl.W) ? (int)idx : -1;

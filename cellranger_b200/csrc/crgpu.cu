@@ -481,38 +481,41 @@ int crgpu_whitelist_add(crgpu_ctx* c, const uint8_t* seqs, uint64_t n, int L, co
     CU(cudaMemcpy(dk.p, keys.data(), (size_t)(W + 4) * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dof.p, offs.data(), (n_buckets + 1) * 4, cudaMemcpyHostToDevice));
     if (o == 0) {
-      // exact-membership slots: about 3 entries per bucket on average, six at most inline; the suffix kept in a
-      // slot must fit 16 bits
+      // exact-membership slots: about 6.5 entries per bucket on average, fourteen at most inline; the suffix
+      // kept in a slot must fit 16 bits
+      if ((uint64_t)W >= (1ull << 27)) return fail(CRGPU_E_INVALID, "whitelist too large for the slot table");
       int pe = 0;
       while (pe < nbits && (1ull << pe) < (uint64_t)W) pe++;  // ceil(log2 W)
-      pe = pe > 2 ? pe - 2 : 0;  // about 3 entries per bucket: the table stays small enough for L2
+      pe = pe > 3 ? pe - 3 : 0;  // 32 bytes per ~6.5 entries: the table stays small enough for L2
       if (pe < nbits - 16) pe = nbits - 16;
       if (pe > 26) pe = 26;
       if (pe > nbits) pe = nbits;
       const int sshift = nbits - pe;
       const uint64_t nb = 1ull << pe;
-      std::vector<uint4> slots(nb, make_uint4(0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu));
+      constexpr uint32_t CAP = 14;
+      std::vector<uint4> slots(2 * nb, make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu));
+      for (uint64_t b = 0; b < nb; b++) slots[2 * b].x = 0u;
       {
+        const uint32_t smask = (sshift >= 32) ? 0xFFFFFFFFu : ((1u << sshift) - 1u);
         uint32_t i = 0;
         while (i < W) {
           const uint64_t b = sshift >= 32 ? 0 : (keys[i] >> sshift);
           uint32_t j = i;
           while (j < W && (sshift >= 32 ? 0 : (keys[j] >> sshift)) == b) j++;
           const uint32_t cnt = j - i;
-          uint16_t suf[6] = {0xFFFF, 0xFFFF, 0xFFFF, 0xFFFF, 0xFFFF, 0xFFFF};
-          for (uint32_t k = 0; k < cnt && k < 6; k++) suf[k] = (uint16_t)(keys[i + k] & ((sshift >= 32) ? 0xFFFFFFFFu : ((1u << sshift) - 1u)));
-          uint4 v;
-          v.x = i | ((cnt <= 6 ? cnt : 7u) << 29);
-          v.y = suf[0] | ((uint32_t)suf[1] << 16);
-          v.z = suf[2] | ((uint32_t)suf[3] << 16);
-          v.w = suf[4] | ((uint32_t)suf[5] << 16);
-          slots[b] = v;
+          uint16_t suf[CAP];
+          for (uint32_t k = 0; k < CAP; k++) suf[k] = k < cnt ? (uint16_t)(keys[i + k] & smask) : (uint16_t)0xFFFF;
+          uint32_t wd[8];
+          wd[0] = i | ((cnt <= CAP ? cnt : 31u) << 27);
+          for (uint32_t k = 0; k < CAP / 2; k++) wd[1 + k] = suf[2 * k] | ((uint32_t)suf[2 * k + 1] << 16);
+          slots[2 * b] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+          slots[2 * b + 1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
           i = j;
         }
       }
       DevBuf de;
-      if ((rc = de.ensure(nb * sizeof(uint4)))) return rc;
-      CU(cudaMemcpy(de.p, slots.data(), nb * sizeof(uint4), cudaMemcpyHostToDevice));
+      if ((rc = de.ensure(2 * nb * sizeof(uint4)))) return rc;
+      CU(cudaMemcpy(de.p, slots.data(), 2 * nb * sizeof(uint4), cudaMemcpyHostToDevice));
       w->dev.slots = de.as<uint4>();
       w->dev.slot_shift = sshift;
       w->bufs.push_back(de);
