@@ -125,12 +125,9 @@ struct Packed {
   uint4 bcq;
 };
 
-template <int R1_LEN, int UMI_LEN>
-__device__ __forceinline__ void pack_record(const uint8_t* s_seq, const uint8_t* s_qual, int j, Packed* o) {
-  constexpr int NW = (R1_LEN + 3) / 4;
-  uint32_t ws[NW], wq[NW];
-  load_record<R1_LEN>(s_seq, j, ws);
-  load_record<R1_LEN>(s_qual, j, wq);
+// stage 1 of the packing: the barcode (so that its whitelist lookup can start), stage 2: UMI and qualities
+template <int R1_LEN>
+__device__ __forceinline__ void pack_barcode(const uint32_t (&ws)[(R1_LEN + 3) / 4], Packed* o) {
   uint32_t bad0, bad1, bad2, bad3;
   o->bc = (pack4(ws[0], &bad0) << 24) | (pack4(ws[1], &bad1) << 16) | (pack4(ws[2], &bad2) << 8) | pack4(ws[3], &bad3);
   uint32_t nmask = 0;
@@ -143,6 +140,10 @@ __device__ __forceinline__ void pack_record(const uint8_t* s_seq, const uint8_t*
         if (bb[wd] & (0x80u << (8 * by))) nmask |= 1u << (wd * 4 + by);
   }
   o->nmask = nmask;
+}
+template <int R1_LEN, int UMI_LEN>
+__device__ __forceinline__ void pack_umi(const uint32_t (&ws)[(R1_LEN + 3) / 4], const uint32_t (&wq)[(R1_LEN + 3) / 4],
+                                         Packed* o) {
   uint32_t umi = 0, ubad = 0, ulow = 0;
   constexpr int UW = (UMI_LEN + 3) / 4;
 #pragma unroll
@@ -166,6 +167,15 @@ __device__ __forceinline__ void pack_record(const uint8_t* s_seq, const uint8_t*
   o->umi_has_n = ubad != 0;
   o->umi_lowq = ulow != 0;
   o->bcq = make_uint4(wq[0], wq[1], wq[2], wq[3]);
+}
+template <int R1_LEN, int UMI_LEN>
+__device__ __forceinline__ void pack_record(const uint8_t* s_seq, const uint8_t* s_qual, int j, Packed* o) {
+  constexpr int NW = (R1_LEN + 3) / 4;
+  uint32_t ws[NW], wq[NW];
+  load_record<R1_LEN>(s_seq, j, ws);
+  load_record<R1_LEN>(s_qual, j, wq);
+  pack_barcode<R1_LEN>(ws, o);
+  pack_umi<R1_LEN, UMI_LEN>(ws, wq, o);
 }
 
 __device__ __forceinline__ unsigned long long make_evict_first_policy() {
@@ -259,25 +269,38 @@ __global__ void __launch_bounds__(THREADS) pass1_staged_kernel(const Pass1Args a
       __syncthreads();
     }
 
-    // ---- phase 1: shared memory -> registers, 2-bit packing, UMI checks ----
+    // ---- phase 1: shared memory -> registers, 2-bit packing, UMI checks. The whitelist slot of each read is
+    // requested as soon as its barcode is packed, so the rest of the packing runs under the load ----
     Packed pk[RPT];
     uint32_t feat[RPT];
     bool live[RPT];
+    WlProbe pr[RPT];
+    {
+      constexpr int NW = (R1_LEN + 3) / 4;
+      uint32_t ws[RPT][NW];
 #pragma unroll
-    for (int k = 0; k < RPT; k++) {
-      const int j = tid + k * THREADS;
-      live[k] = j < cnt;
-      if (live[k]) {
-        pack_record<R1_LEN, UMI_LEN>(stage_seq(s), stage_qual(s), j, &pk[k]);
-        feat[k] = have_feat ? stage_feat(s)[j] : NO_FEATURE;
-      } else {
-        pk[k].bc = 0;
-        pk[k].nmask = 1;
-        pk[k].umi = 0;
-        pk[k].umi_has_n = true;
-        pk[k].umi_lowq = false;
-        pk[k].bcq = make_uint4(0, 0, 0, 0);
-        feat[k] = NO_FEATURE;
+      for (int k = 0; k < RPT; k++) {
+        const int j = tid + k * THREADS;
+        live[k] = j < cnt;
+        load_record<R1_LEN>(stage_seq(s), live[k] ? j : 0, ws[k]);
+        pack_barcode<R1_LEN>(ws[k], &pk[k]);
+        pr[k] = wl_find_probe(a.wl, wl_find_begin(a.wl, pk[k].bc));
+      }
+#pragma unroll
+      for (int k = 0; k < RPT; k++) {
+        const int j = tid + k * THREADS;
+        uint32_t wq[NW];
+        load_record<R1_LEN>(stage_qual(s), live[k] ? j : 0, wq);
+        pack_umi<R1_LEN, UMI_LEN>(ws[k], wq, &pk[k]);
+        feat[k] = (have_feat && live[k]) ? stage_feat(s)[j] : NO_FEATURE;
+        if (!live[k]) {
+          pk[k].bc = 0;
+          pk[k].nmask = 1;
+          pk[k].umi = 0;
+          pk[k].umi_has_n = true;
+          pk[k].umi_lowq = false;
+          pk[k].bcq = make_uint4(0, 0, 0, 0);
+        }
       }
     }
     // Stage s is free once every warp has read its records: each warp arrives on the stage's "empty"
@@ -296,12 +319,6 @@ __global__ void __launch_bounds__(THREADS) pass1_staged_kernel(const Pass1Args a
     }
 
     // ---- phase 2: exact whitelist lookups, all loads of the RPT reads in flight together ----
-    uint32_t st0[RPT];
-#pragma unroll
-    for (int k = 0; k < RPT; k++) st0[k] = wl_find_begin(a.wl, pk[k].bc);
-    WlProbe pr[RPT];
-#pragma unroll
-    for (int k = 0; k < RPT; k++) pr[k] = wl_find_probe(a.wl, st0[k]);
     uint32_t bcw[RPT], umw[RPT];
     unsigned long long key[RPT];
     bool emit[RPT], inval[RPT];
