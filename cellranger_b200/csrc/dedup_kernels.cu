@@ -294,6 +294,44 @@ __device__ __forceinline__ void cu_probe(const unsigned long long* w_key, const 
   }
 }
 
+// Segments of at most CU_PAIR keys that lie completely inside the window are answered by comparing the key
+// with every other key of its segment (a few XOR / popcount-style tests each); only longer segments, and the
+// ones cut by the window edge, use the hash set. Segment bounds come from a bitmap of segment heads.
+constexpr int CU_PAIR = 64;
+constexpr int CU_HEAD_WORDS = CU_WIN / 32;
+
+// segment [a, b) of window position i from the head bitmap; false if it is longer than CU_PAIR (or its bounds
+// are further than the scan limit)
+__device__ __forceinline__ bool cu_small_segment(const uint32_t* heads, int i, int wn, int* a_out, int* b_out) {
+  constexpr int LIMIT = CU_PAIR / 32 + 1;  // words looked at on each side
+  int word = i >> 5;
+  const int bit = i & 31;
+  uint32_t mk = heads[word] & (0xFFFFFFFFu >> (31 - bit));
+  int steps = 0;
+  while (mk == 0u) {
+    if (++steps > LIMIT || word == 0) return false;
+    mk = heads[--word];
+  }
+  const int a = word * 32 + 31 - __clz(mk);
+  word = i >> 5;
+  mk = bit == 31 ? 0u : (heads[word] & (0xFFFFFFFEu << bit));
+  steps = 0;
+  int b = wn;
+  while (true) {
+    if (mk != 0u) {
+      b = word * 32 + __ffs(mk) - 1;
+      break;
+    }
+    if (++steps > LIMIT) return false;
+    if (++word >= CU_HEAD_WORDS) break;  // no head up to the end of the window: the segment ends at wn
+    mk = heads[word];
+  }
+  if (b > wn) b = wn;
+  *a_out = a;
+  *b_out = b;
+  return b - a <= CU_PAIR;
+}
+
 template <int UB>
 __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsigned long long* __restrict__ dkeys,
                                                                      const uint32_t* __restrict__ c0, uint64_t m,
@@ -306,7 +344,9 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
   uint32_t* table = reinterpret_cast<uint32_t*>(w_key + CU_WIN);                // CU_SLOTS
   uint32_t* bitmap = table + CU_SLOTS;                                          // CU_BITS / 32
   unsigned short* work = reinterpret_cast<unsigned short*>(bitmap + CU_BITS / 32);  // CU_TILE
-  __shared__ uint32_t s_nwork;
+  __shared__ uint32_t heads[CU_HEAD_WORDS];  // bit i: window key i starts a segment
+  __shared__ uint32_t bigs[CU_HEAD_WORDS];   // bit i: window key i belongs to a long or cut segment
+  __shared__ uint32_t s_nwork, s_any_big;
 
   const int ub = kl.umi_bits;
   const unsigned long long umask = (1ull << ub) - 1ull;
@@ -318,41 +358,87 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
   const uint64_t w_hi = q_hi + CU_HALO < m ? q_hi + CU_HALO : m;
   const int wn = (int)(w_hi - w_lo);
 
-  if (tid == 0) s_nwork = 0;
+  if (tid == 0) {
+    s_nwork = 0;
+    s_any_big = 0;
+  }
   for (int i = tid; i < wn; i += CU_THREADS) w_key[i] = dkeys[w_lo + i];
-  for (int i = tid; i < CU_SLOTS; i += CU_THREADS) table[i] = CU_EMPTY;
-  for (int i = tid; i < CU_BITS / 32; i += CU_THREADS) bitmap[i] = 0u;
   __syncthreads();
   // is the first / last segment of the window cut by the window edge?
   const unsigned long long seg_l = w_key[0] >> ub, seg_r = w_key[wn - 1] >> ub;
   const bool cut_l = w_lo > 0 && (dkeys[w_lo - 1] >> ub) == seg_l;
   const bool cut_r = w_hi < m && (dkeys[w_hi] >> ub) == seg_r;
-  // keys that are alone in their segment can be nobody's neighbour: they stay out of the tables
-  cu_build(w_key, wn, table, bitmap, [&](int i, unsigned long long k) {
-    const unsigned long long sg = k >> ub;
-    const bool alone = (i == 0 ? !cut_l : (w_key[i - 1] >> ub) != sg) && (i + 1 >= wn ? !cut_r : (w_key[i + 1] >> ub) != sg);
-    return !alone;
-  });
-
-  // singletons are done; everything else goes to the work list (bit 15: the segment is cut)
-  const int q_off = (int)(q_lo - w_lo);
-  const int qn = (int)(q_hi - q_lo);
-  for (int qi = tid; qi < qn; qi += CU_THREADS) {
-    const int i = q_off + qi;
-    const unsigned long long key = w_key[i];
-    const unsigned long long seg = key >> ub;
-    const uint32_t lib = (uint32_t)(key >> kl.lib_shift) & lmask;
-    const bool is_cut = (cut_l && seg == seg_l) || (cut_r && seg == seg_r);
-    const bool alone = (i == 0 || (w_key[i - 1] >> ub) != seg) && (i + 1 >= wn || (w_key[i + 1] >> ub) != seg);
-    if (!((corr_mask >> lib) & 1u) || (alone && !is_cut))
-      best[w_lo + i] = (uint32_t)(w_lo + i);
-    else
-      work[atomicAdd(&s_nwork, 1u)] = (unsigned short)(i | (is_cut ? 0x8000 : 0));
+  // segment heads (position wn counts as a head so that the last segment is closed)
+  for (int i = tid; i < CU_WIN; i += CU_THREADS) {  // warp-uniform trip count: ballots inside
+    const bool head = i < wn ? (i == 0 || (w_key[i] >> ub) != (w_key[i - 1] >> ub)) : (i == wn);
+    const uint32_t mk = __ballot_sync(0xFFFFFFFFu, head);
+    if ((tid & 31) == 0) heads[i >> 5] = mk;
   }
   __syncthreads();
 
   unsigned long long n_corr = 0, n_corr_reads = 0;
+  // classify every window key; tile keys of short segments are answered here, pairwise
+  const int q_off = (int)(q_lo - w_lo);
+  const int q_end = q_off + (int)(q_hi - q_lo);
+  bool any_big = false;
+  for (int i = tid; i < CU_WIN; i += CU_THREADS) {
+    bool big = false;
+    if (i < wn) {
+      const unsigned long long key = w_key[i];
+      const unsigned long long seg = key >> ub;
+      const bool is_cut = (cut_l && seg == seg_l) || (cut_r && seg == seg_r);
+      int a = i, b = i + 1;
+      const bool small = !is_cut && cu_small_segment(heads, i, wn, &a, &b);
+      const bool in_tile = i >= q_off && i < q_end;
+      const uint32_t lib = (uint32_t)(key >> kl.lib_shift) & lmask;
+      const bool correct = ((corr_mask >> lib) & 1u) != 0u;
+      big = !small && correct;
+      if (in_tile) {
+        const uint64_t j = w_lo + i;
+        if (!correct || (small && b - a == 1)) {
+          best[j] = (uint32_t)j;
+        } else if (small) {
+          const uint32_t lo = (uint32_t)key;
+          BestPick bp{0u, key & umask, (uint32_t)j};
+          bool have_own = false;
+          for (int t = a; t < b; t++) {
+            const uint32_t x = (uint32_t)w_key[t] ^ lo;  // same segment: only UMI bits can differ
+            const uint32_t y = (x | (x >> 1)) & 0x55555555u;
+            if (y != 0u && (y & (y - 1u)) == 0u) {
+              if (!have_own) {
+                bp.count = c0[j];
+                have_own = true;
+              }
+              bp.consider(c0[w_lo + t], w_key[t] & umask, (uint32_t)(w_lo + t));
+            }
+          }
+          best[j] = bp.idx;
+          if (bp.idx != (uint32_t)j) {
+            const uint32_t own = c0[j];
+            atomicAdd(inc + bp.idx, (1ull << 40) | (unsigned long long)own);
+            n_corr++;
+            n_corr_reads += own;
+          }
+        } else {
+          work[atomicAdd(&s_nwork, 1u)] = (unsigned short)(i | (is_cut ? 0x8000 : 0));
+        }
+      }
+    }
+    const uint32_t mk = __ballot_sync(0xFFFFFFFFu, big);
+    if ((tid & 31) == 0) bigs[i >> 5] = mk;
+    any_big |= mk != 0u;
+  }
+  if (any_big && (tid & 31) == 0) s_any_big = 1u;
+  __syncthreads();
   const int nwork = (int)s_nwork;
+  if (s_any_big) {  // block-uniform
+    for (int i = tid; i < CU_SLOTS; i += CU_THREADS) table[i] = CU_EMPTY;
+    for (int i = tid; i < CU_BITS / 32; i += CU_THREADS) bitmap[i] = 0u;
+    __syncthreads();
+    cu_build(w_key, wn, table, bitmap, [&](int i, unsigned long long) { return ((bigs[i >> 5] >> (i & 31)) & 1u) != 0u; });
+    __syncthreads();
+  }
+
   for (int w = tid; w < nwork; w += CU_THREADS) {
     const int i = work[w] & 0x7FFF;
     const bool is_cut = (work[w] & 0x8000) != 0;
