@@ -297,13 +297,14 @@ __device__ __forceinline__ void cu_probe(const unsigned long long* w_key, const 
 // Segments of at most CU_PAIR keys that lie completely inside the window are answered by comparing the key
 // with every other key of its segment (a few XOR / popcount-style tests each); only longer segments, and the
 // ones cut by the window edge, use the hash set. Segment bounds come from a bitmap of segment heads.
-constexpr int CU_PAIR = 64;
+constexpr int CU_PAIR = 32;  // default; CRGPU_CU_PAIR overrides it for profiling
 constexpr int CU_HEAD_WORDS = CU_WIN / 32;
 
 // segment [a, b) of window position i from the head bitmap; false if it is longer than CU_PAIR (or its bounds
 // are further than the scan limit)
-__device__ __forceinline__ bool cu_small_segment(const uint32_t* heads, int i, int wn, int* a_out, int* b_out) {
-  constexpr int LIMIT = CU_PAIR / 32 + 1;  // words looked at on each side
+__device__ __forceinline__ bool cu_small_segment(const uint32_t* heads, int i, int wn, int pair_max, int* a_out,
+                                                 int* b_out) {
+  const int LIMIT = pair_max / 32 + 1;  // words looked at on each side
   int word = i >> 5;
   const int bit = i & 31;
   uint32_t mk = heads[word] & (0xFFFFFFFFu >> (31 - bit));
@@ -329,7 +330,7 @@ __device__ __forceinline__ bool cu_small_segment(const uint32_t* heads, int i, i
   if (b > wn) b = wn;
   *a_out = a;
   *b_out = b;
-  return b - a <= CU_PAIR;
+  return b - a <= pair_max;
 }
 
 template <int UB>
@@ -338,15 +339,17 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
                                                                      KeyLayout kl, uint32_t corr_mask,
                                                                      uint32_t* __restrict__ best,
                                                                      unsigned long long* __restrict__ inc,
-                                                                     unsigned long long* __restrict__ scalars) {
+                                                                     unsigned long long* __restrict__ scalars,
+                                                                     int pair_max) {
   extern __shared__ __align__(16) unsigned char cu_smem[];
   unsigned long long* w_key = reinterpret_cast<unsigned long long*>(cu_smem);  // CU_WIN
   uint32_t* table = reinterpret_cast<uint32_t*>(w_key + CU_WIN);                // CU_SLOTS
   uint32_t* bitmap = table + CU_SLOTS;                                          // CU_BITS / 32
   unsigned short* work = reinterpret_cast<unsigned short*>(bitmap + CU_BITS / 32);  // CU_TILE
+  unsigned short* w_cnt = work + CU_TILE;  // CU_WIN raw counts of the home window, saturated at 0xFFFF
   __shared__ uint32_t heads[CU_HEAD_WORDS];  // bit i: window key i starts a segment
   __shared__ uint32_t bigs[CU_HEAD_WORDS];   // bit i: window key i belongs to a long or cut segment
-  __shared__ uint32_t s_nwork, s_any_big;
+  __shared__ uint32_t s_nwork, s_any_big, s_ncut;
 
   const int ub = kl.umi_bits;
   const unsigned long long umask = (1ull << ub) - 1ull;
@@ -361,8 +364,18 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
   if (tid == 0) {
     s_nwork = 0;
     s_any_big = 0;
+    s_ncut = 0;
   }
-  for (int i = tid; i < wn; i += CU_THREADS) w_key[i] = dkeys[w_lo + i];
+  for (int i = tid; i < wn; i += CU_THREADS) {
+    w_key[i] = dkeys[w_lo + i];
+    const uint32_t c = c0[w_lo + i];
+    w_cnt[i] = (unsigned short)(c < 0xFFFFu ? c : 0xFFFFu);
+  }
+  // raw count of home-window key i: from shared memory unless it saturated the 16-bit cache
+  auto count_of = [&](int i) -> uint32_t {
+    const uint32_t c = w_cnt[i];
+    return c != 0xFFFFu ? c : c0[w_lo + i];
+  };
   __syncthreads();
   // is the first / last segment of the window cut by the window edge?
   const unsigned long long seg_l = w_key[0] >> ub, seg_r = w_key[wn - 1] >> ub;
@@ -388,7 +401,7 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
       const unsigned long long seg = key >> ub;
       const bool is_cut = (cut_l && seg == seg_l) || (cut_r && seg == seg_r);
       int a = i, b = i + 1;
-      const bool small = !is_cut && cu_small_segment(heads, i, wn, &a, &b);
+      const bool small = !is_cut && cu_small_segment(heads, i, wn, pair_max, &a, &b);
       const bool in_tile = i >= q_off && i < q_end;
       const uint32_t lib = (uint32_t)(key >> kl.lib_shift) & lmask;
       const bool correct = ((corr_mask >> lib) & 1u) != 0u;
@@ -406,21 +419,22 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
             const uint32_t y = (x | (x >> 1)) & 0x55555555u;
             if (y != 0u && (y & (y - 1u)) == 0u) {
               if (!have_own) {
-                bp.count = c0[j];
+                bp.count = count_of(i);
                 have_own = true;
               }
-              bp.consider(c0[w_lo + t], w_key[t] & umask, (uint32_t)(w_lo + t));
+              bp.consider(count_of(t), w_key[t] & umask, (uint32_t)(w_lo + t));
             }
           }
           best[j] = bp.idx;
           if (bp.idx != (uint32_t)j) {
-            const uint32_t own = c0[j];
+            const uint32_t own = count_of(i);
             atomicAdd(inc + bp.idx, (1ull << 40) | (unsigned long long)own);
             n_corr++;
             n_corr_reads += own;
           }
         } else {
           work[atomicAdd(&s_nwork, 1u)] = (unsigned short)(i | (is_cut ? 0x8000 : 0));
+          if (is_cut) s_ncut = 1u;
         }
       }
     }
@@ -448,21 +462,22 @@ __global__ void __launch_bounds__(CU_THREADS, 2) correct_umis_kernel(const unsig
     bool have_own = false;
     cu_probe<UB>(w_key, table, bitmap, key, ub, [&](uint32_t idx) {
       if (!have_own) {
-        bp.count = c0[j];
+        bp.count = count_of(i);
         have_own = true;
       }
-      bp.consider(c0[w_lo + idx], w_key[idx] & umask, (uint32_t)(w_lo + idx));
+      bp.consider(count_of((int)idx), w_key[idx] & umask, (uint32_t)(w_lo + idx));
     });
     best[j] = bp.idx;  // provisional for a cut segment: the rest of it is still to come
     if (!is_cut && bp.idx != (uint32_t)j) {
-      const uint32_t own = c0[j];
+      const uint32_t own = count_of(i);
       atomicAdd(inc + bp.idx, (1ull << 40) | (unsigned long long)own);
       n_corr++;
       n_corr_reads += own;
     }
   }
-  // further windows for the cut segments (block-uniform conditions)
-  if (cut_l || cut_r) {
+  // further windows for the cut segments (block-uniform conditions); a window edge that cuts a segment of the
+  // halo only - none of the tile's keys - needs nothing
+  if ((cut_l || cut_r) && s_ncut) {
     const uint64_t home_lo = w_lo;
     for (int side = 0; side < 2; side++) {
       if (side == 0 ? !cut_l : !cut_r) continue;
@@ -1055,12 +1070,15 @@ int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
   cudaMemsetAsync(b.inc, 0, m * 8, st);
   cudaMemsetAsync(b.low, 0, m, st);
   {
-    const size_t smem = (size_t)CU_WIN * 8 + (size_t)CU_SLOTS * 4 + (size_t)CU_BITS / 8 + (size_t)CU_TILE * 2;
+    const size_t smem = (size_t)CU_WIN * 8 + (size_t)CU_SLOTS * 4 + (size_t)CU_BITS / 8 + (size_t)CU_TILE * 2 +
+                        (size_t)CU_WIN * 2;
     auto kern = b.kl.umi_bits == 24 ? correct_umis_kernel<24>
                 : b.kl.umi_bits == 20 ? correct_umis_kernel<20> : correct_umis_kernel<0>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const unsigned blocks = (unsigned)((m + CU_TILE - 1) / CU_TILE);
-    kern<<<blocks, CU_THREADS, smem, st>>>(b.dkeys, b.c0, m, b.kl, b.umi_correction_mask, b.best, b.inc, b.scalars);
+    const int pair_max = getenv("CRGPU_CU_PAIR") ? atoi(getenv("CRGPU_CU_PAIR")) : CU_PAIR;
+    kern<<<blocks, CU_THREADS, smem, st>>>(b.dkeys, b.c0, m, b.kl, b.umi_correction_mask, b.best, b.inc, b.scalars,
+                                           pair_max < 1 ? 1 : (pair_max > CU_HALO ? CU_HALO : pair_max));
     launches++;
   }
   mark("count.dedup.low_support");
