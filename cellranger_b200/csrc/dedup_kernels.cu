@@ -209,8 +209,8 @@ struct BestPick {
 // hash set. A segment longer than the halo is cut by the window edge: its keys are probed against
 // further windows until the whole segment has been seen.
 constexpr int CU_THREADS = 512;
-constexpr int CU_TILE = 2048;
-constexpr int CU_HALO = 1024;
+constexpr int CU_TILE = 3072;
+constexpr int CU_HALO = 512;
 constexpr int CU_WIN = CU_TILE + 2 * CU_HALO;  // 4096
 constexpr int CU_SLOTS = 8192;                 // 32-bit slots: native shared-memory CAS
 constexpr int CU_BITS = 1 << 18;               // presence bitmap (32 KB)
@@ -224,8 +224,12 @@ __device__ __forceinline__ uint32_t cu_mix(uint32_t lo, uint32_t hi_mix) {
   return h ^ (h >> 15);
 }
 __device__ __forceinline__ uint32_t cu_slot(uint32_t h) { return (h * 0x2C1B3C6Du) >> 19; }  // 13 bits
-__device__ __forceinline__ uint32_t cu_bit(uint32_t h) { return h >> 14; }                    // 18 bits
 static_assert(CU_SLOTS == 8192 && CU_BITS == (1 << 18), "hash field widths");
+// Presence-bitmap index: XOR-linear in the low key word (an 18-bit fold of it) plus a per-segment term, so
+// the index of a mutant is the index of the key XOR a compile-time constant - one instruction per mutant.
+// Bit b lives in word b >> 5 at position 31 - (b & 31), which lets a funnel shift bring it to the sign bit.
+__device__ __forceinline__ uint32_t cu_fold(uint32_t lo) { return (lo ^ (lo >> 18)) & (CU_BITS - 1); }
+__device__ __forceinline__ uint32_t cu_bit_of(uint32_t lo, uint32_t hi_mix) { return cu_fold(lo) ^ (hi_mix >> 14); }
 
 // insert the keys w_key[0..n) that pass `take` into the hash set and the bitmap (tables already cleared)
 template <typename Take>
@@ -234,10 +238,10 @@ __device__ __forceinline__ void cu_build(const unsigned long long* w_key, int n,
   for (int i = threadIdx.x; i < n; i += CU_THREADS) {
     const unsigned long long k = w_key[i];
     if (!take(i, k)) continue;
-    const uint32_t h = cu_mix((uint32_t)k, cu_hi_mix(k));
-    const uint32_t b = cu_bit(h);
-    atomicOr(&bitmap[b >> 5], 1u << (b & 31));
-    uint32_t sl = cu_slot(h);
+    const uint32_t hm = cu_hi_mix(k);
+    const uint32_t b = cu_bit_of((uint32_t)k, hm);
+    atomicOr(&bitmap[b >> 5], 0x80000000u >> (b & 31));
+    uint32_t sl = cu_slot(cu_mix((uint32_t)k, hm));
     while (atomicCAS(&table[sl], CU_EMPTY, (uint32_t)i) != CU_EMPTY) sl = (sl + 1) & (CU_SLOTS - 1);
   }
 }
@@ -252,32 +256,33 @@ template <int UB, typename Hit>
 __device__ __forceinline__ void cu_probe(const unsigned long long* w_key, const uint32_t* table,
                                          const uint32_t* bitmap, unsigned long long key, int ub, Hit hit) {
   const uint32_t lo = (uint32_t)key, hm = cu_hi_mix(key);
-  uint32_t cand_lo = 0u, cand_hi = 0u;  // bit m = mutant m (3 per base, base 0 = least significant)
+  // candidate bits are shifted in from the right: after the loop mutant m sits at bit (n_mut - 1 - m)
+  uint32_t cand_lo = 0u, cand_hi = 0u;
+  const uint32_t bk = cu_bit_of(lo, hm);
+  int n_mut;
   if constexpr (UB > 0) {
+    n_mut = 3 * (UB / 2);
 #pragma unroll
     for (int m = 0; m < 3 * (UB / 2); m++) {
-      const uint32_t b = cu_bit(cu_mix(lo ^ ((uint32_t)(m % 3 + 1) << (2 * (m / 3))), hm));
-      const uint32_t bit = (bitmap[b >> 5] >> (b & 31)) & 1u;
-      if (m < 32)
-        cand_lo |= bit << (m & 31);
-      else
-        cand_hi |= bit << (m & 31);
+      const uint32_t delta = (uint32_t)(m % 3 + 1) << (2 * (m / 3));
+      const uint32_t b = bk ^ ((delta ^ (delta >> 18)) & (CU_BITS - 1));  // constant folded
+      const uint32_t t = __funnelshift_l(0u, bitmap[b >> 5], b);           // presence bit -> sign bit
+      cand_hi = __funnelshift_l(cand_lo, cand_hi, 1);
+      cand_lo = __funnelshift_l(t, cand_lo, 1);
     }
   } else {
-    int m = 0;
+    n_mut = 0;
     for (int sh = 0; sh < ub; sh += 2)
-      for (uint32_t d = 1; d < 4; d++, m++) {
-        const uint32_t b = cu_bit(cu_mix(lo ^ (d << sh), hm));
-        const uint32_t bit = (bitmap[b >> 5] >> (b & 31)) & 1u;
-        if (m < 32)
-          cand_lo |= bit << (m & 31);
-        else
-          cand_hi |= bit << (m & 31);
+      for (uint32_t d = 1; d < 4; d++, n_mut++) {
+        const uint32_t b = bk ^ cu_fold(d << sh);
+        const uint32_t t = __funnelshift_l(0u, bitmap[b >> 5], b);
+        cand_hi = __funnelshift_l(cand_lo, cand_hi, 1);
+        cand_lo = __funnelshift_l(t, cand_lo, 1);
       }
   }
   unsigned long long cand = ((unsigned long long)cand_hi << 32) | cand_lo;
   while (cand) {
-    const int mi = __ffsll((long long)cand) - 1;
+    const int mi = n_mut - 1 - (__ffsll((long long)cand) - 1);
     cand &= cand - 1ull;
     const uint32_t tlo = lo ^ ((uint32_t)(mi % 3 + 1) << (2 * (mi / 3)));
     const unsigned long long t = (key & 0xFFFFFFFF00000000ull) | tlo;
