@@ -1237,7 +1237,7 @@ int crgpu_count(crgpu_ctx* c) {
   b.sort_temp_bytes = c->sort_temp.cap;
   {
     int slot_bits = 16;
-    while (slot_bits < 29 && (1ull << slot_bits) < 8 * cap) slot_bits++;
+    while (slot_bits < 30 && (1ull << slot_bits) < 8 * cap) slot_bits++;
     if ((rc = c->ls_slots.ensure(((size_t)1 << slot_bits) / 4))) return rc;
     b.slots = c->ls_slots.as<uint32_t>();
     b.slots_bytes = c->ls_slots.cap;

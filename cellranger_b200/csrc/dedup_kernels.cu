@@ -583,12 +583,13 @@ __global__ void make_key2_kernel(const unsigned long long* __restrict__ dkeys, u
 // features, which is rare. Each distinct key hashes its (rank, library, umi) into a table of 2-bit
 // slots: the first visitor sets bit 0, any later visitor sets bit 1. Keys whose slot has bit 1 are the
 // candidates (all true groups plus hash collisions); only they are sorted and regrouped exactly.
-// Slot of a key's (rank, library, umi) group. The table is split into regions of 2^17 slots (32 KB): the
+// Slot of a key's (rank, library, umi) group. The table is split into regions of 2^17 slots (32 KB; larger
+// regions give fewer false candidates but measured slower - locality wins): the
 // region is chosen by the barcode rank alone, so the keys of one barcode - which are neighbours in the
 // sorted table and therefore processed together - stay inside one L2-resident region.
-#define LS_REGION_BITS 17
+static int ls_region_bits_host() { return getenv("CRGPU_LS_REGION") ? atoi(getenv("CRGPU_LS_REGION")) : 17; }
 __device__ __forceinline__ unsigned long long group_slot(unsigned long long key, const KeyLayout& kl,
-                                                         const FieldMasks& fm, int slot_bits) {
+                                                         const FieldMasks& fm, int slot_bits, int LS_REGION_BITS) {
   unsigned long long umi = key & ((1ull << fm.ubits) - 1ull);
   unsigned long long lib = (key >> kl.lib_shift) & ((1ull << fm.lbits) - 1ull);
   unsigned long long rank = key >> kl.rank_shift;
@@ -604,10 +605,11 @@ __device__ __forceinline__ unsigned long long group_slot(unsigned long long key,
 }
 
 __global__ void __launch_bounds__(256) ls_mark_kernel(const unsigned long long* __restrict__ dkeys, uint64_t m,
-                                                      KeyLayout kl, uint32_t* __restrict__ slots, int slot_bits) {
+                                                      KeyLayout kl, uint32_t* __restrict__ slots, int slot_bits,
+                                                      int region_bits) {
   const FieldMasks fm = field_masks(kl);
   for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < m; j += (uint64_t)gridDim.x * blockDim.x) {
-    unsigned long long h = group_slot(dkeys[j], kl, fm, slot_bits);
+    unsigned long long h = group_slot(dkeys[j], kl, fm, slot_bits, region_bits);
     uint32_t bit = 1u << (2 * (h & 15));
     uint32_t old = atomicOr(slots + (h >> 4), bit);
     if (old & bit) atomicOr(slots + (h >> 4), bit << 1);
@@ -616,7 +618,8 @@ __global__ void __launch_bounds__(256) ls_mark_kernel(const unsigned long long* 
 
 __global__ void __launch_bounds__(256) ls_collect_kernel(const unsigned long long* __restrict__ dkeys, uint64_t m,
                                                          KeyLayout kl, const uint32_t* __restrict__ slots,
-                                                         int slot_bits, unsigned long long* __restrict__ cand,
+                                                         int slot_bits, int region_bits,
+                                                         unsigned long long* __restrict__ cand,
                                                          unsigned long long* __restrict__ n_cand) {
   __shared__ uint32_t scan_s[9];
   __shared__ unsigned long long base_s;
@@ -628,7 +631,7 @@ __global__ void __launch_bounds__(256) ls_collect_kernel(const unsigned long lon
     unsigned long long k2 = 0;
     if (j < m) {
       unsigned long long k = dkeys[j];
-      unsigned long long h = group_slot(k, kl, fm, slot_bits);
+      unsigned long long h = group_slot(k, kl, fm, slot_bits, region_bits);
       hit = (slots[h >> 4] >> (2 * (h & 15) + 1)) & 1u;
       if (hit) {
         unsigned long long umi = k & ((1ull << fm.ubits) - 1ull);
@@ -1090,12 +1093,14 @@ int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
   // 3. low-support filter: candidates by hashing (rank, library, umi), exact regrouping of those only
   if (b.filter_umis) {
     int slot_bits = 16;
-    while (slot_bits < 29 && (1ull << slot_bits) < 8 * m) slot_bits++;
+    const int slot_cap = getenv("CRGPU_LS_SLOTCAP") ? atoi(getenv("CRGPU_LS_SLOTCAP")) : 29;
+    const int region_bits = ls_region_bits_host();
+    while (slot_bits < slot_cap && (1ull << slot_bits) < 8 * m) slot_bits++;
     const size_t slot_bytes = ((size_t)1 << slot_bits) / 4;  // 2 bits per slot
     if (b.slots_bytes < slot_bytes) return -1;
     cudaMemsetAsync(b.slots, 0, slot_bytes, st);
-    ls_mark_kernel<<<grid_for(m, 256, 148 * 32), 256, 0, st>>>(b.dkeys, m, b.kl, b.slots, slot_bits);
-    ls_collect_kernel<<<grid_for(m, 256, 148 * 16), 256, 0, st>>>(b.dkeys, m, b.kl, b.slots, slot_bits, b.key2,
+    ls_mark_kernel<<<grid_for(m, 256, 148 * 32), 256, 0, st>>>(b.dkeys, m, b.kl, b.slots, slot_bits, region_bits);
+    ls_collect_kernel<<<grid_for(m, 256, 148 * 16), 256, 0, st>>>(b.dkeys, m, b.kl, b.slots, slot_bits, region_bits, b.key2,
                                                                  b.scalars + 9);
     launches += 2;
     unsigned long long n_cand = 0;
@@ -1103,7 +1108,9 @@ int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
     cudaStreamSynchronize(st);
     if (n_cand) {
       unsigned long long* sorted2 = nullptr;
-      launches += sort_keys(b.key2, b.key2_alt, n_cand, b.kl.total_bits, b.sort_temp, b.sort_temp_bytes, &sorted2, st);
+      // grouping by (rank, library, umi) only needs the bits above the feature field
+      launches += sort_keys(b.key2, b.key2_alt, n_cand, b.kl.total_bits, b.sort_temp, b.sort_temp_bytes, &sorted2, st,
+                            field_masks(b.kl).fbits);
       low_support_kernel<<<grid_for(n_cand, 256, 148 * 32), 256, 0, st>>>(sorted2, n_cand, m, b.kl, b.dkeys, b.c0,
                                                                           b.best, b.inc, b.low, b.scalars);
       launches++;

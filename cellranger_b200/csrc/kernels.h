@@ -82,14 +82,16 @@ int launch_emit_keys(const EmitArgs& a, cudaStream_t st);
 int launch_valid_counts(const uint32_t* prior, const uint32_t* corrected, uint32_t* out, uint64_t n, cudaStream_t st);
 
 // ---- sort (sort.cu) ----
-// sorts n 64-bit keys on bits [0, end_bit); result in *out (one of the two buffers)
+// sorts n 64-bit keys on bits [begin_bit, end_bit) (stable: lower bits keep their input order); result in
+// *out (one of the two buffers)
 int sort_keys(unsigned long long* keys, unsigned long long* alt, uint64_t n, int end_bit, void* temp,
-              size_t temp_bytes, unsigned long long** out, cudaStream_t st);
+              size_t temp_bytes, unsigned long long** out, cudaStream_t st, int begin_bit = 0);
 size_t sort_temp_bytes(uint64_t n);
 int sort_num_passes(int end_bit);
-int sort_histograms(const unsigned long long* keys, uint64_t n, int end_bit, void* temp, cudaStream_t st);
+int sort_histograms(const unsigned long long* keys, uint64_t n, int end_bit, void* temp, cudaStream_t st,
+                    int begin_bit = 0);
 int sort_passes(unsigned long long* keys, unsigned long long* alt, uint64_t n, int end_bit, void* temp,
-                unsigned long long** out, cudaStream_t st);
+                unsigned long long** out, cudaStream_t st, int begin_bit = 0);
 
 // ---- dedup / count (dedup_kernels.cu) ----
 struct DedupBuffers {

@@ -20,14 +20,14 @@ constexpr int MIN_TILE = 2048;  // smallest tile of any configuration (sizes the
 
 // ---- upfront histograms: hist[pass][digit] over all keys ----
 __global__ void __launch_bounds__(512) radix_hist_kernel(const unsigned long long* __restrict__ keys, uint64_t n,
-                                                         int n_passes, unsigned long long* __restrict__ hist) {
+                                                         int n_passes, int begin_bit, unsigned long long* __restrict__ hist) {
   __shared__ uint32_t s_hist[MAX_PASSES * RADIX];
   for (int i = threadIdx.x; i < n_passes * RADIX; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
     unsigned long long k = keys[i];
-    for (int p = 0; p < n_passes; p++) atomicAdd(&s_hist[p * RADIX + (int)((k >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
+    for (int p = 0; p < n_passes; p++) atomicAdd(&s_hist[p * RADIX + (int)((k >> (begin_bit + p * RADIX_BITS)) & (RADIX - 1))], 1u);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < n_passes * RADIX; i += blockDim.x)
@@ -261,8 +261,8 @@ size_t sort_temp_bytes(uint64_t n) {
   return (size_t)MAX_PASSES * RADIX * 8 + (size_t)(tiles + 1) * RADIX * 8 + 256;
 }
 
-static int plan_passes(int end_bit) {
-  int n_passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
+static int plan_passes(int end_bit, int begin_bit = 0) {
+  int n_passes = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
   if (n_passes < 1) n_passes = 1;
   if (n_passes > MAX_PASSES) n_passes = MAX_PASSES;
   return n_passes;
@@ -271,20 +271,21 @@ static int plan_passes(int end_bit) {
 int sort_num_passes(int end_bit) { return plan_passes(end_bit); }
 
 // step 1: digit histograms of every pass + their exclusive scans
-int sort_histograms(const unsigned long long* keys, uint64_t n, int end_bit, void* temp, cudaStream_t st) {
+int sort_histograms(const unsigned long long* keys, uint64_t n, int end_bit, void* temp, cudaStream_t st,
+                    int begin_bit) {
   if (n <= 1) return 0;
-  const int n_passes = plan_passes(end_bit);
+  const int n_passes = plan_passes(end_bit, begin_bit);
   unsigned long long* hist = reinterpret_cast<unsigned long long*>(temp);
   cudaMemsetAsync(hist, 0, (size_t)MAX_PASSES * RADIX * 8, st);
   int hgrid = (int)std::min<uint64_t>((n + 511) / 512, 148ull * 4);
-  radix_hist_kernel<<<hgrid, 512, 0, st>>>(keys, n, n_passes, hist);
+  radix_hist_kernel<<<hgrid, 512, 0, st>>>(keys, n, n_passes, begin_bit, hist);
   radix_scan_hist_kernel<<<n_passes, RADIX, 0, st>>>(hist);
   return 2;
 }
 
 template <int THREADS, int ITEMS, int MIN_BLOCKS, bool BALLOT, int RANK, int LBK>
-static int run_passes(unsigned long long* keys, unsigned long long* alt, uint64_t n, int n_passes, void* temp,
-                      unsigned long long** out, cudaStream_t st) {
+static int run_passes(unsigned long long* keys, unsigned long long* alt, uint64_t n, int n_passes, int begin_bit,
+                      void* temp, unsigned long long** out, cudaStream_t st) {
   constexpr int TILE = THREADS * ITEMS;
   uint64_t tiles = (n + TILE - 1) / TILE;
   uint64_t max_tiles = (n + MIN_TILE - 1) / MIN_TILE;
@@ -301,7 +302,7 @@ static int run_passes(unsigned long long* keys, unsigned long long* alt, uint64_
   for (int p = 0; p < n_passes; p++) {
     cudaMemsetAsync(desc, 0, (size_t)tiles * RADIX * 8, st);
     cudaMemsetAsync(ticket, 0, 4, st);
-    kern<<<(unsigned)tiles, THREADS, smem, st>>>(src, dst, n, p * RADIX_BITS, hist + (size_t)p * RADIX, desc, ticket);
+    kern<<<(unsigned)tiles, THREADS, smem, st>>>(src, dst, n, begin_bit + p * RADIX_BITS, hist + (size_t)p * RADIX, desc, ticket);
     launches++;
     std::swap(src, dst);
   }
@@ -311,26 +312,26 @@ static int run_passes(unsigned long long* keys, unsigned long long* alt, uint64_
 
 // step 2: the onesweep passes; result in *out
 int sort_passes(unsigned long long* keys, unsigned long long* alt, uint64_t n, int end_bit, void* temp,
-                unsigned long long** out, cudaStream_t st) {
+                unsigned long long** out, cudaStream_t st, int begin_bit) {
   *out = keys;
   if (n <= 1) return 0;
-  const int np = plan_passes(end_bit);
+  const int np = plan_passes(end_bit, begin_bit);
   const int cfg = getenv("CRGPU_SORT_CFG") ? atoi(getenv("CRGPU_SORT_CFG")) : 0;
   switch (cfg) {  // CRGPU_SORT_CFG: variants kept for profiling; 0 = the measured best on B200
-    case 1: return run_passes<256, 16, 4, false, 0, 4>(keys, alt, n, np, temp, out, st);  // match.any, not ballots
-    case 2: return run_passes<512, 12, 2, true, 0, 4>(keys, alt, n, np, temp, out, st);
-    case 3: return run_passes<384, 16, 3, true, 0, 4>(keys, alt, n, np, temp, out, st);
-    case 4: return run_passes<256, 16, 4, true, 1, 4>(keys, alt, n, np, temp, out, st);  // peers re-read the counter
-    case 5: return run_passes<256, 16, 4, true, 0, 1>(keys, alt, n, np, temp, out, st);  // one descriptor per step
-    case 6: return run_passes<256, 16, 4, true, 0, 8>(keys, alt, n, np, temp, out, st);
-    default: return run_passes<256, 16, 4, true, 0, 4>(keys, alt, n, np, temp, out, st);
+    case 1: return run_passes<256, 16, 4, false, 0, 4>(keys, alt, n, np, begin_bit, temp, out, st);  // match.any, not ballots
+    case 2: return run_passes<512, 12, 2, true, 0, 4>(keys, alt, n, np, begin_bit, temp, out, st);
+    case 3: return run_passes<384, 16, 3, true, 0, 4>(keys, alt, n, np, begin_bit, temp, out, st);
+    case 4: return run_passes<256, 16, 4, true, 1, 4>(keys, alt, n, np, begin_bit, temp, out, st);  // peers re-read the counter
+    case 5: return run_passes<256, 16, 4, true, 0, 1>(keys, alt, n, np, begin_bit, temp, out, st);  // one descriptor per step
+    case 6: return run_passes<256, 16, 4, true, 0, 8>(keys, alt, n, np, begin_bit, temp, out, st);
+    default: return run_passes<256, 16, 4, true, 0, 4>(keys, alt, n, np, begin_bit, temp, out, st);
   }
 }
 
 int sort_keys(unsigned long long* keys, unsigned long long* alt, uint64_t n, int end_bit, void* temp, size_t temp_bytes,
-              unsigned long long** out, cudaStream_t st) {
+              unsigned long long** out, cudaStream_t st, int begin_bit) {
   (void)temp_bytes;
-  int launches = sort_histograms(keys, n, end_bit, temp, st);
-  launches += sort_passes(keys, alt, n, end_bit, temp, out, st);
+  int launches = sort_histograms(keys, n, end_bit, temp, st, begin_bit);
+  launches += sort_passes(keys, alt, n, end_bit, temp, out, st, begin_bit);
   return launches;
 }
