@@ -37,6 +37,9 @@ struct DevWhitelist {
   const uint32_t* vals[CRGPU_MAX_ORD];  // content rank of each entry; nullptr = the entry's own index
   const uint32_t* offs[CRGPU_MAX_ORD];  // (1 << p) + 1 bucket starts
   int rot[CRGPU_MAX_ORD];
+  // sfx[o][i] = low s bits of keys[o][i] as 16 bits (s <= 16), what the neighbour scans read: half the bytes of
+  // the full keys, so that all orderings together stay L2-resident. nullptr when s > 16; keys[o > 0] is then kept.
+  const uint16_t* sfx[CRGPU_MAX_ORD];
   uint32_t resp[CRGPU_MAX_ORD];  // bit `pos` set: this ordering answers for mutations at base `pos`
   // exact membership: one 32-byte slot (one L2 sector) per bucket of the top (2L - slot_shift) key bits,
   // fetched with two 128-bit loads: word 0 = index of the bucket's first entry in keys[0] (low 27 bits) |
@@ -120,9 +123,12 @@ __device__ __forceinline__ unsigned long long wl_neighbor_mask(const DevWhitelis
     uint32_t b = wl.s >= 32 ? 0u : (rq >> wl.s);
     uint32_t lo = __ldg(offs + b), hi = __ldg(offs + b + 1);
     const uint32_t resp = wl.resp[o];
+    const uint16_t* __restrict__ sfx = wl.sfx[o];
+    const uint32_t smask = mask_bits(wl.s);
     for (uint32_t i = lo; i < hi; i++) {
-      uint32_t e = __ldg(keys + i);
-      uint32_t x = e ^ rq;
+      // the bucket fixes the prefix: only the suffix can differ
+      const uint32_t e = sfx ? (uint32_t)__ldg(sfx + i) : (__ldg(keys + i) & smask);
+      uint32_t x = e ^ (rq & smask);
       uint32_t y = (x | (x >> 1)) & 0x55555555u;
       if (y != 0u && (y & (y - 1u)) == 0u) {  // exactly one base differs
         int k = (31 - __clz(y)) >> 1;         // base index from the right in the rotated key

@@ -524,6 +524,17 @@ int crgpu_whitelist_add(crgpu_ctx* c, const uint8_t* seqs, uint64_t n, int L, co
     w->dev.offs[o] = dof.as<uint32_t>();
     w->bufs.push_back(dk);
     w->bufs.push_back(dof);
+    w->dev.sfx[o] = nullptr;
+    if (s <= 16) {  // 16-bit suffix copy for the neighbour scans
+      std::vector<uint16_t> sfx(W + 8, (uint16_t)0xFFFF);
+      const uint32_t sm = s >= 32 ? 0xFFFFFFFFu : ((1u << s) - 1u);
+      for (uint32_t i = 0; i < W; i++) sfx[i] = (uint16_t)(keys[i] & sm);
+      DevBuf ds;
+      if ((rc = ds.ensure((size_t)(W + 8) * 2))) return rc;
+      CU(cudaMemcpy(ds.p, sfx.data(), (size_t)(W + 8) * 2, cudaMemcpyHostToDevice));
+      w->dev.sfx[o] = ds.as<uint16_t>();
+      w->bufs.push_back(ds);
+    }
     if (o == 0 && identity) {
       w->dev.vals[o] = nullptr;
     } else {
