@@ -142,6 +142,9 @@ def tethered_offset(pattern: str) -> int:
     return len(pre)
 
 
+FEATURE_TYPE_NAMES = {1: "Antibody Capture", 2: "CRISPR Guide Capture", 3: "Multiplexing Capture", 4: "Custom"}
+
+
 @dataclass
 class FeatureReference:
     """Genes (indices 0..n_genes-1) followed by feature-barcode features."""
@@ -215,6 +218,7 @@ class GemWell:
         self._whitelists = []
         self._libs = []
         self._batches = []
+        self._dev_owned = []   # device arrays allocated by add_fastq, released with the reads
         self.bc_length = None
         self.umi_length = None
         self.feature_reference: Optional[FeatureReference] = None
@@ -225,6 +229,9 @@ class GemWell:
             for p, _ in self._pinned_bufs.values():
                 self.L.crgpu_host_free_pinned(C.c_void_p(p))
             self._pinned_bufs = {}
+            for p in getattr(self, "_dev_owned", []):
+                self.L.crgpu_dev_free(self._ctx, C.c_void_p(p))
+            self._dev_owned = []
             self.L.crgpu_ctx_destroy(self._ctx)
             self._ctx = None
 
@@ -319,8 +326,53 @@ class GemWell:
         self._batches.append((library, n))
         return out.value
 
+    def add_fastq(self, library: int, r1_fastq, feature=None, read_len: Optional[int] = None) -> dict:
+        """One chunk of uncompressed R1 FASTQ text (bytes or uint8 array, whole 4-line records) as a read batch:
+        crgpu_fastq_extract slices the first `read_len` bases / qualities of every record on the device
+        (RnaProcessor::process_read, cr_types/src/rna_read.rs:363-467), `feature` (uint32 per record, from
+        the aligner) goes along as in add_reads. Returns {batch, n_records, n_short, n_malformed}."""
+        text = np.frombuffer(r1_fastq, dtype=np.uint8) if isinstance(r1_fastq, (bytes, bytearray, memoryview)) \
+            else np.ascontiguousarray(r1_fastq, dtype=np.uint8)
+        d = self._libs[library]
+        rl = int(read_len or max(d.bc_offset + d.bc_length, d.umi_offset + d.umi_length))
+        cap = int(np.count_nonzero(text == 10) // 4 + 1)
+        dev = []
+        for _ in range(2):
+            p = C.c_void_p()
+            check(self.L.crgpu_dev_alloc(self._ctx, C.c_uint64(cap * rl + 16), C.byref(p)), "crgpu_dev_alloc")
+            dev.append(p.value)
+        n_rec, n_short, n_bad = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(self.L.crgpu_fastq_extract(self._ctx, ptr(text), C.c_uint64(text.shape[0]), 0, rl, C.c_void_p(dev[0]),
+                                         C.c_void_p(dev[1]), C.c_uint64(cap), C.byref(n_rec), C.byref(n_short),
+                                         C.byref(n_bad)), "crgpu_fastq_extract")
+        n = int(n_rec.value)
+        fdev = 0
+        if feature is not None:
+            f = np.ascontiguousarray(feature, dtype=np.uint32)
+            if f.shape[0] != n:
+                raise ValueError(f"{n} FASTQ records but {f.shape[0]} feature assignments")
+            p = C.c_void_p()
+            check(self.L.crgpu_dev_alloc(self._ctx, C.c_uint64(max(n, 1) * 4), C.byref(p)), "crgpu_dev_alloc")
+            check(self.L.crgpu_memcpy_h2d(self._ctx, p, ptr(f), C.c_uint64(f.nbytes)), "crgpu_memcpy_h2d")
+            fdev = p.value
+            dev.append(fdev)
+        self._dev_owned.extend(dev)
+        batch = self.add_reads_device(library, n, rl, dev[0], dev[1], fdev)
+        return {"batch": batch, "n_records": n, "n_short": int(n_short.value), "n_malformed": int(n_bad.value),
+                "read_len": rl, "dev_seq": dev[0], "dev_qual": dev[1]}
+
+    def read_device(self, dev: int, shape, dtype=np.uint8) -> np.ndarray:
+        """Copy a device array of this context to the host (inspection, tests)."""
+        out = np.zeros(shape, dtype=dtype)
+        if out.nbytes:
+            check(self.L.crgpu_memcpy_d2h(self._ctx, ptr(out), C.c_void_p(dev), C.c_uint64(out.nbytes)), "crgpu_memcpy_d2h")
+        return out
+
     def clear_reads(self):
         check(self.L.crgpu_reads_clear(self._ctx))
+        for p in self._dev_owned:
+            self.L.crgpu_dev_free(self._ctx, C.c_void_p(p))
+        self._dev_owned = []
         self._keep.clear()
         self._batches.clear()
 
@@ -505,6 +557,51 @@ class GemWell:
         data = mk("data", (nnz.value,), np.int32)
         check(self.L.crgpu_matrix_get(self._ctx, ptr(rank), ptr(indptr), ptr(indices), ptr(data)), "crgpu_matrix_get")
         return CountMatrix(rank, indptr, indices, data, int(nf.value), resolve_barcodes=self.barcode_seqs)
+
+    def barcode_summary(self, library: int = 0) -> np.ndarray:
+        """BarcodeSummary rows of one library (cr_lib/src/aligner.rs:33-68): a structured array in matrix
+        column order with fields barcode_rank, reads, umis, candidate_dup_reads, umi_corrected_reads. Like the
+        reference (visit_read_annotation, cr_lib/src/align_metrics.rs:705-721) only barcodes with at least one
+        read in this library get a row."""
+        nb = C.c_uint64()
+        check(self.L.crgpu_matrix_dims(self._ctx, C.byref(nb), None, None), "crgpu_matrix_dims")
+        raw = np.zeros((nb.value, 4), dtype=np.uint32)
+        check(self.L.crgpu_barcode_summary(self._ctx, library, ptr(raw)), "crgpu_barcode_summary")
+        rank = np.zeros(nb.value, dtype=np.uint32)
+        check(self.L.crgpu_matrix_get(self._ctx, ptr(rank), None, None, None), "crgpu_matrix_get")
+        keep = raw[:, 0] > 0
+        out = np.zeros(int(keep.sum()), dtype=[("barcode_rank", np.uint32), ("reads", np.uint64), ("umis", np.uint64),
+                                               ("candidate_dup_reads", np.uint64), ("umi_corrected_reads", np.uint64)])
+        out["barcode_rank"] = rank[keep]
+        for i, f in enumerate(("reads", "umis", "candidate_dup_reads", "umi_corrected_reads")):
+            out[f] = raw[keep, i]
+        return out
+
+    def barcode_correction_metrics(self, library: int = 0) -> dict:
+        """InnerBarcodeCorrectionMetrics of one library (cr_lib/src/barcode_correction_metrics.rs:16-39,62-86):
+        corrected_bc = corrected reads / all reads, good_bc = (valid before + corrected) / all reads."""
+        total = sum(n for lib, n in self._batches if lib == library)
+        valid_before = int(self.prior(library).sum(dtype=np.uint64))
+        corrected = int(self.corrected_counts(library).sum(dtype=np.uint64))
+        frac = (lambda a: a / total) if total else (lambda a: float("nan"))
+        return {"total_reads": total, "valid_before": valid_before, "corrected": corrected,
+                "corrected_bc": frac(corrected), "good_bc": frac(valid_before + corrected)}
+
+    def write_mex(self, folder: str, software_version: str = "Cell Ranger cellranger_b200", gem_group: int = 1):
+        """raw_feature_bc_matrix/{matrix.mtx.gz, barcodes.tsv.gz, features.tsv.gz}
+        (MtxWriter, cr_lib/src/stages/write_matrix_market.rs:41-120)."""
+        fr = self.feature_reference
+        rows = []
+        if fr is not None:
+            names = getattr(fr, "gene_names", None)
+            for g in range(fr.n_genes):
+                gid = names[g] if names else f"GENE{g:06d}"
+                rows.append(f"{gid}\t{gid}\tGene Expression")
+            for fid, ft in zip(fr.fb_ids, fr.fb_types):
+                rows.append(f"{fid}\t{fid}\t{FEATURE_TYPE_NAMES.get(ft, 'Custom')}")
+        tsv = ("\n".join(rows) + "\n").encode() if rows else None
+        check(self.L.crgpu_matrix_write_mex(self._ctx, folder.encode(), software_version.encode(), int(gem_group), tsv),
+              "crgpu_matrix_write_mex")
 
     def molecules(self) -> np.ndarray:
         """UmiCount rows: (barcode column, library, feature, umi 2-bit, read_count)."""

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libcrgpu.so")
-SOURCES = ["crgpu.cu", "pass_kernels.cu", "sort.cu", "dedup_kernels.cu", "synth.cu"]
+SOURCES = ["crgpu.cu", "pass_kernels.cu", "sort.cu", "dedup_kernels.cu", "synth.cu", "fastq.cu", "mex_writer.cpp"]
 HEADERS = ["common.cuh", "kernels.h", os.path.join(ROOT, "include", "crgpu.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -34,7 +34,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return SO
     cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + \
-          [os.path.join(CSRC, s) for s in SOURCES]
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-lz"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

@@ -143,7 +143,7 @@ struct crgpu_ctx {
 
   // dedup
   DevBuf dkeys, c0, best, inc, low, key2, key2_alt, lb_desc, tickets, scalars, ent_rank, ent_feature, ent_count, mol;
-  DevBuf col_of_rank, barcode_rank, indptr, mol_rows, min_read, rep_raw, ls_slots;
+  DevBuf col_of_rank, barcode_rank, indptr, mol_rows, min_read, rep_raw, ls_slots, summary, fastq_text, fastq_tmp;
   uint64_t n_distinct = 0, n_mol = 0, nnz = 0, n_barcodes = 0;
   uint32_t own_lo = 0, own_hi = 0xFFFFFFFFu;
   bool annotated = false;
@@ -371,7 +371,7 @@ void crgpu_ctx_destroy(crgpu_ctx* c) {
   DevBuf* all[] = {&c->d_fb_counts, &c->d_feat_dist, &c->bc_out, &c->umi_out, &c->umi_proc, &c->flags, &c->keys,
                    &c->keys_alt, &c->sort_temp, &c->counters, &c->dkeys, &c->c0, &c->best, &c->inc, &c->low, &c->key2,
                    &c->key2_alt, &c->lb_desc, &c->tickets, &c->scalars, &c->ent_rank, &c->ent_feature, &c->ent_count,
-                   &c->mol, &c->col_of_rank, &c->barcode_rank, &c->indptr, &c->mol_rows, &c->min_read, &c->rep_raw,
+                   &c->mol, &c->col_of_rank, &c->barcode_rank, &c->indptr, &c->mol_rows, &c->min_read, &c->rep_raw, &c->summary, &c->fastq_text, &c->fastq_tmp,
                    &c->ls_slots};
   for (auto* b : all) b->release();
   for (auto& p : c->phases) {
@@ -671,6 +671,44 @@ int crgpu_reads_add(crgpu_ctx* c, int lib, const crgpu_read_batch* rb, int* out_
   if (out_batch) *out_batch = (int)c->batches.size() - 1;
   return CRGPU_OK;
 }
+
+int crgpu_fastq_extract(crgpu_ctx* c, const void* text, uint64_t n_bytes, int on_device, int read_len,
+                        uint8_t* dev_seq, uint8_t* dev_qual, uint64_t capacity, uint64_t* n_records, uint64_t* n_short,
+                        uint64_t* n_malformed) {
+  if (!c || (!text && n_bytes) || !dev_seq || !dev_qual) return fail(CRGPU_E_INVALID, "NULL argument");
+  if (read_len < 1 || read_len > 4096) return fail(CRGPU_E_INVALID, "read_len out of range");
+  CU(cudaSetDevice(c->device));
+  int rc;
+  const uint8_t* d_text = static_cast<const uint8_t*>(text);
+  if (!on_device) {
+    if ((rc = c->fastq_text.ensure(n_bytes + 16))) return rc;
+    CU(cudaMemcpyAsync(c->fastq_text.p, text, n_bytes, cudaMemcpyHostToDevice, c->stream));
+    d_text = c->fastq_text.as<uint8_t>();
+  } else if ((uintptr_t)text % 16 != 0) {
+    return fail(CRGPU_E_INVALID, "device FASTQ text must be 16-byte aligned");
+  }
+  const size_t tb = fastq_temp_bytes(n_bytes);
+  if ((rc = c->fastq_tmp.ensure(tb + 64))) return rc;
+  unsigned long long* counters = reinterpret_cast<unsigned long long*>(c->fastq_tmp.as<unsigned char>() + ((tb + 7) & ~(size_t)7));
+  c->launches += launch_fastq_extract(d_text, n_bytes, read_len, dev_seq, dev_qual, capacity, c->fastq_tmp.p, counters,
+                                      c->stream);
+  CHECK_KERNEL();
+  unsigned long long h[3] = {0, 0, 0};
+  uint8_t last = '\n';
+  CU(cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  if (n_bytes) CU(cudaMemcpyAsync(&last, d_text + n_bytes - 1, 1, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  const uint64_t lines = h[0] + (n_bytes && last != '\n' ? 1 : 0);
+  if (lines % 4 != 0) return fail(CRGPU_E_INVALID, "FASTQ text does not hold a whole number of 4-line records");
+  if (lines / 4 > capacity) return fail(CRGPU_E_LIMIT, "more FASTQ records than the output arrays hold");
+  if (n_records) *n_records = lines / 4;
+  if (n_short) *n_short = h[1];
+  if (n_malformed) *n_malformed = h[2];
+  return CRGPU_OK;
+}
+
+// error reporting for the host-only translation units of the library (mex_writer.cpp)
+extern "C" int crgpu_set_error_(int code, const char* msg) { return fail(code, msg ? msg : ""); }
 
 int crgpu_reads_clear(crgpu_ctx* c) {
   if (!c) return fail(CRGPU_E_INVALID, "ctx is NULL");
@@ -1474,6 +1512,31 @@ int crgpu_matrix_get(crgpu_ctx* c, uint32_t* barcode_rank, int64_t* indptr, uint
   if (indptr) CU(cudaMemcpyAsync(indptr, c->indptr.p, (c->n_barcodes + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
   if (indices && c->nnz) CU(cudaMemcpyAsync(indices, c->ent_feature.p, c->nnz * 4, cudaMemcpyDeviceToHost, c->stream));
   if (data && c->nnz) CU(cudaMemcpyAsync(data, c->ent_count.p, c->nnz * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return CRGPU_OK;
+}
+
+int crgpu_barcode_summary(crgpu_ctx* c, int lib, uint32_t* out) {
+  if (!c || !out) return fail(CRGPU_E_INVALID, "bad argument");
+  if (c->stage < 3) return fail(CRGPU_E_INVALID, "crgpu_count must run first");
+  if (lib < 0 || lib >= (int)c->libs.size()) return fail(CRGPU_E_INVALID, "no such library");
+  if (c->n_barcodes == 0) return CRGPU_OK;
+  CU(cudaSetDevice(c->device));
+  int rc;
+  if ((rc = c->summary.ensure(c->n_barcodes * 16))) return rc;
+  DedupBuffers b;
+  memset(&b, 0, sizeof(b));
+  b.kl = c->kl;
+  b.dkeys = c->dkeys.as<unsigned long long>();
+  b.c0 = c->c0.as<uint32_t>();
+  b.best = c->best.as<uint32_t>();
+  b.inc = c->inc.as<unsigned long long>();
+  b.low = c->low.as<uint8_t>();
+  c->launches += run_barcode_summary(b, c->n_distinct, (uint32_t)lib, c->barcode_rank.as<uint32_t>(),
+                                     c->libs[lib]->valid.as<uint32_t>(), c->col_of_rank.as<uint32_t>(), c->n_barcodes,
+                                     c->summary.as<uint32_t>(), c->stream);
+  CHECK_KERNEL();
+  CU(cudaMemcpyAsync(out, c->summary.p, c->n_barcodes * 16, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return CRGPU_OK;
 }

@@ -1267,6 +1267,71 @@ int run_matrix(DedupBuffers& b, MatrixArgs& ma, uint64_t /*nnz_unused*/, uint64_
   return launches;
 }
 
+// ---------------------------------------------------------------------------
+// BarcodeSummary (cr_lib/src/aligner.rs:33-68, filled by visit_read_annotation, cr_lib/src/align_metrics.rs:705-721):
+// per valid barcode and library {reads, umis, candidate_dup_reads, umi_corrected_reads}. Every read of a raw key
+// shares its DupInfo flags, so the sums run over the distinct-key table:
+//   candidate_dup_reads += c0[j] unless the corrected key best[j] is low support
+//   umi_corrected_reads += c0[j] if best[j] != j
+//   umis               += 1 for every correction target that is not low support (its representative read)
+// `reads` is the valid-barcode read count of the library (prior + corrected).
+// ---------------------------------------------------------------------------
+__global__ void summary_reads_kernel(const uint32_t* __restrict__ barcode_rank, const uint32_t* __restrict__ valid,
+                                     uint64_t n_bc, uint32_t* __restrict__ out) {
+  for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < n_bc; c += (uint64_t)gridDim.x * blockDim.x)
+    reinterpret_cast<uint4*>(out)[c] = make_uint4(valid[barcode_rank[c]], 0u, 0u, 0u);
+}
+
+__global__ void __launch_bounds__(256) summary_keys_kernel(const unsigned long long* __restrict__ dkeys,
+                                                           const uint32_t* __restrict__ c0,
+                                                           const uint32_t* __restrict__ best,
+                                                           const unsigned long long* __restrict__ inc,
+                                                           const uint8_t* __restrict__ low, uint64_t m, KeyLayout kl,
+                                                           uint32_t lib, const uint32_t* __restrict__ col_of_rank,
+                                                           uint32_t* __restrict__ out) {
+  const uint32_t lmask = (1u << (kl.feature_shift - kl.lib_shift)) - 1u;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  // warp-uniform trip count: the warp-level reductions below need every lane
+  const uint64_t rounds = (m + stride - 1) / stride;
+  for (uint64_t r = 0; r < rounds; r++) {
+    const uint64_t j = r * stride + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint32_t rank = 0xFFFFFFFFu, umis = 0, cand = 0, corr = 0;
+    if (j < m) {
+      const unsigned long long k = dkeys[j];
+      if (((uint32_t)(k >> kl.lib_shift) & lmask) == lib) {
+        rank = (uint32_t)(k >> kl.rank_shift);
+        const uint32_t t = best[j];
+        const uint32_t n = c0[j];
+        if (!low[t]) cand = n;
+        if (t != (uint32_t)j) corr = n;
+        const bool is_target = t == (uint32_t)j || (inc[j] >> 40) != 0ull;
+        umis = is_target && !low[j];
+      }
+    }
+    // the table is sorted by rank: a warp sees a handful of barcodes; one atomic per barcode and counter
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, rank);
+    const uint32_t s_umis = __reduce_add_sync(peers, umis);
+    const uint32_t s_cand = __reduce_add_sync(peers, cand);
+    const uint32_t s_corr = __reduce_add_sync(peers, corr);
+    if (rank != 0xFFFFFFFFu && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0u) {
+      uint32_t* o = out + 4 * (size_t)col_of_rank[rank];
+      if (s_umis) atomicAdd(o + 1, s_umis);
+      if (s_cand) atomicAdd(o + 2, s_cand);
+      if (s_corr) atomicAdd(o + 3, s_corr);
+    }
+  }
+}
+
+int run_barcode_summary(DedupBuffers& b, uint64_t m, uint32_t lib, const uint32_t* barcode_rank, const uint32_t* valid,
+                        const uint32_t* col_of_rank, uint64_t n_bc, uint32_t* out4, cudaStream_t st) {
+  if (n_bc == 0) return 0;
+  summary_reads_kernel<<<grid_for(n_bc), 256, 0, st>>>(barcode_rank, valid, n_bc, out4);
+  if (m == 0) return 1;
+  summary_keys_kernel<<<grid_for(m, 256, 148 * 8), 256, 0, st>>>(b.dkeys, b.c0, b.best, b.inc, b.low, m, b.kl, lib,
+                                                                col_of_rank, out4);
+  return 2;
+}
+
 int run_molecule_rows(DedupBuffers& b, const uint32_t* col_of_rank, uint64_t n_mol, uint32_t* out5, cudaStream_t st) {
   if (!n_mol) return 0;
   molecules_kernel<<<grid_for(n_mol), 256, 0, st>>>(b.key2, b.mol, n_mol, b.kl, col_of_rank, out5);

@@ -1,0 +1,111 @@
+// fastq.cu — FASTQ text -> fixed-stride read arrays, on the device.
+//
+// The front end of MAKE_SHARD reads FASTQ records and slices barcode / UMI ranges out of R1
+// (RnaProcessor::process_read, cr_types/src/rna_read.rs:363-467; the ranges are chemistry constants,
+// extract_barcode :285-368). The kernels of pass 1 want the sequence and quality lines as fixed-stride arrays.
+// One kernel does the conversion in a single pass over the text: a tile counts its newlines, a chained scan
+// (decoupled look-back) turns that into the line number at the start of the tile, and every thread that finds
+// a line start of kind "sequence" (line % 4 == 1) or "quality" (line % 4 == 3) copies the first `read_len`
+// bytes of that line to the record's slot. No array of line offsets is ever materialised.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+constexpr int FQ_THREADS = 256;
+constexpr int FQ_BYTES = 16;  // bytes per thread
+constexpr int FQ_TILE = FQ_THREADS * FQ_BYTES;
+
+// bit j set iff byte j of the 16-byte chunk is '\n'
+__device__ __forceinline__ uint32_t newline_mask(const uint4 v) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const uint32_t x = w[i] ^ 0x0A0A0A0Au;
+    // exact zero-byte detector: bit 7 of a byte is set iff the byte is zero
+    const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+    m |= (((z >> 7) & 1u) | ((z >> 14) & 2u) | ((z >> 21) & 4u) | ((z >> 28) & 8u)) << (4 * i);
+  }
+  return m;
+}
+
+__global__ void __launch_bounds__(FQ_THREADS) fastq_extract_kernel(
+    const uint8_t* __restrict__ text, uint64_t n_bytes, int read_len, uint8_t* __restrict__ out_seq,
+    uint8_t* __restrict__ out_qual, uint64_t capacity, unsigned long long* desc, uint32_t* ticket,
+    unsigned long long* counters /* [0] lines, [1] short reads, [2] malformed records */) {
+  __shared__ uint32_t scan_s[FQ_THREADS / 32 + 1];
+  __shared__ unsigned long long bcast;
+  __shared__ uint32_t tile_s;
+  if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = tile_s;
+  const uint64_t p0 = (uint64_t)tile * FQ_TILE + (uint64_t)threadIdx.x * FQ_BYTES;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (p0 + FQ_BYTES <= n_bytes) {
+    v = __ldg(reinterpret_cast<const uint4*>(text + p0));
+  } else if (p0 < n_bytes) {
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    for (int j = 0; j < FQ_BYTES && p0 + j < n_bytes; j++) w[j >> 2] |= (uint32_t)text[p0 + j] << (8 * (j & 3));
+    v = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  uint32_t m = newline_mask(v);
+  if (p0 + FQ_BYTES > n_bytes) m &= p0 < n_bytes ? ((1u << (n_bytes - p0)) - 1u) : 0u;
+  uint32_t total;
+  const uint32_t off = block_exclusive_scan<FQ_THREADS>((uint32_t)__popc(m), &total, scan_s);
+  const uint64_t n_tiles = (n_bytes + FQ_TILE - 1) / FQ_TILE;
+  const unsigned long long before = lookback_exclusive(desc, tile, (unsigned long long)total, &bcast);
+  if (tile == n_tiles - 1 && threadIdx.x == 0) counters[0] = before + total;
+  // line index of the line that starts right after newline j of this thread = newlines before it + 1
+  uint64_t line = before + off;
+  while (m) {
+    const int j = __ffs(m) - 1;
+    m &= m - 1u;
+    line++;
+    const uint64_t start = p0 + j + 1;
+    if (start >= n_bytes) break;  // the newline that ends the text
+    const uint32_t kind = (uint32_t)(line & 3u);
+    const uint64_t rec = line >> 2;
+    if (kind == 0u) {
+      if (text[start] != '@') atomicAdd(counters + 2, 1ull);
+    } else if (kind == 2u) {
+      if (text[start] != '+') atomicAdd(counters + 2, 1ull);
+    } else if (rec < capacity) {
+      uint8_t* dst = (kind == 1u ? out_seq : out_qual) + rec * (uint64_t)read_len;
+      const uint8_t pad = kind == 1u ? (uint8_t)'N' : (uint8_t)'#';
+      bool ended = false;
+      for (int k = 0; k < read_len; k++) {
+        uint8_t ch = pad;
+        if (!ended) {
+          if (start + k < n_bytes) ch = text[start + k];
+          if (start + k >= n_bytes || ch == '\n' || ch == '\r') {
+            ended = true;
+            ch = pad;
+            if (kind == 1u) atomicAdd(counters + 1, 1ull);
+          }
+        }
+        dst[k] = ch;
+      }
+    }
+  }
+  // line 0 starts at byte 0 without a newline in front of it
+  if (tile == 0 && threadIdx.x == 0 && n_bytes && text[0] != '@') atomicAdd(counters + 2, 1ull);
+}
+
+}  // namespace
+
+size_t fastq_temp_bytes(uint64_t n_bytes) { return ((n_bytes + FQ_TILE - 1) / FQ_TILE + 1) * 8 + 64; }
+
+// temp: fastq_temp_bytes(n_bytes); counters: 3 x u64 (zeroed here)
+int launch_fastq_extract(const uint8_t* text, uint64_t n_bytes, int read_len, uint8_t* out_seq, uint8_t* out_qual,
+                         uint64_t capacity, void* temp, unsigned long long* counters, cudaStream_t st) {
+  cudaMemsetAsync(counters, 0, 3 * 8, st);
+  if (n_bytes == 0) return 0;
+  const uint64_t tiles = (n_bytes + FQ_TILE - 1) / FQ_TILE;
+  unsigned long long* desc = static_cast<unsigned long long*>(temp);
+  uint32_t* ticket = reinterpret_cast<uint32_t*>(desc + tiles + 1);
+  cudaMemsetAsync(temp, 0, (tiles + 1) * 8 + 8, st);
+  fastq_extract_kernel<<<(unsigned)tiles, FQ_THREADS, 0, st>>>(text, n_bytes, read_len, out_seq, out_qual, capacity, desc,
+                                                              ticket, counters);
+  return 1;
+}

@@ -81,6 +81,11 @@ int launch_fb(const FbArgs& a, cudaStream_t st);
 int launch_emit_keys(const EmitArgs& a, cudaStream_t st);
 int launch_valid_counts(const uint32_t* prior, const uint32_t* corrected, uint32_t* out, uint64_t n, cudaStream_t st);
 
+// ---- FASTQ text -> fixed-stride read arrays (fastq.cu) ----
+size_t fastq_temp_bytes(uint64_t n_bytes);
+int launch_fastq_extract(const uint8_t* text, uint64_t n_bytes, int read_len, uint8_t* out_seq, uint8_t* out_qual,
+                         uint64_t capacity, void* temp, unsigned long long* counters, cudaStream_t st);
+
 // ---- sort (sort.cu) ----
 // sorts n 64-bit keys on bits [begin_bit, end_bit) (stable: lower bits keep their input order); result in
 // *out (one of the two buffers)
@@ -158,6 +163,8 @@ struct AnnotateArgs {
   uint64_t read_base;  // global index of read 0 of this batch
 };
 int run_molecule_rows(DedupBuffers& b, const uint32_t* col_of_rank, uint64_t n_mol, uint32_t* out5, cudaStream_t st);
+int run_barcode_summary(DedupBuffers& b, uint64_t n_distinct, uint32_t lib, const uint32_t* barcode_rank,
+                        const uint32_t* valid, const uint32_t* col_of_rank, uint64_t n_bc, uint32_t* out4, cudaStream_t st);
 int run_annotate_prepare(DedupBuffers& b, uint64_t n_distinct, uint32_t* min_read, uint32_t* rep_raw, cudaStream_t st);
 int run_annotate_min(DedupBuffers& b, uint64_t n_distinct, const AnnotateArgs& a, uint32_t* min_read, cudaStream_t st);
 int run_annotate_final(DedupBuffers& b, uint64_t n_distinct, const AnnotateArgs& a, const uint32_t* min_read,

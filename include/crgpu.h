@@ -111,6 +111,20 @@ typedef struct crgpu_read_batch {
   int32_t on_device;
 } crgpu_read_batch;
 int crgpu_reads_add(crgpu_ctx* ctx, int library, const crgpu_read_batch* batch, int* out_batch);
+/* FASTQ front end: the read loop of MAKE_SHARD slices barcode / UMI ranges out of FASTQ records
+ * (RnaProcessor::process_read, cr_types/src/rna_read.rs:363-467; ranges from the chemistry, extract_barcode
+ * :285-368). crgpu_fastq_extract turns uncompressed 4-line FASTQ text into the fixed-stride arrays of
+ * crgpu_read_batch, on the device, in one pass: record r gets bytes [0, read_len) of its sequence and quality
+ * lines at dev_seq / dev_qual + r * read_len (device memory, capacity records each). A sequence line shorter
+ * than read_len is padded with 'N' (quality '#') and counted in n_short - the reference fails such a read with
+ * "Barcode range out of bounds" (ReadPair::check_range), here its barcode simply cannot be valid. n_malformed
+ * counts records whose header / separator line does not start with '@' / '+'. text: host memory, or device
+ * memory (16-byte aligned) when on_device != 0; a chunk must hold whole records. Feed the arrays to
+ * crgpu_reads_add with on_device = 1. */
+int crgpu_fastq_extract(crgpu_ctx* ctx, const void* text, uint64_t n_bytes, int on_device, int read_len,
+                        uint8_t* dev_seq, uint8_t* dev_qual, uint64_t capacity, uint64_t* n_records, uint64_t* n_short,
+                        uint64_t* n_malformed);
+
 int crgpu_reads_clear(crgpu_ctx* ctx);
 
 /* ---- Stage MAKE_SHARD hot loop: exact whitelist check + priors ----
@@ -223,6 +237,22 @@ int crgpu_fb_counts_get(crgpu_ctx* ctx, int64_t* out, int32_t n);
  * indptr[n_barcodes+1], indices[nnz] (feature index), data[nnz] */
 int crgpu_matrix_dims(crgpu_ctx* ctx, uint64_t* n_barcodes, uint64_t* nnz, uint64_t* n_features);
 int crgpu_matrix_get(crgpu_ctx* ctx, uint32_t* barcode_rank, int64_t* indptr, uint32_t* indices, int32_t* data);
+
+/* raw_feature_bc_matrix in Matrix Market form: MtxWriter::{write_matrix_mtx, write_barcodes_tsv,
+ * write_features_tsv} (cr_lib/src/stages/write_matrix_market.rs:41-120). Writes folder/matrix.mtx.gz
+ * ("%%MatrixMarket matrix coordinate integer general", the %metadata_json line with software_version =
+ * "<product> <version>" as the caller passes it, "features barcodes nnz", then "feature+1 barcode+1 count" per
+ * entry in (barcode, feature) order), folder/barcodes.tsv.gz ("SEQ-<gem_group>" per column) and, when
+ * features_tsv is not NULL, folder/features.tsv.gz with that text (id, name, feature type per row). */
+int crgpu_matrix_write_mex(crgpu_ctx* ctx, const char* folder, const char* software_version, int gem_group,
+                           const char* features_tsv);
+
+/* BarcodeSummary rows (cr_lib/src/aligner.rs:33-68, accumulated per valid barcode and library type by
+ * visit_read_annotation, cr_lib/src/align_metrics.rs:705-721; written as barcode_summary.csv by ALIGN_AND_COUNT,
+ * stages/align_and_count.rs:806-817). out: uint32[n_barcodes][4] in matrix column order =
+ * {reads, umis, candidate_dup_reads, umi_corrected_reads} of `library`; the reference emits a row only where
+ * reads > 0. Needs crgpu_count() first. */
+int crgpu_barcode_summary(crgpu_ctx* ctx, int library, uint32_t* out);
 
 /* UmiCount rows (cr_types/src/types.rs:148-160), sorted by (barcode, library, feature, umi):
  * out5[5*i..] = {barcode column index, library, feature, umi 2-bit, read_count} */

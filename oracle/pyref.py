@@ -284,3 +284,27 @@ def run_pipeline(whitelists, libraries, feature_type, fb_seqs, batches, threshol
                 content=content, indptr=indptr, indices=[f for _, f, _ in dd["entries"]],
                 data=[c for _, _, c in dd["entries"]],
                 molecules=[(col[r], l, f, u, c) for r, l, f, u, c in dd["molecules"]])
+
+
+def barcode_summary(bc_ascii, state, flags):
+    """BarcodeSummary::observe (cr_lib/src/aligner.rs:33-68) over the reads of ONE library type, as driven by
+    visit_read_annotation (cr_lib/src/align_metrics.rs:705-721): one row per valid barcode, in barcode order.
+
+    bc_ascii: (n, L) uint8 processed barcode of every read; state: BarcodeSegmentState per read (1 = valid
+    before, 2 = valid after correction); flags: per-read DupInfo bits as cro_get_reads returns them
+    (bit1 dup_info is Some, bit2 is_corrected, bit3 is_low_support_umi, bit4 is_umi_count).
+    Returns (barcodes (k, L) uint8 sorted, reads, umis, candidate_dup_reads, umi_corrected_reads)."""
+    valid = (state == 1) | (state == 2)
+    if not valid.any():
+        z = np.zeros(0, dtype=np.int64)
+        return bc_ascii[:0], z, z, z, z
+    uniq, inv = np.unique(bc_ascii[valid], axis=0, return_inverse=True)
+    inv = inv.reshape(-1)
+    f = flags[valid]
+    has = (f & 2) != 0
+    k = len(uniq)
+    reads = np.bincount(inv, minlength=k)                                   # self.reads += 1
+    cand = np.bincount(inv[has & ((f & 8) == 0)], minlength=k)              # !dup_info.is_low_support_umi
+    corr = np.bincount(inv[has & ((f & 4) != 0)], minlength=k)              # dup_info.is_corrected
+    umis = np.bincount(inv[has & ((f & 16) != 0)], minlength=k)             # dup_info.is_umi_count()
+    return uniq, reads, umis, cand, corr

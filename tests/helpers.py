@@ -117,6 +117,15 @@ def compare_all(o, gw, prob, check_reads: bool = True):
             has_dup = (fo & 2) != 0
             umi_g = cb.unpack_2bit(rg["umi"], Lu)
             assert np.array_equal(ro["umi"][base:base + n][has_dup], umi_g[has_dup]), f"processed UMI, batch {batch}"
+            # BarcodeSummary rows of this library (aligner.rs:33-68), from the oracle's per-read DupInfo
+            from oracle import pyref
+            eb, er, eu, ec, ek = pyref.barcode_summary(ro["bc"][base:base + n], so, fo)
+            sm = gw.barcode_summary(batch)
+            assert np.array_equal(eb, gw.barcode_seqs(sm["barcode_rank"])), f"summary barcodes, library {batch}"
+            assert np.array_equal(er, sm["reads"].astype(np.int64)), f"summary reads, library {batch}"
+            assert np.array_equal(eu, sm["umis"].astype(np.int64)), f"summary umis, library {batch}"
+            assert np.array_equal(ec, sm["candidate_dup_reads"].astype(np.int64)), f"candidate_dup_reads, library {batch}"
+            assert np.array_equal(ek, sm["umi_corrected_reads"].astype(np.int64)), f"umi_corrected_reads, library {batch}"
             base += n
     # matrix
     mo = o.matrix()

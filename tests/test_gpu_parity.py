@@ -361,3 +361,106 @@ def test_long_umi_segments_span_several_windows():
     so, sg = o.stats(), gw.stats()
     assert so["umi_corrected_reads"] == sg["umi_corrected_reads"] and so["low_support_reads"] == sg["low_support_reads"]
     gw.close()
+
+
+def test_barcode_correction_metrics_match_oracle_counts():
+    """corrected_bc / good_bc of InnerBarcodeCorrectionMetrics (barcode_correction_metrics.rs:16-39,62-86)."""
+    prob = helpers.make_problem("cfg1", 60_000)
+    o = helpers.run_oracle(prob)
+    gw = helpers.run_gpu(prob, annotate=False)
+    so = o.stats()
+    m = gw.barcode_correction_metrics(0)
+    n = 60_000
+    assert m["total_reads"] == n and m["valid_before"] == so["valid_before"] and m["corrected"] == so["corrected"]
+    assert m["corrected_bc"] == so["corrected"] / n
+    assert m["good_bc"] == (so["valid_before"] + so["corrected"]) / n
+    gw.close()
+
+
+def _fastq_text(seq, qual, rng, trailing_newline=True):
+    """4-line FASTQ records with headers of varying length (what bcl2fastq writes, roughly)."""
+    parts = []
+    for i in range(seq.shape[0]):
+        head = f"@A00123:45:HXXXXXXXX:{1 + i % 4}:{1101 + int(rng.integers(0, 500))}:{i}:{int(rng.integers(1000, 99999))} 1:N:0:SI-GA-A1"
+        parts.append(head.encode() + b"\n" + bytes(seq[i]) + b"\n+\n" + bytes(qual[i]) + b"\n")
+    text = b"".join(parts)
+    return text if trailing_newline else text[:-1]
+
+
+@pytest.mark.parametrize("trailing_newline", [True, False])
+def test_fastq_ingestion_matches_array_ingestion(trailing_newline):
+    """FASTQ text -> device read arrays (crgpu_fastq_extract) gives the same arrays, and the same
+    matrix, as handing the arrays over directly."""
+    import cellranger_b200 as cb
+
+    prob = helpers.make_problem("cfg1", 50_000)
+    g = prob["gex"]
+    rng = np.random.default_rng(5)
+    text = _fastq_text(g["r1_seq"], g["r1_qual"], rng, trailing_newline)
+    ref = helpers.run_gpu(prob, annotate=False)
+    m_ref = ref.count_matrix()
+
+    cfg, t = prob["cfg"], prob["tables"]
+    gw = cb.GemWell()
+    wl = gw.add_whitelist(cb.Whitelist.plain(t.whitelist))
+    lib = gw.add_library(wl, cb.ChemistryDef(cfg.name, 0, cfg.bc_len, cfg.bc_len, cfg.umi_len))
+    gw.set_feature_reference(cb.FeatureReference(cfg.n_genes))
+    info = gw.add_fastq(lib, text, g["feature"])
+    assert info["n_records"] == 50_000 and info["n_short"] == 0 and info["n_malformed"] == 0
+    rl = info["read_len"]
+    assert rl == cfg.bc_len + cfg.umi_len
+    assert np.array_equal(gw.read_device(info["dev_seq"], (50_000, rl)), g["r1_seq"][:, :rl])
+    assert np.array_equal(gw.read_device(info["dev_qual"], (50_000, rl)), g["r1_qual"][:, :rl])
+    gw.run()
+    m = gw.count_matrix()
+    assert np.array_equal(m.barcode_rank, m_ref.barcode_rank) and np.array_equal(m.indptr, m_ref.indptr)
+    assert np.array_equal(m.indices, m_ref.indices) and np.array_equal(m.data, m_ref.data)
+    assert gw.stats()["molecules"] == ref.stats()["molecules"]
+    gw.close()
+    ref.close()
+
+
+def test_fastq_short_and_malformed_records():
+    import cellranger_b200 as cb
+
+    recs = [b"@r0\nACGTACGTACGTACGTAAAACCCCGG\n+\nIIIIIIIIIIIIIIIIIIIIIIIIII\n",
+            b"@r1\nACGTACGT\n+\nIIIIIIII\n",                       # shorter than the 26 cycles asked for
+            b"r2\nTTTTACGTACGTACGTAAAACCCCGG\n-\nIIIIIIIIIIIIIIIIIIIIIIIIII\n",   # bad header and separator
+            b"@r3\nGGGGACGTACGTACGTAAAACCCCGGTTTTTTTT\r\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII\r\n"]  # longer, CRLF
+    gw = cb.GemWell()
+    wl = gw.add_whitelist(cb.Whitelist.plain(np.frombuffer(b"ACGTACGTACGTACGT", dtype=np.uint8).reshape(1, 16)))
+    lib = gw.add_library(wl, cb.ChemistryDef("SC3Pv2", 0, 16, 16, 10))
+    gw.set_feature_reference(cb.FeatureReference(10))
+    info = gw.add_fastq(lib, b"".join(recs), np.zeros(4, dtype=np.uint32))
+    assert (info["n_records"], info["n_short"], info["n_malformed"]) == (4, 1, 2)
+    seq = gw.read_device(info["dev_seq"], (4, 26))
+    qual = gw.read_device(info["dev_qual"], (4, 26))
+    assert bytes(seq[0]) == b"ACGTACGTACGTACGTAAAACCCCGG" and bytes(qual[0]) == b"I" * 26
+    assert bytes(seq[1]) == b"ACGTACGT" + b"N" * 18 and bytes(qual[1]) == b"I" * 8 + b"#" * 18
+    assert bytes(seq[2]) == b"TTTTACGTACGTACGTAAAACCCCGG"
+    assert bytes(seq[3]) == b"GGGGACGTACGTACGTAAAACCCCGG"
+    with pytest.raises(cb.CrgpuError):
+        gw.add_fastq(lib, b"@r0\nACGT\n+\n", np.zeros(0, dtype=np.uint32))   # three lines: not whole records
+    gw.close()
+
+
+def test_write_mex_matches_matrix(tmp_path):
+    """MtxWriter (write_matrix_market.rs:41-120): header lines, 1-based triplets in (barcode, feature) order,
+    SEQ-gem_group barcodes."""
+    import gzip
+
+    prob = helpers.make_problem("cfg1", 40_000)
+    gw = helpers.run_gpu(prob, annotate=False)
+    m = gw.count_matrix()
+    out = tmp_path / "raw_feature_bc_matrix"
+    gw.write_mex(str(out), software_version="Cell Ranger test-1.0", gem_group=1)
+    lines = gzip.open(out / "matrix.mtx.gz", "rt").read().split("\n")
+    assert lines[0] == "%%MatrixMarket matrix coordinate integer general"
+    assert lines[1] == '%metadata_json: {"software_version": "Cell Ranger test-1.0", "format_version": 2}'
+    assert lines[2] == f"{m.n_features} {len(m.barcode_rank)} {len(m.data)}"
+    assert lines[3:-1] == m.mtx_lines() and lines[-1] == ""
+    bcs = gzip.open(out / "barcodes.tsv.gz", "rt").read().split("\n")
+    assert bcs[:-1] == m.barcode_strings(1) and bcs[-1] == ""
+    feats = gzip.open(out / "features.tsv.gz", "rt").read().split("\n")
+    assert len(feats) - 1 == m.n_features and feats[0].split("\t")[2] == "Gene Expression"
+    gw.close()

@@ -102,3 +102,19 @@ def test_umi_collision_stress_exercises_low_support():
     assert m["data"].tolist() == p["data"] and m["indices"].tolist() == p["indices"]
     st = o.stats()
     assert st["low_support_reads"] > 100 and st["umi_corrected_reads"] > 100
+
+
+def test_barcode_summary_hand_case():
+    """BarcodeSummary::observe (aligner.rs:53-67) on six reads written out by hand."""
+    from oracle import pyref
+
+    bc = np.array([list(b"AAAA"), list(b"AAAA"), list(b"CCCC"), list(b"AAAA"), list(b"GGGG"), list(b"CCCC")], dtype=np.uint8)
+    state = np.array([1, 2, 1, 1, 3, 1], dtype=np.uint8)      # the GGGG read stays invalid: no row
+    #        has_dup | corrected | low support | umi_count
+    flags = np.array([2 | 16, 2 | 4, 0, 2 | 8, 2 | 16, 2 | 4 | 8], dtype=np.uint8)
+    b, reads, umis, cand, corr = pyref.barcode_summary(bc, state, flags)
+    assert [bytes(x) for x in b] == [b"AAAA", b"CCCC"]
+    assert reads.tolist() == [3, 2]
+    assert umis.tolist() == [1, 0]
+    assert cand.tolist() == [2, 0]      # AAAA: reads 0 and 1 (read 3 is low support); CCCC: read 5 is low support
+    assert corr.tolist() == [1, 1]
