@@ -244,6 +244,10 @@ def run_ours(args):
     launches = (stats["kernel_launches"] - launches0) // max(args.steps, 1)
     value = n_total / (ms * 1e-3)
 
+    if world > 1 and sharded.timing and rank == 0:
+        n_runs = args.warmup + args.steps
+        print("dist phases (ms/step, host clock, rank 0): " +
+              " ".join(f"{k}={v / n_runs:.2f}" for k, v in sharded.times.items()), file=sys.stderr)
     # per-phase device times of one more step (phase_times() synchronises, so outside the timed loop)
     step_device()
     phases = gw.phase_times()

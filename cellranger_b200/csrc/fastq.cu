@@ -4,9 +4,9 @@
 // (RnaProcessor::process_read, cr_types/src/rna_read.rs:363-467; the ranges are chemistry constants,
 // extract_barcode :285-368). The kernels of pass 1 want the sequence and quality lines as fixed-stride arrays.
 // One kernel does the conversion in a single pass over the text: a tile counts its newlines, a chained scan
-// (decoupled look-back) turns that into the line number at the start of the tile, and every thread that finds
-// a line start of kind "sequence" (line % 4 == 1) or "quality" (line % 4 == 3) copies the first `read_len`
-// bytes of that line to the record's slot. No array of line offsets is ever materialised.
+// (decoupled look-back) turns that into the line number at the start of the tile, and every line start of kind
+// "sequence" (line % 4 == 1) or "quality" (line % 4 == 3) found in the tile is copied - its first `read_len`
+// bytes, one warp per line - to the record's slot. No global array of line offsets is ever materialised.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -37,10 +37,12 @@ __global__ void __launch_bounds__(FQ_THREADS) fastq_extract_kernel(
   __shared__ uint32_t scan_s[FQ_THREADS / 32 + 1];
   __shared__ unsigned long long bcast;
   __shared__ uint32_t tile_s;
+  __shared__ uint16_t nl_s[FQ_TILE];  // offsets of the tile's newlines, in order
   if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
   __syncthreads();
   const uint32_t tile = tile_s;
-  const uint64_t p0 = (uint64_t)tile * FQ_TILE + (uint64_t)threadIdx.x * FQ_BYTES;
+  const uint64_t tile_base = (uint64_t)tile * FQ_TILE;
+  const uint64_t p0 = tile_base + (uint64_t)threadIdx.x * FQ_BYTES;
   uint4 v = make_uint4(0u, 0u, 0u, 0u);
   if (p0 + FQ_BYTES <= n_bytes) {
     v = __ldg(reinterpret_cast<const uint4*>(text + p0));
@@ -51,42 +53,44 @@ __global__ void __launch_bounds__(FQ_THREADS) fastq_extract_kernel(
   }
   uint32_t m = newline_mask(v);
   if (p0 + FQ_BYTES > n_bytes) m &= p0 < n_bytes ? ((1u << (n_bytes - p0)) - 1u) : 0u;
-  uint32_t total;
-  const uint32_t off = block_exclusive_scan<FQ_THREADS>((uint32_t)__popc(m), &total, scan_s);
-  const uint64_t n_tiles = (n_bytes + FQ_TILE - 1) / FQ_TILE;
-  const unsigned long long before = lookback_exclusive(desc, tile, (unsigned long long)total, &bcast);
-  if (tile == n_tiles - 1 && threadIdx.x == 0) counters[0] = before + total;
-  // line index of the line that starts right after newline j of this thread = newlines before it + 1
-  uint64_t line = before + off;
+  uint32_t n_nl;
+  uint32_t off = block_exclusive_scan<FQ_THREADS>((uint32_t)__popc(m), &n_nl, scan_s);
   while (m) {
     const int j = __ffs(m) - 1;
     m &= m - 1u;
-    line++;
-    const uint64_t start = p0 + j + 1;
-    if (start >= n_bytes) break;  // the newline that ends the text
+    nl_s[off++] = (uint16_t)(threadIdx.x * FQ_BYTES + j);
+  }
+  const uint64_t n_tiles = (n_bytes + FQ_TILE - 1) / FQ_TILE;
+  const unsigned long long before = lookback_exclusive(desc, tile, (unsigned long long)n_nl, &bcast);  // syncs
+  if (tile == n_tiles - 1 && threadIdx.x == 0) counters[0] = before + n_nl;
+  // The line that starts after newline i of the tile has index before + i + 1. One warp per line, one lane per
+  // byte: the loads and the stores of a line are contiguous.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t i = warp; i < n_nl; i += FQ_THREADS / 32) {
+    const uint64_t line = before + i + 1;
     const uint32_t kind = (uint32_t)(line & 3u);
-    const uint64_t rec = line >> 2;
-    if (kind == 0u) {
-      if (text[start] != '@') atomicAdd(counters + 2, 1ull);
-    } else if (kind == 2u) {
-      if (text[start] != '+') atomicAdd(counters + 2, 1ull);
-    } else if (rec < capacity) {
-      uint8_t* dst = (kind == 1u ? out_seq : out_qual) + rec * (uint64_t)read_len;
-      const uint8_t pad = kind == 1u ? (uint8_t)'N' : (uint8_t)'#';
-      bool ended = false;
-      for (int k = 0; k < read_len; k++) {
-        uint8_t ch = pad;
-        if (!ended) {
-          if (start + k < n_bytes) ch = text[start + k];
-          if (start + k >= n_bytes || ch == '\n' || ch == '\r') {
-            ended = true;
-            ch = pad;
-            if (kind == 1u) atomicAdd(counters + 1, 1ull);
-          }
-        }
-        dst[k] = ch;
-      }
+    const uint64_t start = tile_base + nl_s[i] + 1;
+    if (start >= n_bytes) continue;  // the newline that ends the text
+    if (!(kind & 1u)) {              // header / separator line: only its first byte is looked at
+      if (lane == 0 && text[start] != (kind == 0u ? '@' : '+')) atomicAdd(counters + 2, 1ull);
+      continue;
     }
+    const uint64_t rec = line >> 2;
+    if (rec >= capacity) continue;
+    // length of the line, without its line terminator
+    int len;
+    if (i + 1 < n_nl) {
+      const uint64_t end = tile_base + nl_s[i + 1];
+      len = (int)(end - start);
+      if (len > 0 && text[end - 1] == '\r') len--;
+    } else {  // the line runs into the next tile: look for its end, read_len bytes at most
+      len = 0;
+      while (len < read_len && start + len < n_bytes && text[start + len] != '\n' && text[start + len] != '\r') len++;
+    }
+    uint8_t* dst = (kind == 1u ? out_seq : out_qual) + rec * (uint64_t)read_len;
+    const uint8_t pad = kind == 1u ? (uint8_t)'N' : (uint8_t)'#';
+    for (int k = lane; k < read_len; k += 32) dst[k] = k < len ? text[start + k] : pad;
+    if (lane == 0 && kind == 1u && len < read_len) atomicAdd(counters + 1, 1ull);
   }
   // line 0 starts at byte 0 without a newline in front of it
   if (tile == 0 && threadIdx.x == 0 && n_bytes && text[0] != '@') atomicAdd(counters + 2, 1ull);

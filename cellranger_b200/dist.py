@@ -21,6 +21,8 @@ logic — owner ranges, split sizes, the exchange — is what the world_size-2 g
 """
 from __future__ import annotations
 
+import os
+import time
 from typing import List, Sequence
 
 import numpy as np
@@ -149,6 +151,18 @@ class ShardedGemWell:
         self.rank, self.world, self.group = rank, world, group
         self.bounds = None
         self.exchange_bytes = 0
+        # CRGPU_DIST_TIMING=1: host-clock time of every phase of run() (with a device sync at each boundary, so
+        # only for diagnosis - the syncs cost a little themselves)
+        self.timing = bool(os.environ.get("CRGPU_DIST_TIMING"))
+        self.times = {}
+
+    def _t(self, name, t0):
+        if not self.timing:
+            return t0
+        self.e.sync()
+        t1 = time.perf_counter()
+        self.times[name] = self.times.get(name, 0.0) + (t1 - t0) * 1e3
+        return t1
 
     def _allreduce(self, t: torch.Tensor):
         if self.world > 1 and t is not None and t.numel():
@@ -156,23 +170,29 @@ class ShardedGemWell:
 
     def run(self):
         e = self.e
+        t = time.perf_counter() if self.timing else 0.0
         p2p = self.world > 1 and getattr(e, "p2p", False)
         if p2p:
             e.exchange_reset()  # ordered before every peer's scatter by the all-reduces below
         e.make_shard()
-        for t in e.prior_tensors():
-            self._allreduce(t)
+        t = self._t("pass1", t)
+        for x in e.prior_tensors():
+            self._allreduce(x)
         self._allreduce(e.fb_counts_tensor())
         e.sync()
+        t = self._t("allreduce.priors", t)
         e.barcode_correction()
-        for t in e.corrected_tensors():
-            self._allreduce(t)
+        t = self._t("pass2", t)
+        for x in e.corrected_tensors():
+            self._allreduce(x)
         e.sync()
+        t = self._t("allreduce.corrected", t)
         valid = e.valid_count_tensors()  # identical on every rank
         total = valid[0].to(torch.int64)
-        for t in valid[1:]:
-            total = total + t.to(torch.int64)
+        for x in valid[1:]:
+            total = total + x.to(torch.int64)
         self.bounds = owner_bounds(total, self.world)
+        t = self._t("owner_bounds", t)
         if p2p:
             # fused: one pass writes every key into its owner's receive buffer over NVLink
             sent = e.keys_scatter_peers(self.bounds)
@@ -190,5 +210,7 @@ class ShardedGemWell:
                                    input_split_sizes=[int(x) for x in send_counts], group=self.group)
             self.exchange_bytes = int(send_counts.sum() - send_counts[self.rank]) * 8
             e.keys_set(recv)
+        t = self._t("exchange", t)
         e.set_owned_range(int(self.bounds[self.rank]), int(self.bounds[self.rank + 1]))
         e.align_and_count()
+        t = self._t("count", t)
