@@ -715,7 +715,7 @@ __global__ void __launch_bounds__(CP_THREADS) molecules_compact_kernel(
     const unsigned long long* __restrict__ dkeys, const uint32_t* __restrict__ c0, const uint32_t* __restrict__ best,
     const unsigned long long* __restrict__ inc, const uint8_t* __restrict__ low, uint64_t m,
     unsigned long long* __restrict__ mol_key, uint32_t* __restrict__ mol_reads, unsigned long long* desc,
-    uint32_t* ticket, unsigned long long* total_out) {
+    uint32_t* ticket, unsigned long long* total_out, unsigned long long* low_reads_out) {
   __shared__ uint32_t scan_s[CP_THREADS / 32 + 1];
   __shared__ unsigned long long bcast;
   __shared__ uint32_t tile_s;
@@ -753,12 +753,18 @@ __global__ void __launch_bounds__(CP_THREADS) molecules_compact_kernel(
   }
   bool f[CP_ITEMS];
   uint32_t cnt = 0;
+  unsigned long long low_reads = 0;  // reads whose corrected key is low support (is_low_support_umi)
 #pragma unroll
   for (int i = 0; i < CP_ITEMS; i++) {
-    const bool is_target = b[i] == (uint32_t)(first + i) || (in[i] >> 40) != 0ull;
-    f[i] = first + i < m && is_target && !lw[i];
+    const uint64_t j = first + i;
+    const bool self = b[i] == (uint32_t)j;
+    const bool is_target = self || (in[i] >> 40) != 0ull;
+    f[i] = j < m && is_target && !lw[i];
     cnt += f[i];
+    if (j < m && (self ? lw[i] != 0 : low[b[i]] != 0)) low_reads += c0[j];
   }
+  for (int d = 16; d > 0; d >>= 1) low_reads += __shfl_xor_sync(0xFFFFFFFFu, low_reads, d);
+  if ((threadIdx.x & 31) == 0 && low_reads) atomicAdd(low_reads_out, low_reads);
   const uint64_t n_tiles = (m + CP_TILE - 1) / CP_TILE;
   const CpPlace pl = cp_place(cnt, tile, n_tiles, desc, total_out, scan_s, &bcast);
   __shared__ unsigned long long st_k[CP_TILE];
@@ -791,15 +797,6 @@ __global__ void entries_kernel(const unsigned long long* __restrict__ mol_key, c
     ent_feature[e] = (uint32_t)((k >> kl.feature_shift) & ((1ull << fm.fbits) - 1ull));
     ent_count[e] = (uint32_t)(nxt - p);
   }
-}
-
-__global__ void low_reads_kernel(const uint32_t* __restrict__ c0, const uint32_t* __restrict__ best,
-                                 const uint8_t* __restrict__ low, uint64_t m, unsigned long long* scalars) {
-  unsigned long long s = 0;
-  for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < m; j += (uint64_t)gridDim.x * blockDim.x)
-    if (low[best[j]]) s += c0[j];
-  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
-  if ((threadIdx.x & 31) == 0 && s) atomicAdd(scalars + 6, s);
 }
 
 // ---------------------------------------------------------------------------
@@ -1117,15 +1114,14 @@ int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
     }
   }
   mark("count.dedup.molecules");
-  low_reads_kernel<<<grid_for(m), 256, 0, st>>>(b.c0, b.best, b.low, m, b.scalars);
-  launches++;
   // 4. molecules = correction targets that are not low support (key2 now holds their keys)
   {
     uint64_t tiles = (m + CP_TILE - 1) / CP_TILE;
     cudaMemsetAsync(ss.desc, 0, tiles * 8, st);
     cudaMemsetAsync(ss.ticket, 0, 4, st);
     molecules_compact_kernel<<<(unsigned)tiles, CP_THREADS, 0, st>>>(b.dkeys, b.c0, b.best, b.inc, b.low, m, b.key2,
-                                                                    b.mol, ss.desc, ss.ticket, b.scalars + 2);
+                                                                    b.mol, ss.desc, ss.ticket, b.scalars + 2,
+                                                                    b.scalars + 6);
     launches++;
   }
   return launches;

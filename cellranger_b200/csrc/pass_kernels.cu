@@ -246,6 +246,40 @@ __global__ void __launch_bounds__(THREADS) pass1_staged_kernel(const Pass1Args a
     }
   }
 
+  // Output placement is deferred by one tile: the keys / invalid entries of tile i wait in registers until the
+  // block scan of tile i+1 has passed its barrier, by which time the global atomic that reserved their space
+  // has long returned - its round trip is off the critical path and one of the two block barriers is gone.
+  bool have_p = false;
+  unsigned long long p_key[RPT];
+  uint32_t p_bc[RPT], p_nmask[RPT], p_flags = 0, p_excl = 0;  // p_flags: bit k = key, bit 8+k = invalid entry
+  uint4 p_bcq[RPT];
+  uint64_t p_first = 0;
+  int p_par = 0;
+  unsigned long long pend_base = 0ull;  // thread 0: the atomic's result, stored to shared memory one tile later
+  bool pend_store = false;
+#pragma unroll
+  for (int k = 0; k < RPT; k++) {
+    p_key[k] = 0ull;
+    p_bc[k] = p_nmask[k] = 0u;
+    p_bcq[k] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  auto flush_pending = [&]() {
+    const unsigned long long base = base_bcast[p_par];
+    uint64_t kpos = (base & 0xFFFFFFFFull) + (p_excl & 0xFFFFu);
+    uint64_t ipos = (base >> 32) + (p_excl >> 16);
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
+      if ((p_flags >> k) & 1u) __stcs(a.keys + kpos++, p_key[k]);
+      if ((p_flags >> (8 + k)) & 1u) {
+        a.inv_idx[ipos] = (uint32_t)(p_first + tid + k * THREADS);
+        a.inv_bc[ipos] = p_bc[k];
+        a.inv_nmask[ipos] = p_nmask[k];
+        a.inv_qual[ipos] = p_bcq[k];
+        ipos++;
+      }
+    }
+  };
+
   uint32_t it = 0;
   for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
     const int s = it % STAGES;
@@ -349,6 +383,14 @@ __global__ void __launch_bounds__(THREADS) pass1_staged_kernel(const Pass1Args a
       n_inv += inval[k];
     }
 
+    // the per-read words need no placement
+#pragma unroll
+    for (int k = 0; k < RPT; k++)
+      if (live[k]) {
+        const uint64_t gi = first + tid + k * THREADS;
+        __stcs(a.bc_out + gi, bcw[k]);
+        __stcs(a.umi_out + gi, umw[k]);
+      }
     // ---- phase 3: one block scan places the tile's keys and invalid entries (counts packed 16+16) ----
     const uint32_t v = n_key | (n_inv << 16);
     uint32_t inc = v;
@@ -359,6 +401,10 @@ __global__ void __launch_bounds__(THREADS) pass1_staged_kernel(const Pass1Args a
     }
     const int par = it & 1;
     if (lane == 31) warp_tot[par][warp] = inc;
+    if (tid == 0 && pend_store) {  // the previous tile's base: its atomic was issued a whole tile ago
+      base_bcast[par ^ 1] = pend_base;
+      pend_store = false;
+    }
     __syncthreads();
     uint32_t wsum = 0, tot = 0;
 #pragma unroll
@@ -367,32 +413,31 @@ __global__ void __launch_bounds__(THREADS) pass1_staged_kernel(const Pass1Args a
       if (w < warp) wsum += c;
       tot += c;
     }
-    const uint32_t excl = wsum + inc - v;
-    if (tid == 0)
-      base_bcast[par] = tot ? atomicAdd(a.counters, (unsigned long long)(tot & 0xFFFFu) |
-                                                        ((unsigned long long)(tot >> 16) << 32))
-                            : 0ull;
-    __syncthreads();
-    const unsigned long long base = base_bcast[par];
-    uint64_t kpos = (base & 0xFFFFFFFFull) + (excl & 0xFFFFu);
-    uint64_t ipos = (base >> 32) + (excl >> 16);
+    if (tid == 0) {
+      pend_base = tot ? atomicAdd(a.counters, (unsigned long long)(tot & 0xFFFFu) | ((unsigned long long)(tot >> 16) << 32))
+                      : 0ull;
+      pend_store = true;
+    }
+    if (have_p) flush_pending();
+    // this tile becomes the pending one
+    p_flags = 0u;
 #pragma unroll
     for (int k = 0; k < RPT; k++) {
-      if (live[k]) {
-        uint64_t gi = first + tid + k * THREADS;
-        __stcs(a.bc_out + gi, bcw[k]);
-        __stcs(a.umi_out + gi, umw[k]);
-        if (emit[k]) __stcs(a.keys + kpos++, key[k]);
-        if (inval[k]) {
-          a.inv_idx[ipos] = (uint32_t)gi;
-          a.inv_bc[ipos] = pk[k].bc;
-          a.inv_nmask[ipos] = pk[k].nmask;
-          a.inv_qual[ipos] = pk[k].bcq;
-          ipos++;
-        }
-      }
+      p_key[k] = key[k];
+      p_bc[k] = pk[k].bc;
+      p_nmask[k] = pk[k].nmask;
+      p_bcq[k] = pk[k].bcq;
+      p_flags |= (emit[k] ? 1u : 0u) << k;
+      p_flags |= (inval[k] ? 1u : 0u) << (8 + k);
     }
+    p_excl = wsum + inc - v;
+    p_first = first;
+    p_par = par;
+    have_p = true;
   }
+  if (tid == 0 && pend_store) base_bcast[p_par] = pend_base;
+  __syncthreads();
+  if (have_p) flush_pending();
 }
 
 // counters layout for the staged kernel: one packed 64-bit word (keys in the low half). The host keeps
