@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #define CRGPU_MAX_ORD 8
 #define CRGPU_MAX_LIBS 4
@@ -208,6 +209,21 @@ __device__ __forceinline__ unsigned long long lb_load(const unsigned long long* 
   unsigned long long w;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
   return w;
+}
+
+// Tile index of a block in a chained scan. Default: blockIdx.x - blocks are dispatched in index order, so every
+// predecessor of a resident block is itself resident or finished and the look-back cannot starve (the same
+// assumption CUB's single-pass scan makes). With ticket != nullptr (CRGPU_TICKETS=1) the index comes from an
+// atomic counter instead, which costs one global round trip and a barrier before the first load of the tile.
+__device__ __forceinline__ uint32_t acquire_tile(uint32_t* ticket, uint32_t* tile_s) {
+  if (!ticket) return blockIdx.x;
+  if (threadIdx.x == 0) *tile_s = atomicAdd(ticket, 1u);
+  __syncthreads();
+  return *tile_s;
+}
+inline uint32_t* tile_ticket(uint32_t* ticket) {  // host: which ticket pointer to hand to a kernel
+  static const bool use = getenv("CRGPU_TICKETS") && atoi(getenv("CRGPU_TICKETS")) != 0;
+  return use ? ticket : nullptr;
 }
 
 // Called by every thread of the block with the block aggregate; returns the exclusive prefix of the tile.

@@ -26,9 +26,7 @@ __global__ void __launch_bounds__(THREADS) compact_kernel(Op op, uint64_t n, uns
   __shared__ unsigned long long bcast;
   __shared__ uint32_t tile_s;
   constexpr int TILE = THREADS * ITEMS;
-  if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
-  __syncthreads();
-  const uint32_t tile = tile_s;
+  const uint32_t tile = acquire_tile(ticket, &tile_s);
   const uint64_t first = (uint64_t)tile * TILE + (uint64_t)threadIdx.x * ITEMS;
   bool f[ITEMS];
   uint32_t cnt = 0;
@@ -65,7 +63,7 @@ static int run_compact(const Op& op, uint64_t n, ScanScratch s, unsigned long lo
   uint64_t tiles = (n + TILE - 1) / TILE;
   cudaMemsetAsync(s.desc, 0, tiles * 8, st);
   cudaMemsetAsync(s.ticket, 0, 4, st);
-  compact_kernel<THREADS, ITEMS, Op><<<(unsigned)tiles, THREADS, 0, st>>>(op, n, s.desc, s.ticket, total_out);
+  compact_kernel<THREADS, ITEMS, Op><<<(unsigned)tiles, THREADS, 0, st>>>(op, n, s.desc, tile_ticket(s.ticket), total_out);
   return 1;
 }
 
@@ -93,6 +91,10 @@ __device__ __forceinline__ CpPlace cp_place(uint32_t cnt, uint32_t tile, uint64_
 }
 
 // run-length encoding of sorted keys compared after `>> shift`; heads go to out_pos (and out_keys)
+// A chained scan retires at most ~32 tiles per L2 round trip (the look-back window), 60-85 tiles per
+// microsecond measured, so the byte rate of a cheap compaction is set by the bytes per tile: RLE_ITEMS = 16.
+constexpr int RLE_ITEMS = 16;
+constexpr int RLE_TILE = CP_THREADS * RLE_ITEMS;
 template <bool WRITE_KEYS>
 __global__ void __launch_bounds__(CP_THREADS) rle_kernel(const unsigned long long* __restrict__ keys, uint64_t n,
                                                          int shift, unsigned long long* __restrict__ out_keys,
@@ -101,49 +103,47 @@ __global__ void __launch_bounds__(CP_THREADS) rle_kernel(const unsigned long lon
   __shared__ uint32_t scan_s[CP_THREADS / 32 + 1];
   __shared__ unsigned long long bcast;
   __shared__ uint32_t tile_s;
-  if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
-  __syncthreads();
-  const uint32_t tile = tile_s;
-  const uint64_t first = (uint64_t)tile * CP_TILE + (uint64_t)threadIdx.x * CP_ITEMS;
-  unsigned long long k[CP_ITEMS];
-  if (first + CP_ITEMS <= n) {
+  const uint32_t tile = acquire_tile(ticket, &tile_s);
+  const uint64_t first = (uint64_t)tile * RLE_TILE + (uint64_t)threadIdx.x * RLE_ITEMS;
+  unsigned long long k[RLE_ITEMS];
+  if (first + RLE_ITEMS <= n) {
     const ulonglong2* v = reinterpret_cast<const ulonglong2*>(keys + first);  // 64-byte aligned
 #pragma unroll
-    for (int i = 0; i < CP_ITEMS / 2; i++) {
+    for (int i = 0; i < RLE_ITEMS / 2; i++) {
       ulonglong2 t = __ldcs(v + i);
       k[2 * i] = t.x;
       k[2 * i + 1] = t.y;
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < CP_ITEMS; i++) k[i] = first + i < n ? keys[first + i] : 0ull;
+    for (int i = 0; i < RLE_ITEMS; i++) k[i] = first + i < n ? keys[first + i] : 0ull;
   }
   // the key before this thread's first: the neighbour lane's last key, or one global load for lane 0
-  unsigned long long prev = __shfl_up_sync(0xFFFFFFFFu, k[CP_ITEMS - 1], 1);
+  unsigned long long prev = __shfl_up_sync(0xFFFFFFFFu, k[RLE_ITEMS - 1], 1);
   if ((threadIdx.x & 31) == 0 && first > 0 && first < n) prev = keys[first - 1];
-  bool f[CP_ITEMS];
+  bool f[RLE_ITEMS];
   uint32_t cnt = 0;
 #pragma unroll
-  for (int i = 0; i < CP_ITEMS; i++) {
+  for (int i = 0; i < RLE_ITEMS; i++) {
     const unsigned long long before = i == 0 ? prev : k[i - 1];
     f[i] = first + i < n && ((first + i == 0) || (k[i] >> shift) != (before >> shift));
     cnt += f[i];
   }
-  const uint64_t n_tiles = (n + CP_TILE - 1) / CP_TILE;
+  const uint64_t n_tiles = (n + RLE_TILE - 1) / RLE_TILE;
   const CpPlace pl = cp_place(cnt, tile, n_tiles, desc, total_out, scan_s, &bcast);
   // stage the tile's heads in shared memory so the global stores are contiguous
-  __shared__ unsigned long long st_k[WRITE_KEYS ? CP_TILE : 1];
-  __shared__ uint16_t st_p[CP_TILE];
+  __shared__ unsigned long long st_k[WRITE_KEYS ? RLE_TILE : 1];
+  __shared__ uint16_t st_p[RLE_TILE];
   uint32_t o = pl.off;
 #pragma unroll
-  for (int i = 0; i < CP_ITEMS; i++)
+  for (int i = 0; i < RLE_ITEMS; i++)
     if (f[i]) {
       if (WRITE_KEYS) st_k[o] = k[i];
-      st_p[o] = (uint16_t)(threadIdx.x * CP_ITEMS + i);
+      st_p[o] = (uint16_t)(threadIdx.x * RLE_ITEMS + i);
       o++;
     }
   __syncthreads();
-  const uint64_t tile_base = (uint64_t)tile * CP_TILE;
+  const uint64_t tile_base = (uint64_t)tile * RLE_TILE;
   for (uint32_t i = threadIdx.x; i < pl.total; i += CP_THREADS) {
     if (WRITE_KEYS) out_keys[pl.excl + i] = st_k[i];
     out_pos[pl.excl + i] = (uint32_t)(tile_base + st_p[i]);
@@ -158,10 +158,11 @@ static int run_rle(const unsigned long long* keys, uint64_t n, int shift, unsign
     cudaMemsetAsync(total_out, 0, 8, st);
     return 0;
   }
-  uint64_t tiles = (n + CP_TILE - 1) / CP_TILE;
+  uint64_t tiles = (n + RLE_TILE - 1) / RLE_TILE;
   cudaMemsetAsync(desc, 0, tiles * 8, st);
   cudaMemsetAsync(ticket, 0, 4, st);
-  rle_kernel<WRITE_KEYS><<<(unsigned)tiles, CP_THREADS, 0, st>>>(keys, n, shift, out_keys, out_pos, desc, ticket, total_out);
+  rle_kernel<WRITE_KEYS><<<(unsigned)tiles, CP_THREADS, 0, st>>>(keys, n, shift, out_keys, out_pos, desc,
+                                                                tile_ticket(ticket), total_out);
   return 1;
 }
 
@@ -719,9 +720,7 @@ __global__ void __launch_bounds__(CP_THREADS) molecules_compact_kernel(
   __shared__ uint32_t scan_s[CP_THREADS / 32 + 1];
   __shared__ unsigned long long bcast;
   __shared__ uint32_t tile_s;
-  if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
-  __syncthreads();
-  const uint32_t tile = tile_s;
+  const uint32_t tile = acquire_tile(ticket, &tile_s);
   const uint64_t first = (uint64_t)tile * CP_TILE + (uint64_t)threadIdx.x * CP_ITEMS;
   uint32_t b[CP_ITEMS];
   unsigned long long in[CP_ITEMS];
@@ -1120,7 +1119,7 @@ int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
     cudaMemsetAsync(ss.desc, 0, tiles * 8, st);
     cudaMemsetAsync(ss.ticket, 0, 4, st);
     molecules_compact_kernel<<<(unsigned)tiles, CP_THREADS, 0, st>>>(b.dkeys, b.c0, b.best, b.inc, b.low, m, b.key2,
-                                                                    b.mol, ss.desc, ss.ticket, b.scalars + 2,
+                                                                    b.mol, ss.desc, tile_ticket(ss.ticket), b.scalars + 2,
                                                                     b.scalars + 6);
     launches++;
   }
@@ -1174,9 +1173,7 @@ __global__ void __launch_bounds__(THREADS) inclusive_scan_i64_kernel(long long* 
   __shared__ unsigned long long bcast;
   __shared__ uint32_t tile_s;
   constexpr int TILE = THREADS * ITEMS;
-  if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
-  __syncthreads();
-  const uint32_t tile = tile_s;
+  const uint32_t tile = acquire_tile(ticket, &tile_s);
   const uint64_t first = (uint64_t)tile * TILE + (uint64_t)threadIdx.x * ITEMS;
   uint32_t v[ITEMS];
   uint32_t sum = 0;
@@ -1257,7 +1254,7 @@ int run_matrix(DedupBuffers& b, MatrixArgs& ma, uint64_t /*nnz_unused*/, uint64_
     uint64_t tiles = (n_bc + 1 + TILE - 1) / TILE;
     cudaMemsetAsync(ss.desc, 0, tiles * 8, st);
     cudaMemsetAsync(ss.ticket, 0, 4, st);
-    inclusive_scan_i64_kernel<THREADS, ITEMS><<<(unsigned)tiles, THREADS, 0, st>>>(ma.indptr, n_bc + 1, ss.desc, ss.ticket);
+    inclusive_scan_i64_kernel<THREADS, ITEMS><<<(unsigned)tiles, THREADS, 0, st>>>(ma.indptr, n_bc + 1, ss.desc, tile_ticket(ss.ticket));
     launches++;
   }
   return launches;

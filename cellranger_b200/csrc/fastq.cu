@@ -13,7 +13,7 @@
 namespace {
 
 constexpr int FQ_THREADS = 256;
-constexpr int FQ_BYTES = 16;  // bytes per thread
+constexpr int FQ_BYTES = 64;  // bytes per thread: 16 KB tiles (a chained scan retires ~60-85 tiles per microsecond)
 constexpr int FQ_TILE = FQ_THREADS * FQ_BYTES;
 
 // bit j set iff byte j of the 16-byte chunk is '\n'
@@ -38,26 +38,24 @@ __global__ void __launch_bounds__(FQ_THREADS) fastq_extract_kernel(
   __shared__ unsigned long long bcast;
   __shared__ uint32_t tile_s;
   __shared__ uint16_t nl_s[FQ_TILE];  // offsets of the tile's newlines, in order
-  if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
-  __syncthreads();
-  const uint32_t tile = tile_s;
+  const uint32_t tile = acquire_tile(ticket, &tile_s);
   const uint64_t tile_base = (uint64_t)tile * FQ_TILE;
   const uint64_t p0 = tile_base + (uint64_t)threadIdx.x * FQ_BYTES;
-  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  // newline mask of the thread's 64 bytes
+  unsigned long long m = 0ull;
   if (p0 + FQ_BYTES <= n_bytes) {
-    v = __ldg(reinterpret_cast<const uint4*>(text + p0));
+    const uint4* src = reinterpret_cast<const uint4*>(text + p0);
+#pragma unroll
+    for (int c = 0; c < FQ_BYTES / 16; c++) m |= (unsigned long long)newline_mask(__ldg(src + c)) << (16 * c);
   } else if (p0 < n_bytes) {
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
-    for (int j = 0; j < FQ_BYTES && p0 + j < n_bytes; j++) w[j >> 2] |= (uint32_t)text[p0 + j] << (8 * (j & 3));
-    v = make_uint4(w[0], w[1], w[2], w[3]);
+    for (int j = 0; j < FQ_BYTES && p0 + j < n_bytes; j++)
+      if (text[p0 + j] == '\n') m |= 1ull << j;
   }
-  uint32_t m = newline_mask(v);
-  if (p0 + FQ_BYTES > n_bytes) m &= p0 < n_bytes ? ((1u << (n_bytes - p0)) - 1u) : 0u;
   uint32_t n_nl;
-  uint32_t off = block_exclusive_scan<FQ_THREADS>((uint32_t)__popc(m), &n_nl, scan_s);
+  uint32_t off = block_exclusive_scan<FQ_THREADS>((uint32_t)__popcll(m), &n_nl, scan_s);
   while (m) {
-    const int j = __ffs(m) - 1;
-    m &= m - 1u;
+    const int j = __ffsll((long long)m) - 1;
+    m &= m - 1ull;
     nl_s[off++] = (uint16_t)(threadIdx.x * FQ_BYTES + j);
   }
   const uint64_t n_tiles = (n_bytes + FQ_TILE - 1) / FQ_TILE;
@@ -110,6 +108,6 @@ int launch_fastq_extract(const uint8_t* text, uint64_t n_bytes, int read_len, ui
   uint32_t* ticket = reinterpret_cast<uint32_t*>(desc + tiles + 1);
   cudaMemsetAsync(temp, 0, (tiles + 1) * 8 + 8, st);
   fastq_extract_kernel<<<(unsigned)tiles, FQ_THREADS, 0, st>>>(text, n_bytes, read_len, out_seq, out_qual, capacity, desc,
-                                                              ticket, counters);
+                                                              tile_ticket(ticket), counters);
   return 1;
 }
