@@ -13,7 +13,7 @@
 namespace {
 
 constexpr int FQ_THREADS = 256;
-constexpr int FQ_BYTES = 64;  // bytes per thread: 16 KB tiles (a chained scan retires ~60-85 tiles per microsecond)
+constexpr int FQ_BYTES = 32;  // bytes per thread: 8 KB tiles, staged in shared memory for the line copies
 constexpr int FQ_TILE = FQ_THREADS * FQ_BYTES;
 
 // bit j set iff byte j of the 16-byte chunk is '\n'
@@ -41,15 +41,24 @@ __global__ void __launch_bounds__(FQ_THREADS) fastq_extract_kernel(
   const uint32_t tile = acquire_tile(ticket, &tile_s);
   const uint64_t tile_base = (uint64_t)tile * FQ_TILE;
   const uint64_t p0 = tile_base + (uint64_t)threadIdx.x * FQ_BYTES;
-  // newline mask of the thread's 64 bytes
+  // stage the thread's bytes in shared memory and find its newlines
+  __shared__ __align__(16) uint8_t text_s[FQ_TILE];
   unsigned long long m = 0ull;
   if (p0 + FQ_BYTES <= n_bytes) {
     const uint4* src = reinterpret_cast<const uint4*>(text + p0);
+    uint4* dst = reinterpret_cast<uint4*>(text_s + threadIdx.x * FQ_BYTES);
 #pragma unroll
-    for (int c = 0; c < FQ_BYTES / 16; c++) m |= (unsigned long long)newline_mask(__ldg(src + c)) << (16 * c);
-  } else if (p0 < n_bytes) {
-    for (int j = 0; j < FQ_BYTES && p0 + j < n_bytes; j++)
-      if (text[p0 + j] == '\n') m |= 1ull << j;
+    for (int c = 0; c < FQ_BYTES / 16; c++) {
+      const uint4 v = __ldg(src + c);
+      dst[c] = v;
+      m |= (unsigned long long)newline_mask(v) << (16 * c);
+    }
+  } else {
+    for (int j = 0; j < FQ_BYTES; j++) {
+      const uint8_t ch = p0 + j < n_bytes ? text[p0 + j] : (uint8_t)0;
+      text_s[threadIdx.x * FQ_BYTES + j] = ch;
+      if (ch == '\n') m |= 1ull << j;
+    }
   }
   uint32_t n_nl;
   uint32_t off = block_exclusive_scan<FQ_THREADS>((uint32_t)__popcll(m), &n_nl, scan_s);
@@ -61,16 +70,22 @@ __global__ void __launch_bounds__(FQ_THREADS) fastq_extract_kernel(
   const uint64_t n_tiles = (n_bytes + FQ_TILE - 1) / FQ_TILE;
   const unsigned long long before = lookback_exclusive(desc, tile, (unsigned long long)n_nl, &bcast);  // syncs
   if (tile == n_tiles - 1 && threadIdx.x == 0) counters[0] = before + n_nl;
-  // The line that starts after newline i of the tile has index before + i + 1. One warp per line, one lane per
-  // byte: the loads and the stores of a line are contiguous.
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (uint32_t i = warp; i < n_nl; i += FQ_THREADS / 32) {
+  // byte at tile offset o: from the staged copy, or from global memory past the end of the tile
+  auto byte_at = [&](uint32_t o) -> uint8_t { return o < (uint32_t)FQ_TILE ? text_s[o] : text[tile_base + o]; };
+  // The line that starts after newline i of the tile has index before + i + 1. Eight lanes per line (four
+  // lines per warp instruction - with a whole warp per line the kernel was bound by the scalar per-line logic,
+  // 94 warp instructions per line): the group works out where the line goes, its lanes copy the bytes.
+  constexpr int GROUP = 8;
+  const int lane = threadIdx.x & 31, sub = lane & (GROUP - 1);
+  const uint32_t group = threadIdx.x / GROUP, n_groups = FQ_THREADS / GROUP;
+  for (uint32_t i = group; i < n_nl; i += n_groups) {
     const uint64_t line = before + i + 1;
     const uint32_t kind = (uint32_t)(line & 3u);
-    const uint64_t start = tile_base + nl_s[i] + 1;
+    const uint32_t so = (uint32_t)nl_s[i] + 1u;  // tile offset of the line start
+    const uint64_t start = tile_base + so;
     if (start >= n_bytes) continue;  // the newline that ends the text
     if (!(kind & 1u)) {              // header / separator line: only its first byte is looked at
-      if (lane == 0 && text[start] != (kind == 0u ? '@' : '+')) atomicAdd(counters + 2, 1ull);
+      if (sub == 0 && byte_at(so) != (kind == 0u ? '@' : '+')) atomicAdd(counters + 2, 1ull);
       continue;
     }
     const uint64_t rec = line >> 2;
@@ -78,17 +93,21 @@ __global__ void __launch_bounds__(FQ_THREADS) fastq_extract_kernel(
     // length of the line, without its line terminator
     int len;
     if (i + 1 < n_nl) {
-      const uint64_t end = tile_base + nl_s[i + 1];
-      len = (int)(end - start);
-      if (len > 0 && text[end - 1] == '\r') len--;
+      const uint32_t eo = nl_s[i + 1];
+      len = (int)(eo - so);
+      if (len > 0 && text_s[eo - 1] == '\r') len--;
     } else {  // the line runs into the next tile: look for its end, read_len bytes at most
       len = 0;
-      while (len < read_len && start + len < n_bytes && text[start + len] != '\n' && text[start + len] != '\r') len++;
+      while (len < read_len && start + len < n_bytes) {
+        const uint8_t ch = byte_at(so + len);
+        if (ch == '\n' || ch == '\r') break;
+        len++;
+      }
     }
     uint8_t* dst = (kind == 1u ? out_seq : out_qual) + rec * (uint64_t)read_len;
     const uint8_t pad = kind == 1u ? (uint8_t)'N' : (uint8_t)'#';
-    for (int k = lane; k < read_len; k += 32) dst[k] = k < len ? text[start + k] : pad;
-    if (lane == 0 && kind == 1u && len < read_len) atomicAdd(counters + 1, 1ull);
+    for (int k = sub; k < read_len; k += GROUP) dst[k] = k < len ? byte_at(so + k) : pad;
+    if (sub == 0 && kind == 1u && len < read_len) atomicAdd(counters + 1, 1ull);
   }
   // line 0 starts at byte 0 without a newline in front of it
   if (tile == 0 && threadIdx.x == 0 && n_bytes && text[0] != '@') atomicAdd(counters + 2, 1ull);

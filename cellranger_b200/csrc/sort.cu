@@ -238,13 +238,12 @@ __global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) radix_onesweep_kerne
   constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* s_warp_hist = reinterpret_cast<uint32_t*>(smem_raw + SORT_TILE * 8);
-  __shared__ uint32_t tile_s;
   const int tid = threadIdx.x;
-  if (ticket && tid == 0) tile_s = atomicAdd(ticket, 1u);
   for (int i = tid; i < WARPS * RADIX / 4; i += SORT_THREADS)
     reinterpret_cast<uint4*>(s_warp_hist)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
-  const uint32_t tile = ticket ? tile_s : blockIdx.x;  // see acquire_tile() in common.cuh
+  const uint32_t tile = blockIdx.x;  // blocks are dispatched in index order, see acquire_tile() in common.cuh
+  (void)ticket;
   const uint64_t tile_first = (uint64_t)tile * SORT_TILE;
   const int cnt = (n - tile_first) < (uint64_t)SORT_TILE ? (int)(n - tile_first) : SORT_TILE;
   if (cnt == SORT_TILE)
@@ -302,7 +301,7 @@ static int run_passes(unsigned long long* keys, unsigned long long* alt, uint64_
   for (int p = 0; p < n_passes; p++) {
     cudaMemsetAsync(desc, 0, (size_t)tiles * RADIX * 8, st);
     cudaMemsetAsync(ticket, 0, 4, st);
-    kern<<<(unsigned)tiles, THREADS, smem, st>>>(src, dst, n, begin_bit + p * RADIX_BITS, hist + (size_t)p * RADIX, desc, ticket);  // tickets: 5 % faster here than blockIdx order
+    kern<<<(unsigned)tiles, THREADS, smem, st>>>(src, dst, n, begin_bit + p * RADIX_BITS, hist + (size_t)p * RADIX, desc, ticket);
     launches++;
     std::swap(src, dst);
   }
