@@ -473,6 +473,10 @@ class GemWell:
     def exchange_reset(self):
         check(self.L.crgpu_exchange_reset(self._ctx), "crgpu_exchange_reset")
 
+    def keys_scatter_peers_begin(self, bounds):
+        b = np.ascontiguousarray(bounds, dtype=np.uint32)
+        check(self.L.crgpu_keys_scatter_peers_begin(self._ctx, b.shape[0] - 1, ptr(b)), "crgpu_keys_scatter_peers_begin")
+
     def keys_scatter_peers(self, bounds) -> np.ndarray:
         b = np.ascontiguousarray(bounds, dtype=np.uint32)
         out = np.zeros(b.shape[0] - 1, dtype=np.uint64)

@@ -156,6 +156,12 @@ struct crgpu_ctx {
   unsigned long long* peer_buf[CRGPU_MAX_PARTS] = {nullptr};
   unsigned long long* peer_cursor[CRGPU_MAX_PARTS] = {nullptr};
   bool peer_opened[CRGPU_MAX_PARTS] = {false};
+  // early part of the exchange (keys of pass 1, sent on a second stream while pass 2 runs)
+  cudaStream_t xchg_stream = nullptr;
+  cudaEvent_t xchg_ready = nullptr, xchg_done = nullptr;
+  bool xchg_early = false;
+  uint64_t xchg_early_keys = 0;
+  uint32_t xchg_early_bounds[CRGPU_MAX_PARTS + 1] = {0};
 
   uint64_t stats[CRGPU_STAT_COUNT] = {0};
   uint64_t launches = 0;
@@ -383,6 +389,9 @@ void crgpu_ctx_destroy(crgpu_ctx* c) {
       cudaIpcCloseMemHandle(c->peer_buf[r]);
       cudaIpcCloseMemHandle(c->peer_cursor[r]);
     }
+  if (c->xchg_stream) cudaStreamDestroy(c->xchg_stream);
+  if (c->xchg_ready) cudaEventDestroy(c->xchg_ready);
+  if (c->xchg_done) cudaEventDestroy(c->xchg_done);
   if (c->xchg_buf) cudaFree(c->xchg_buf);
   if (c->xchg_cursor) cudaFree(c->xchg_cursor);
   cudaStreamDestroy(c->stream);
@@ -1166,6 +1175,36 @@ int crgpu_exchange_reset(crgpu_ctx* c) {
   CU(cudaSetDevice(c->device));
   CU(cudaMemsetAsync(c->xchg_cursor, 0, 16, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  c->xchg_early = false;
+  return CRGPU_OK;
+}
+
+int crgpu_keys_scatter_peers_begin(crgpu_ctx* c, int32_t n_parts, const uint32_t* bounds) {
+  if (!c || !bounds || n_parts != c->xchg_ranks) return fail(CRGPU_E_INVALID, "bad argument / exchange not connected");
+  if (c->stage < 1) return fail(CRGPU_E_INVALID, "crgpu_pass1 must run first");
+  if (c->keys_external) return fail(CRGPU_E_INVALID, "the keys of this context were replaced");
+  CU(cudaSetDevice(c->device));
+  for (int p = 0; p < n_parts; p++)
+    if (bounds[p] > bounds[p + 1]) return fail(CRGPU_E_INVALID, "bounds must be non-decreasing");
+  if (!c->xchg_stream) {
+    CU(cudaStreamCreateWithFlags(&c->xchg_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->xchg_ready, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->xchg_done, cudaEventDisableTiming));
+  }
+  // the keys emitted so far (pass 1 is complete on the context stream once the counter has been read)
+  unsigned long long n1 = 0;
+  CU(cudaMemcpyAsync(&n1, c->counters.as<unsigned long long>() + 1, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaEventRecord(c->xchg_ready, c->stream));
+  CU(cudaStreamWaitEvent(c->xchg_stream, c->xchg_ready, 0));
+  unsigned long long* d_sent = c->scalars.as<unsigned long long>() + 32;
+  c->launches += run_owner_scatter_peers(c->keys.as<unsigned long long>(), n1, c->kl.rank_shift, bounds, n_parts,
+                                         c->peer_buf, c->peer_cursor, c->xchg_capacity, d_sent, c->xchg_stream);
+  CHECK_KERNEL();
+  CU(cudaEventRecord(c->xchg_done, c->xchg_stream));
+  c->xchg_early = true;
+  c->xchg_early_keys = n1;
+  memcpy(c->xchg_early_bounds, bounds, (size_t)(n_parts + 1) * 4);
   return CRGPU_OK;
 }
 
@@ -1177,15 +1216,28 @@ int crgpu_keys_scatter_peers(crgpu_ctx* c, int32_t n_parts, const uint32_t* boun
   if ((rc = fetch_n_keys(c))) return rc;
   for (int p = 0; p < n_parts; p++)
     if (bounds[p] > bounds[p + 1]) return fail(CRGPU_E_INVALID, "bounds must be non-decreasing");
+  uint64_t first = 0;
+  if (c->xchg_early) {
+    if (memcmp(c->xchg_early_bounds, bounds, (size_t)(n_parts + 1) * 4) != 0)
+      return fail(CRGPU_E_INVALID, "bounds differ from the ones given to crgpu_keys_scatter_peers_begin");
+    first = c->xchg_early_keys;  // already on their way
+    if (first > c->n_keys) return fail(CRGPU_E_INVALID, "internal: early key count exceeds the key count");
+  }
   unsigned long long* d_sent = c->scalars.as<unsigned long long>() + 16;
-  c->launches += run_owner_scatter_peers(c->keys.as<unsigned long long>(), c->n_keys, c->kl.rank_shift, bounds, n_parts,
-                                         c->peer_buf, c->peer_cursor, c->xchg_capacity, d_sent, c->stream);
+  c->launches += run_owner_scatter_peers(c->keys.as<unsigned long long>() + first, c->n_keys - first, c->kl.rank_shift,
+                                         bounds, n_parts, c->peer_buf, c->peer_cursor, c->xchg_capacity, d_sent,
+                                         c->stream);
   CHECK_KERNEL();
-  unsigned long long h[CRGPU_MAX_PARTS] = {0};
+  unsigned long long h[CRGPU_MAX_PARTS] = {0}, h_early[CRGPU_MAX_PARTS] = {0};
+  if (c->xchg_early) {
+    CU(cudaStreamWaitEvent(c->stream, c->xchg_done, 0));
+    CU(cudaMemcpyAsync(h_early, c->scalars.as<unsigned long long>() + 32, n_parts * 8, cudaMemcpyDeviceToHost, c->stream));
+    c->xchg_early = false;
+  }
   CU(cudaMemcpyAsync(h, d_sent, n_parts * 8, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));  // this rank's peer stores are complete
+  CU(cudaStreamSynchronize(c->stream));  // this rank's peer stores (both parts) are complete
   if (out_sent)
-    for (int p = 0; p < n_parts; p++) out_sent[p] = h[p];
+    for (int p = 0; p < n_parts; p++) out_sent[p] = h[p] + h_early[p];
   return CRGPU_OK;
 }
 

@@ -174,7 +174,7 @@ int crgpu_valid_counts_refresh(crgpu_ctx* ctx);
  * straight into the buffer of the rank that owns its barcode (one pass over the keys, block-aggregated remote
  * cursor claims, coalesced peer stores). Protocol per step, on every rank:
  *   crgpu_exchange_reset            (before the first collective of the step)
- *   ... pass1, all-reduces, pass2 ...
+ *   ... pass1, all-reduce of the priors [, crgpu_keys_scatter_peers_begin], pass2, all-reduce ...
  *   crgpu_keys_scatter_peers        (returns when this rank's stores are complete)
  *   <any cross-rank barrier>
  *   crgpu_exchange_finish           (adopts the received keys as this context's key set)
@@ -184,6 +184,11 @@ int crgpu_exchange_init(crgpu_ctx* ctx, uint64_t capacity_keys, void* out_handle
 int crgpu_exchange_connect(crgpu_ctx* ctx, int32_t n_ranks, int32_t my_rank, const void* handles);
 int crgpu_exchange_reset(crgpu_ctx* ctx);
 int crgpu_keys_scatter_peers(crgpu_ctx* ctx, int32_t n_parts, const uint32_t* bounds, uint64_t* out_sent);
+/* Optional early part: called between crgpu_pass1 and crgpu_pass2 (once the bounds are known - e.g. from the
+ * all-reduced priors), it sends the keys pass 1 emitted on a second stream, so that the NVLink traffic runs
+ * under pass 2; the later crgpu_keys_scatter_peers (same bounds) then sends only the keys of pass 2 and waits
+ * for both parts. */
+int crgpu_keys_scatter_peers_begin(crgpu_ctx* ctx, int32_t n_parts, const uint32_t* bounds);
 int crgpu_exchange_finish(crgpu_ctx* ctx, uint64_t* out_received);
 /* restrict the matrix columns this context owns to content ranks [lo, hi) */
 int crgpu_set_owned_range(crgpu_ctx* ctx, uint32_t lo, uint32_t hi);

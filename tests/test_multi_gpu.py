@@ -44,7 +44,7 @@ def _worker(rank, world, port, outdir, name, n_reads, kw, p2p):
         eng = TorchEngine(gw, 1)
         if p2p:
             assert eng.setup_peer_exchange(rank, world, capacity_keys=n_reads), "no peer access between the GPUs"
-        sh = ShardedGemWell(eng, rank, world)
+        sh = ShardedGemWell(eng, rank, world, early_scatter=(p2p == "early"))
         for _ in range(2):  # twice: the second run reuses every buffer
             sh.run()
         m = gw.count_matrix()
@@ -58,7 +58,7 @@ def _worker(rank, world, port, outdir, name, n_reads, kw, p2p):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("p2p", [True, False], ids=["peer-stores", "nccl-all-to-all"])
+@pytest.mark.parametrize("p2p", [True, "early", False], ids=["peer-stores", "peer-stores-early", "nccl-all-to-all"])
 @pytest.mark.parametrize("name,n,kw", [("cfg1", 400_000, {}), ("cfg2", 300_000, {"n_whitelist": 300_000, "n_cells": 300})])
 def test_two_gpu_sharded_matches_oracle(name, n, kw, p2p):
     import torch
