@@ -165,7 +165,7 @@ def run_reference(args):
 def workload_config(name, cfg, reads_per_gpu, gpus):
     desc = {
         "cfg2": "200M synthetic 3' v3 reads (16bp BC + 12bp UMI) vs 3M-february-2018-size whitelist (6794880), 30k genes, 1xB200",
-        "cfg3": "synthetic 3' v3 reads at NovaSeq S4-lane scale, 200M per GPU, sharded with barcode-owner NCCL all-to-all",
+        "cfg3": "synthetic 3' v3 reads at NovaSeq S4-lane scale, 200M per GPU, sharded by barcode owner (fused NVLink key exchange, NCCL all-to-all fallback)",
     }.get(name, name)
     return {"workload": f"{name}: {desc}", "reads_per_gpu": reads_per_gpu, "total_reads": reads_per_gpu * gpus,
             "whitelist": cfg.n_whitelist, "genes": cfg.n_genes, "cells": cfg.n_cells, "bc_len": cfg.bc_len,
