@@ -67,3 +67,25 @@ def test_feature_reference_and_chemistry_presets():
     # lib/python/cellranger/chemistry_defs.json: SC3Pv2 UMI 10 @16, SC3Pv3 UMI 12 @16
     assert (api.ChemistryDef.SC3Pv2().umi_length, api.ChemistryDef.SC3Pv3().umi_length) == (10, 12)
     assert api.Posterior().bc_confidence_threshold == 0.975
+
+
+def test_bench_reference_arm_line_has_the_contract_keys():
+    """`bench.py --impl reference` (the CPU port of the reference algorithm) prints one JSON line with the keys
+    the driver reads; here on a tiny sample so that it runs in seconds."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--cpu-sample", "30000",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["config"]["workload"].startswith("cfg2")
