@@ -61,3 +61,18 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in txt.lower().replace("# oracle", ""), f"{f} mentions the oracle"
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/crgpu.h must be consumable by a C compiler (the boundary is a C ABI, not a C++ one)."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "crgpu.h"\n'
+                   "int main(void) { crgpu_library_def d; crgpu_read_batch b; (void)d; (void)b;\n"
+                   "  return sizeof(d) == 40 && CRGPU_STAT_COUNT == 16 ? 0 : 1; }\n")
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I" + os.path.join(root, "include"),
+                          "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
