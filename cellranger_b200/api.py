@@ -508,13 +508,17 @@ class GemWell:
         return {k: int(v) for k, v in zip(_lib.STAT_NAMES, out) if not k.startswith("_")}
 
     def phase_times(self) -> dict:
-        ms = (C.c_float * 32)()
+        cap = 64
+        ms = (C.c_float * cap)()
         n = C.c_int32()
-        names = C.c_char_p()
-        check(self.L.crgpu_phase_times(self._ctx, ms, 32, C.byref(n), C.byref(names)))
-        raw = C.string_at(names, 4096) if n.value else b""
-        parts = raw.split(b"\0")[: n.value]
-        return {p.decode(): float(ms[i]) for i, p in enumerate(parts)}
+        names = C.c_void_p()
+        check(self.L.crgpu_phase_times(self._ctx, ms, cap, C.byref(n), C.byref(names)))
+        out, addr = {}, names.value or 0
+        for i in range(min(n.value, cap)):  # the names are NUL-separated; read each up to its own terminator
+            name = C.string_at(addr)
+            addr += len(name) + 1
+            out[name.decode()] = float(ms[i])
+        return out
 
     def barcode_seqs(self, ranks) -> np.ndarray:
         r = np.ascontiguousarray(ranks, dtype=np.uint32)

@@ -31,15 +31,43 @@ def is_stale() -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile libcrgpu.so if it is missing or older than its sources. Several processes may get here at once
+    (every torchrun rank imports the package): the build runs under an exclusive file lock, into a temporary
+    file that replaces the library atomically, so nobody ever loads a half-written file."""
     if not force and not is_stale():
         return SO
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-lz"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    import fcntl
+
+    with open(SO + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():  # another process built it while we waited
+                return SO
+            tmp = f"{SO}.tmp.{os.getpid()}"
+            # one nvcc per translation unit, in parallel; then one link
+            objs, procs = [], []
+            for s in SOURCES:
+                obj = os.path.join(CSRC, f".{s}.{os.getpid()}.o")
+                objs.append(obj)
+                cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) + \
+                      ["-c", os.path.join(CSRC, s), "-o", obj]
+                procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+            logs = [p.communicate()[0] for p in procs]
+            try:
+                if any(p.returncode != 0 for p in procs):
+                    raise RuntimeError("nvcc failed:\n" + "\n".join(logs))
+                res = subprocess.run([_nvcc(), "-shared", "-o", tmp] + objs + ["-lz", "-ldl"], capture_output=True, text=True)
+                if res.returncode != 0:
+                    raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+                os.replace(tmp, SO)
+            finally:
+                for f in objs + [tmp]:
+                    if os.path.exists(f):
+                        os.unlink(f)
+            if verbose:
+                print("\n".join(logs))
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return SO
 
 

@@ -8,6 +8,19 @@
 #define CRGPU_MAX_LIBS 4
 #define CRGPU_MAX_PARTS 16
 
+// SM count of the current device (launch grids are sized in multiples of it); cached per device
+inline int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 // bc_out word: state in the top 2 bits, content rank below (CRGPU_NO_RANK when invalid)
 #define BC_STATE_SHIFT 30
 #define BC_RANK_MASK 0x3FFFFFFFu
@@ -211,6 +224,15 @@ __device__ __forceinline__ unsigned long long lb_load(const unsigned long long* 
   return w;
 }
 
+// Watchdog of the chained scans. A block spins on its predecessors' descriptors; that terminates only if every
+// predecessor of a resident block is itself resident or finished. With blockIdx-ordered dispatch (what the
+// hardware does today) this holds; should a scheduler ever break it (MPS time slicing, preemption), the spin
+// is bounded: after LB_SPIN_LIMIT polls the block raises this translation unit's flag and carries on with a
+// zero prefix, and the host entry point that launched the scan fails with CRGPU_E_CUDA instead of hanging.
+#define LB_SPIN_LIMIT (1u << 22)
+static __device__ unsigned int lb_timeout_flag;
+__device__ __forceinline__ void lb_raise_timeout() { atomicExch(&lb_timeout_flag, 1u); }
+
 // Tile index of a block in a chained scan. Default: blockIdx.x - blocks are dispatched in index order, so every
 // predecessor of a resident block is itself resident or finished and the look-back cannot starve (the same
 // assumption CUB's single-pass scan makes). With ticket != nullptr (CRGPU_TICKETS=1) the index comes from an
@@ -240,9 +262,17 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long l
       while (true) {
         unsigned long long w = LB_PREFIX << 62;  // lanes before tile 0 act as a zero prefix
         if (j >= 0) {
-          do {
+          uint32_t spins = 0;
+          while (true) {
             w = lb_load(desc + j);
-          } while ((w >> 62) == LB_INVALID);
+            if ((w >> 62) != LB_INVALID) break;
+            if (++spins > LB_SPIN_LIMIT) {  // watchdog: fail loudly instead of hanging
+              lb_raise_timeout();
+              w = LB_PREFIX << 62;
+              break;
+            }
+            if (spins > 64u) __nanosleep(64);
+          }
         }
         unsigned status = (unsigned)(w >> 62);
         unsigned long long val = w & 0x3FFFFFFFFFFFFFFFull;

@@ -97,6 +97,10 @@ struct Batch {
   uint64_t base = 0;
 };
 
+// fixed slots at the end of the 1024-word counter block
+constexpr int CTR_KEYS_PASS1 = 1022;   // keys_total as pass 1 left it (pass 2 restarts from here when re-run)
+constexpr int CTR_BAD_FEATURE = 1023;  // reads whose feature index has no row in the matrix
+
 int bits_for(uint64_t n_values) {  // bits to hold values 0..n_values-1
   int b = 0;
   while (b < 63 && (1ull << b) < n_values) b++;
@@ -135,7 +139,7 @@ struct crgpu_ctx {
 
   DevBuf bc_out, umi_out, umi_proc, flags;
   DevBuf keys, keys_alt, sort_temp;
-  DevBuf counters;  // [0] packed scratch, [1] keys_total, [2..] per-batch invalid totals
+  DevBuf counters;  // [0] packed scratch, [1] keys_total, [2..] per-batch invalid totals, [CTR_*] below
   unsigned long long* sorted = nullptr;
   uint64_t n_keys = 0;
   bool keys_external = false;
@@ -166,17 +170,32 @@ struct crgpu_ctx {
   uint64_t stats[CRGPU_STAT_COUNT] = {0};
   uint64_t launches = 0;
 
-  // phase timing
+  // phase timing (events come from a pool: none is created or destroyed in the steady state)
   std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> phases;
+  std::vector<cudaEvent_t> event_pool;
   std::string phase_names;
+
+  // scratch of crgpu_correct_barcodes (grow-only, so that the plugin seam allocates nothing per call)
+  DevBuf cb_seq, cb_qual, cb_bc, cb_umi, cb_keys, cb_ctr, cb_idx, cb_ibc, cb_inm, cb_iq;
+  std::vector<uint32_t> cb_host;
 };
 
 namespace {
 
+int phase_event(crgpu_ctx* c, cudaEvent_t* e) {
+  if (!c->event_pool.empty()) {
+    *e = c->event_pool.back();
+    c->event_pool.pop_back();
+    return CRGPU_OK;
+  }
+  CU(cudaEventCreate(e));
+  return CRGPU_OK;
+}
 int phase_begin(crgpu_ctx* c, const char* name) {
   cudaEvent_t a, b;
-  CU(cudaEventCreate(&a));
-  CU(cudaEventCreate(&b));
+  int rc;
+  if ((rc = phase_event(c, &a))) return rc;
+  if ((rc = phase_event(c, &b))) return rc;
   CU(cudaEventRecord(a, c->stream));
   c->phases.push_back({name, {a, b}});
   return CRGPU_OK;
@@ -190,8 +209,8 @@ void phases_clear(crgpu_ctx* c, const char* prefix) {
   std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> keep;
   for (auto& p : c->phases) {
     if (p.first.rfind(prefix, 0) == 0) {
-      cudaEventDestroy(p.second.first);
-      cudaEventDestroy(p.second.second);
+      c->event_pool.push_back(p.second.first);
+      c->event_pool.push_back(p.second.second);
     } else {
       keep.push_back(p);
     }
@@ -383,6 +402,12 @@ void crgpu_ctx_destroy(crgpu_ctx* c) {
   for (auto& p : c->phases) {
     cudaEventDestroy(p.second.first);
     cudaEventDestroy(p.second.second);
+  }
+  for (auto e : c->event_pool) cudaEventDestroy(e);
+  {
+    DevBuf* cb[] = {&c->cb_seq, &c->cb_qual, &c->cb_bc, &c->cb_umi, &c->cb_keys, &c->cb_ctr, &c->cb_idx, &c->cb_ibc,
+                    &c->cb_inm, &c->cb_iq};
+    for (auto* b : cb) b->release();
   }
   for (int r = 0; r < CRGPU_MAX_PARTS; r++)
     if (c->peer_opened[r]) {
@@ -652,8 +677,14 @@ int crgpu_reads_add(crgpu_ctx* c, int lib, const crgpu_read_batch* rb, int* out_
   } else {
     int rc;
     size_t sb = (size_t)rb->n * rb->r1_len;
-    if ((rc = b->own_seq.ensure(sb + 16))) return rc;
-    if ((rc = b->own_qual.ensure(sb + 16))) return rc;
+    // a batch that cannot be set up goes back to the pool (its buffers are reused, nothing leaks)
+#define ENSURE_OR_RETURN(x)          \
+  if ((rc = (x))) {                  \
+    c->batch_pool.push_back(b);      \
+    return rc;                       \
+  }
+    ENSURE_OR_RETURN(b->own_seq.ensure(sb + 16));
+    ENSURE_OR_RETURN(b->own_qual.ensure(sb + 16));
     CU(cudaMemcpyAsync(b->own_seq.p, rb->r1_seq, sb, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(b->own_qual.p, rb->r1_qual, sb, cudaMemcpyHostToDevice, c->stream));
     b->r1_seq = b->own_seq.as<uint8_t>();
@@ -661,13 +692,14 @@ int crgpu_reads_add(crgpu_ctx* c, int lib, const crgpu_read_batch* rb, int* out_
     b->feature = nullptr;
     b->r2_seq = b->r2_qual = nullptr;
     if (!d.is_feature_barcode) {
-      if ((rc = b->own_feat.ensure((size_t)rb->n * 4 + 16))) return rc;
+      ENSURE_OR_RETURN(b->own_feat.ensure((size_t)rb->n * 4 + 16));
       CU(cudaMemcpyAsync(b->own_feat.p, rb->feature, (size_t)rb->n * 4, cudaMemcpyHostToDevice, c->stream));
       b->feature = b->own_feat.as<uint32_t>();
     } else {
       size_t rb2 = (size_t)rb->n * rb->r2_len;
-      if ((rc = b->own_r2s.ensure(rb2 + 16))) return rc;
-      if ((rc = b->own_r2q.ensure(rb2 + 16))) return rc;
+      ENSURE_OR_RETURN(b->own_r2s.ensure(rb2 + 16));
+      ENSURE_OR_RETURN(b->own_r2q.ensure(rb2 + 16));
+#undef ENSURE_OR_RETURN
       CU(cudaMemcpyAsync(b->own_r2s.p, rb->r2_seq, rb2, cudaMemcpyHostToDevice, c->stream));
       CU(cudaMemcpyAsync(b->own_r2q.p, rb->r2_qual, rb2, cudaMemcpyHostToDevice, c->stream));
       b->r2_seq = b->own_r2s.as<uint8_t>();
@@ -704,9 +736,15 @@ int crgpu_fastq_extract(crgpu_ctx* c, const void* text, uint64_t n_bytes, int on
   CHECK_KERNEL();
   unsigned long long h[3] = {0, 0, 0};
   uint8_t last = '\n';
+  unsigned int lb_flag = 0u;
   CU(cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   if (n_bytes) CU(cudaMemcpyAsync(&last, d_text + n_bytes - 1, 1, cudaMemcpyDeviceToHost, c->stream));
+  fastq_lb_flag_fetch(&lb_flag, c->stream);
   CU(cudaStreamSynchronize(c->stream));
+  if (lb_flag) {
+    fastq_lb_flag_clear(c->stream);
+    return fail(CRGPU_E_CUDA, "chained-scan watchdog fired in crgpu_fastq_extract (see crgpu_count)");
+  }
   const uint64_t lines = h[0] + (n_bytes && last != '\n' ? 1 : 0);
   if (lines % 4 != 0) return fail(CRGPU_E_INVALID, "FASTQ text does not hold a whole number of 4-line records");
   if (lines / 4 > capacity) return fail(CRGPU_E_LIMIT, "more FASTQ records than the output arrays hold");
@@ -738,6 +776,10 @@ int crgpu_pass1(crgpu_ctx* c) {
   if ((rc = ensure_layout(c))) return rc;
   if (c->n_reads >= (1ull << 32)) return fail(CRGPU_E_LIMIT, "a context holds at most 2^32-1 reads");
   if (c->batches.size() > 1000) return fail(CRGPU_E_LIMIT, "too many batches");
+  for (auto* b : c->batches)
+    if (!c->libs[b->lib]->def.is_feature_barcode && b->n && c->n_features <= 0)
+      return fail(CRGPU_E_INVALID, "crgpu_features_set must be called before crgpu_pass1: gene-expression reads carry "
+                                   "feature indices and the matrix has no rows yet");
   phases_clear(c, "pass1");
   if ((rc = phase_begin(c, "pass1"))) return rc;
   const size_t N = c->n_reads;
@@ -785,6 +827,8 @@ int crgpu_pass1(crgpu_ctx* c) {
     a.lib = (uint32_t)b->lib;
     a.emit_keys = l->def.is_feature_barcode ? 0 : 1;
     a.have_qual = 1;
+    a.n_features = (uint32_t)c->n_features;
+    a.bad_feature = ctr + CTR_BAD_FEATURE;
     launch_merge_counter(ctr, ctr + 1, c->stream);
     c->launches += 1 + launch_pass1(a, c->n_sms, c->stream);
     launch_split_counter(ctr, ctr + 1, ctr + 2 + bi, c->stream);
@@ -808,6 +852,8 @@ int crgpu_pass1(crgpu_ctx* c) {
       CHECK_KERNEL();
     }
   }
+  // what pass 1 leaves behind, so that crgpu_pass2 can be repeated
+  CU(cudaMemcpyAsync(ctr + CTR_KEYS_PASS1, ctr + 1, 8, cudaMemcpyDeviceToDevice, c->stream));
   if ((rc = phase_end(c))) return rc;
   c->stage = 1;
   c->keys_external = false;
@@ -847,15 +893,19 @@ int crgpu_pass2(crgpu_ctx* c) {
   phases_clear(c, "pass2");
   if ((rc = phase_begin(c, "pass2"))) return rc;
   const size_t nb = c->batches.size();
-  std::vector<unsigned long long> h(2 + nb);
-  CU(cudaMemcpyAsync(h.data(), c->counters.p, (2 + nb) * 8, cudaMemcpyDeviceToHost, c->stream));
-  std::vector<unsigned long long> fbc;
-  if (c->have_fb && c->n_features) {
-    fbc.resize(c->n_features);
-    CU(cudaMemcpyAsync(fbc.data(), c->d_fb_counts.p, (size_t)c->n_features * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (c->stage >= 2) {
+    // a repeated pass 2 (a retry after a failed collective, or a second call by mistake) starts from the state
+    // pass 1 left: no corrected reads yet, the key list ends where pass 1 ended
+    for (auto* l : c->libs) CU(cudaMemsetAsync(l->corrected.p, 0, c->content.size() * 4, c->stream));
+    CU(cudaMemcpyAsync(c->counters.as<unsigned long long>() + 1, c->counters.as<unsigned long long>() + CTR_KEYS_PASS1, 8,
+                       cudaMemcpyDeviceToDevice, c->stream));
   }
-  CU(cudaStreamSynchronize(c->stream));
+  // The per-batch invalid counts stay on the device (the kernels read them there); only a feature-barcode
+  // library needs a host round trip here, for compute_feature_dist over its exact counts.
   if (c->have_fb && c->n_features) {
+    std::vector<unsigned long long> fbc(c->n_features);
+    CU(cudaMemcpyAsync(fbc.data(), c->d_fb_counts.p, (size_t)c->n_features * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     std::vector<double> dist = feature_dist_host(fbc, c->feature_type);
     CU(cudaMemcpyAsync(c->d_feat_dist.p, dist.data(), dist.size() * 8, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));  // dist is a local
@@ -864,7 +914,6 @@ int crgpu_pass2(crgpu_ctx* c) {
   for (size_t bi = 0; bi < nb; bi++) {
     Batch* b = c->batches[bi];
     Library* l = c->libs[b->lib];
-    b->n_invalid = h[2 + bi];
     const bool is_fb = l->def.is_feature_barcode != 0;
     if (is_fb) {
       if ((rc = b->feature_res.ensure(b->n * 4 + 16))) return rc;
@@ -887,7 +936,9 @@ int crgpu_pass2(crgpu_ctx* c) {
     }
     Pass2Args a;
     memset(&a, 0, sizeof(a));
-    a.n_invalid = b->n_invalid;
+    a.n_invalid = b->n;  // upper bound: the grid is sized for it, the count itself is read on the device
+    a.n_invalid_dev = ctr + 2 + bi;
+    a.n_invalid_dev_shift = 0;
     a.inv_idx = b->inv_idx.as<uint32_t>();
     a.inv_bc = b->inv_bc.as<uint32_t>();
     a.inv_nmask = b->inv_nmask.as<uint32_t>();
@@ -907,6 +958,7 @@ int crgpu_pass2(crgpu_ctx* c) {
     a.threshold = c->threshold;
     a.max_expected_errors = c->max_expected_errors;
     a.check_expected_errors = c->max_expected_errors < 1.7976931348623157e308 ? 1 : 0;
+    a.n_features = (uint32_t)c->n_features;
     c->launches += launch_pass2(a, c->stream);
     CHECK_KERNEL();
     if (is_fb) {
@@ -943,25 +995,13 @@ int crgpu_correct_barcodes(crgpu_ctx* c, int lib, const uint8_t* bc_ascii, const
   CU(cudaSetDevice(c->device));
   Library* l = c->libs[lib];
   const int L = l->def.bc_length;
-  DevBuf d_seq, d_qual, d_bc, d_umi, d_keys, d_ctr, i_idx, i_bc, i_nm, i_q;
+  // grow-only scratch kept in the context: no allocation per call once it has reached its size
+  DevBuf &d_seq = c->cb_seq, &d_qual = c->cb_qual, &d_bc = c->cb_bc, &d_umi = c->cb_umi, &d_keys = c->cb_keys,
+         &d_ctr = c->cb_ctr, &i_idx = c->cb_idx, &i_bc = c->cb_ibc, &i_nm = c->cb_inm, &i_q = c->cb_iq;
   int rc = 0;
-  auto cleanup = [&]() {
-    d_seq.release(); d_qual.release(); d_bc.release(); d_umi.release(); d_keys.release(); d_ctr.release();
-    i_idx.release(); i_bc.release(); i_nm.release(); i_q.release();
-  };
-#define TRY(x)          \
-  if ((rc = (x))) {     \
-    cleanup();          \
-    return rc;          \
-  }
-#define CUX(call)                                                                       \
-  do {                                                                                  \
-    cudaError_t e__ = (call);                                                           \
-    if (e__ != cudaSuccess) {                                                           \
-      cleanup();                                                                        \
-      return fail(CRGPU_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));   \
-    }                                                                                   \
-  } while (0)
+#define TRY(x) \
+  if ((rc = (x))) return rc;
+#define CUX(call) CU(call)
   TRY(d_seq.ensure(n * L + 16));
   TRY(d_qual.ensure(n * L + 16));
   TRY(d_bc.ensure(n * 4));
@@ -1000,12 +1040,13 @@ int crgpu_correct_barcodes(crgpu_ctx* c, int lib, const uint8_t* bc_ascii, const
   a.emit_keys = 0;
   a.have_qual = qual ? 1 : 0;
   c->launches += launch_pass1(a, c->n_sms, c->stream);
-  unsigned long long packed = 0;
-  CUX(cudaMemcpyAsync(&packed, d_ctr.p, 8, cudaMemcpyDeviceToHost, c->stream));
-  CUX(cudaStreamSynchronize(c->stream));
+  // pass 2 takes its entry count from the device (the grid covers all n segments; the blocks past the
+  // invalid count exit at once), so the two kernels run back to back without a host round trip
   Pass2Args b2;
   memset(&b2, 0, sizeof(b2));
-  b2.n_invalid = packed >> 32;
+  b2.n_invalid = n;
+  b2.n_invalid_dev = d_ctr.as<unsigned long long>();
+  b2.n_invalid_dev_shift = 32;
   b2.inv_idx = i_idx.as<uint32_t>();
   b2.inv_bc = i_bc.as<uint32_t>();
   b2.inv_nmask = i_nm.as<uint32_t>();
@@ -1024,11 +1065,11 @@ int crgpu_correct_barcodes(crgpu_ctx* c, int lib, const uint8_t* bc_ascii, const
   b2.max_expected_errors = c->max_expected_errors;
   b2.check_expected_errors = c->max_expected_errors < 1.7976931348623157e308 ? 1 : 0;
   c->launches += launch_pass2(b2, c->stream);
-  std::vector<uint32_t> h(n);
+  c->cb_host.resize(n);
+  std::vector<uint32_t>& h = c->cb_host;
   CUX(cudaMemcpyAsync(h.data(), d_bc.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
   CUX(cudaStreamSynchronize(c->stream));
   cudaError_t e = cudaGetLastError();
-  cleanup();
   if (e != cudaSuccess) return fail(CRGPU_E_CUDA, std::string("correct_barcodes: ") + cudaGetErrorString(e));
   for (uint64_t i = 0; i < n; i++) {
     uint32_t st = h[i] >> BC_STATE_SHIFT;
@@ -1051,12 +1092,18 @@ int crgpu_key_layout(crgpu_ctx* c, int32_t* rank_shift, int32_t* feature_shift, 
   return CRGPU_OK;
 }
 
+// the key count of this context's own reads (one host round trip); reports the reads pass 1 found with a
+// feature index outside the matrix
 static int fetch_n_keys(crgpu_ctx* c) {
   if (c->keys_external) return CRGPU_OK;
-  unsigned long long h = 0;
+  unsigned long long h = 0, bad = 0;
   CU(cudaMemcpyAsync(&h, c->counters.as<unsigned long long>() + 1, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&bad, c->counters.as<unsigned long long>() + CTR_BAD_FEATURE, 8, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   c->n_keys = h;
+  if (bad)
+    return fail(CRGPU_E_INVALID, std::to_string(bad) + " reads carry a feature index >= n_features (" +
+                                     std::to_string(c->n_features) + "): the matrix has no such row");
   return CRGPU_OK;
 }
 
@@ -1384,7 +1431,17 @@ int crgpu_count(crgpu_ctx* c) {
   CU(cudaStreamSynchronize(c->stream));
   c->nnz = c->n_mol ? hs[1] : 0;
   if ((rc = phase_end(c))) return rc;
+  unsigned int lb_flags[2] = {0u, 0u};
+  sort_lb_flag_fetch(&lb_flags[0], c->stream);
+  dedup_lb_flag_fetch(&lb_flags[1], c->stream);
   CU(cudaStreamSynchronize(c->stream));
+  if (lb_flags[0] | lb_flags[1]) {
+    sort_lb_flag_clear(c->stream);
+    dedup_lb_flag_clear(c->stream);
+    return fail(CRGPU_E_CUDA, "chained-scan watchdog: a tile waited for a predecessor that never became resident "
+                              "(blocks were not dispatched in index order); results of this call are invalid - "
+                              "set CRGPU_TICKETS=1 for ticket-ordered tiles");
+  }
   c->stats[CRGPU_STAT_KEYS] = nk;
   c->stats[CRGPU_STAT_DISTINCT_KEYS] = m;
   c->stats[CRGPU_STAT_UMI_CORRECTED_KEYS] = m ? hs[3] : 0;

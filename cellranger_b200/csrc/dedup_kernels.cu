@@ -173,8 +173,17 @@ __global__ void run_lengths_kernel(const uint32_t* pos, uint64_t n_runs, uint64_
   }
 }
 
-static inline int grid_for(uint64_t n, int threads = 256, int cap = 148 * 16) {
-  return (int)std::max<uint64_t>(1, std::min<uint64_t>((n + threads - 1) / threads, (uint64_t)cap));
+// grid for a grid-stride kernel: at most per_sm blocks per SM of the current device
+static inline int grid_for(uint64_t n, int threads = 256, int per_sm = 16) {
+  return (int)std::max<uint64_t>(1, std::min<uint64_t>((n + threads - 1) / threads, (uint64_t)sm_count() * per_sm));
+}
+
+void dedup_lb_flag_fetch(unsigned int* host_out, cudaStream_t st) {
+  cudaMemcpyFromSymbolAsync(host_out, lb_timeout_flag, sizeof(unsigned int), 0, cudaMemcpyDeviceToHost, st);
+}
+void dedup_lb_flag_clear(cudaStream_t st) {
+  static const unsigned int zero = 0;
+  cudaMemcpyToSymbolAsync(lb_timeout_flag, &zero, sizeof(unsigned int), 0, cudaMemcpyHostToDevice, st);
 }
 
 // ---------------------------------------------------------------------------
@@ -999,7 +1008,7 @@ int run_owner_scatter_peers(const unsigned long long* keys, uint64_t n, int rank
   cudaMemsetAsync(d_sent, 0, CRGPU_MAX_PARTS * 8, st);
   if (!n) return 0;
   uint64_t chunks = (n + PX_CHUNK - 1) / PX_CHUNK;
-  int grid = (int)std::min<uint64_t>(chunks, 148ull * 4);
+  int grid = (int)std::min<uint64_t>(chunks, (uint64_t)sm_count() * 4);
   owner_scatter_peers_kernel<<<grid, PX_THREADS, 0, st>>>(keys, n, rank_shift, ob, pt, d_sent);
   return 1;
 }
@@ -1095,8 +1104,8 @@ int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
     const size_t slot_bytes = ((size_t)1 << slot_bits) / 4;  // 2 bits per slot
     if (b.slots_bytes < slot_bytes) return -1;
     cudaMemsetAsync(b.slots, 0, slot_bytes, st);
-    ls_mark_kernel<<<grid_for(m, 256, 148 * 32), 256, 0, st>>>(b.dkeys, m, b.kl, b.slots, slot_bits, region_bits);
-    ls_collect_kernel<<<grid_for(m, 256, 148 * 16), 256, 0, st>>>(b.dkeys, m, b.kl, b.slots, slot_bits, region_bits, b.key2,
+    ls_mark_kernel<<<grid_for(m, 256, 32), 256, 0, st>>>(b.dkeys, m, b.kl, b.slots, slot_bits, region_bits);
+    ls_collect_kernel<<<grid_for(m, 256, 16), 256, 0, st>>>(b.dkeys, m, b.kl, b.slots, slot_bits, region_bits, b.key2,
                                                                  b.scalars + 9);
     launches += 2;
     unsigned long long n_cand = 0;
@@ -1107,7 +1116,7 @@ int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
       // grouping by (rank, library, umi) only needs the bits above the feature field
       launches += sort_keys(b.key2, b.key2_alt, n_cand, b.kl.total_bits, b.sort_temp, b.sort_temp_bytes, &sorted2, st,
                             field_masks(b.kl).fbits);
-      low_support_kernel<<<grid_for(n_cand, 256, 148 * 32), 256, 0, st>>>(sorted2, n_cand, m, b.kl, b.dkeys, b.c0,
+      low_support_kernel<<<grid_for(n_cand, 256, 32), 256, 0, st>>>(sorted2, n_cand, m, b.kl, b.dkeys, b.c0,
                                                                           b.best, b.inc, b.low, b.scalars);
       launches++;
     }
@@ -1320,7 +1329,7 @@ int run_barcode_summary(DedupBuffers& b, uint64_t m, uint32_t lib, const uint32_
   if (n_bc == 0) return 0;
   summary_reads_kernel<<<grid_for(n_bc), 256, 0, st>>>(barcode_rank, valid, n_bc, out4);
   if (m == 0) return 1;
-  summary_keys_kernel<<<grid_for(m, 256, 148 * 8), 256, 0, st>>>(b.dkeys, b.c0, b.best, b.inc, b.low, m, b.kl, lib,
+  summary_keys_kernel<<<grid_for(m, 256, 8), 256, 0, st>>>(b.dkeys, b.c0, b.best, b.inc, b.low, m, b.kl, lib,
                                                                 col_of_rank, out4);
   return 2;
 }
@@ -1402,13 +1411,13 @@ int run_annotate_prepare(DedupBuffers& b, uint64_t m, uint32_t* min_read, uint32
 }
 int run_annotate_min(DedupBuffers& b, uint64_t m, const AnnotateArgs& a, uint32_t* min_read, cudaStream_t st) {
   if (!a.n || !m) return 0;
-  annotate_min_kernel<<<grid_for(a.n, 256, 148 * 32), 256, 0, st>>>(b.dkeys, m, b.kl, a, min_read);
+  annotate_min_kernel<<<grid_for(a.n, 256, 32), 256, 0, st>>>(b.dkeys, m, b.kl, a, min_read);
   return 1;
 }
 int run_annotate_final(DedupBuffers& b, uint64_t m, const AnnotateArgs& a, const uint32_t* min_read,
                        const uint32_t* rep_raw, unsigned long long*, cudaStream_t st) {
   if (!a.n) return 0;
-  annotate_final_kernel<<<grid_for(a.n, 256, 148 * 32), 256, 0, st>>>(b.dkeys, m, b.kl, a, b.best, b.low, min_read,
+  annotate_final_kernel<<<grid_for(a.n, 256, 32), 256, 0, st>>>(b.dkeys, m, b.kl, a, b.best, b.low, min_read,
                                                                      rep_raw);
   return 1;
 }

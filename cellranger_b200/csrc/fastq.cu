@@ -115,6 +115,14 @@ __global__ void __launch_bounds__(FQ_THREADS) fastq_extract_kernel(
 
 }  // namespace
 
+void fastq_lb_flag_fetch(unsigned int* host_out, cudaStream_t st) {
+  cudaMemcpyFromSymbolAsync(host_out, lb_timeout_flag, sizeof(unsigned int), 0, cudaMemcpyDeviceToHost, st);
+}
+void fastq_lb_flag_clear(cudaStream_t st) {
+  static const unsigned int zero = 0;
+  cudaMemcpyToSymbolAsync(lb_timeout_flag, &zero, sizeof(unsigned int), 0, cudaMemcpyHostToDevice, st);
+}
+
 size_t fastq_temp_bytes(uint64_t n_bytes) { return ((n_bytes + FQ_TILE - 1) / FQ_TILE + 1) * 8 + 64; }
 
 // temp: fastq_temp_bytes(n_bytes); counters: 3 x u64 (zeroed here)

@@ -24,10 +24,17 @@ struct Pass1Args {
   int emit_keys;
   int have_qual;  // 0: qualities absent (crgpu_correct_barcodes with qual == NULL)
   int debug_flags;  // profiling ablations (CRGPU_P1_DBG); 0 in production
+  uint32_t n_features;             // rows of the matrix: a feature index >= n_features (and != NO_FEATURE) is an error
+  unsigned long long* bad_feature;  // device counter of such reads (they are treated as unmapped)
 };
 
 struct Pass2Args {
-  uint64_t n_invalid;
+  uint64_t n_invalid;  // entries of the side list (an upper bound when n_invalid_packed_dev is set)
+  // optional: a device word holding the entry count (>> n_invalid_dev_shift: 32 for the packed counter word
+  // pass 1 works on, 0 for a plain count). When set, the kernel reads the count from there, so that no host
+  // round trip separates the two passes.
+  const unsigned long long* n_invalid_dev;
+  int n_invalid_dev_shift;
   const uint32_t* inv_idx;
   const uint32_t* inv_bc;
   const uint32_t* inv_nmask;
@@ -47,6 +54,7 @@ struct Pass2Args {
   double threshold;
   double max_expected_errors;
   int check_expected_errors;
+  uint32_t n_features;  // as in Pass1Args (pass 1 has counted the offenders; here they are only masked)
 };
 
 struct FbArgs {
@@ -85,6 +93,15 @@ int launch_valid_counts(const uint32_t* prior, const uint32_t* corrected, uint32
 size_t fastq_temp_bytes(uint64_t n_bytes);
 int launch_fastq_extract(const uint8_t* text, uint64_t n_bytes, int read_len, uint8_t* out_seq, uint8_t* out_qual,
                          uint64_t capacity, void* temp, unsigned long long* counters, cudaStream_t st);
+
+// look-back watchdog flags (one per translation unit with a chained scan, see common.cuh): fetch = asynchronous
+// copy of the flag to *host_out on the stream; clear = reset after a reported timeout
+void sort_lb_flag_fetch(unsigned int* host_out, cudaStream_t st);
+void sort_lb_flag_clear(cudaStream_t st);
+void dedup_lb_flag_fetch(unsigned int* host_out, cudaStream_t st);
+void dedup_lb_flag_clear(cudaStream_t st);
+void fastq_lb_flag_fetch(unsigned int* host_out, cudaStream_t st);
+void fastq_lb_flag_clear(cudaStream_t st);
 
 // ---- sort (sort.cu) ----
 // sorts n 64-bit keys on bits [begin_bit, end_bit) (stable: lower bits keep their input order); result in

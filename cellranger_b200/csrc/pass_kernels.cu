@@ -69,6 +69,17 @@ __device__ __forceinline__ unsigned long long make_key(const KeyLayout& kl, uint
          ((unsigned long long)lib << kl.lib_shift) | (unsigned long long)umi;
 }
 
+
+// a feature index the matrix has no row for (and that is not the "unmapped" marker): counted as an error of
+// the batch and treated as unmapped, so that it can never spill into the barcode-rank bits of a key
+__device__ __forceinline__ uint32_t checked_feature(uint32_t f, uint32_t n_features, unsigned long long* bad) {
+  if (f != NO_FEATURE && f >= n_features) {
+    if (bad) atomicAdd(bad, 1ull);
+    return NO_FEATURE;
+  }
+  return f;
+}
+
 __device__ __forceinline__ void classify_read(const Pass1Args& a, uint32_t bc, uint32_t nmask, uint32_t umi,
                                               bool umi_has_n, bool umi_lowq, uint32_t feature, ReadResult* r) {
   // UmiInfo::new: valid = !(has_n || is_homopolymer || low_min_qual)
@@ -326,7 +337,7 @@ __global__ void __launch_bounds__(THREADS) pass1_staged_kernel(const Pass1Args a
         uint32_t wq[NW];
         load_record<R1_LEN>(stage_qual(s), live[k] ? j : 0, wq);
         pack_umi<R1_LEN, UMI_LEN>(ws[k], wq, &pk[k]);
-        feat[k] = (have_feat && live[k]) ? stage_feat(s)[j] : NO_FEATURE;
+        feat[k] = (have_feat && live[k]) ? checked_feature(stage_feat(s)[j], a.n_features, a.bad_feature) : NO_FEATURE;
         if (!live[k]) {
           pk[k].bc = 0;
           pk[k].nmask = 1;
@@ -495,7 +506,7 @@ __global__ void __launch_bounds__(256) pass1_generic_kernel(const Pass1Args a) {
         umi = (umi << 2) | code;
         if (q) ulow |= (uint8_t)(q[a.umi_off + i] - 33) < 10;
       }
-      uint32_t feature = a.feature ? a.feature[gi] : NO_FEATURE;
+      uint32_t feature = a.feature ? checked_feature(a.feature[gi], a.n_features, a.bad_feature) : NO_FEATURE;
       classify_read(a, bc, nmask, umi, uhasn, ulow, feature, &res);
     }
     uint32_t tot_key, tot_inv;
@@ -639,6 +650,15 @@ __device__ __forceinline__ uint4 load_bytes16(const uint8_t* p) {
                     __funnelshift_r(x3, x4, sh));
 }
 
+// the same for the last records of a caller-owned buffer: `avail` readable bytes from p on (the plain loader
+// reads up to 20); bytes past the end read as 0
+__device__ __forceinline__ uint4 load_bytes16_bounded(const uint8_t* p, uint64_t avail) {
+  if (avail >= 20) return load_bytes16(p);
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  for (int i = 0; i < 16 && (uint64_t)i < avail; i++) w[i >> 2] |= (uint32_t)p[i] << (8 * (i & 3));
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 template <int THREADS, int RPT>
 __global__ void __launch_bounds__(THREADS) match_kernel(const Pass1Args a) {
   constexpr int TILE = THREADS * RPT;
@@ -660,7 +680,7 @@ __global__ void __launch_bounds__(THREADS) match_kernel(const Pass1Args a) {
       live[k] = gi < a.n;
       bc[k] = live[k] ? a.bc_out[gi] : 0u;
       uw[k] = live[k] ? a.umi_out[gi] : UMI_BCN_BIT;
-      feat[k] = (live[k] && have_feat) ? __ldcs(a.feature + gi) : NO_FEATURE;
+      feat[k] = (live[k] && have_feat) ? checked_feature(__ldcs(a.feature + gi), a.n_features, a.bad_feature) : NO_FEATURE;
     }
     uint32_t st0[RPT];
 #pragma unroll
@@ -730,7 +750,7 @@ __global__ void __launch_bounds__(THREADS) match_kernel(const Pass1Args a) {
         if (inval[k]) {
           uint32_t nmask = 0;
           if (uw[k] & UMI_BCN_BIT) {  // rare: recompute which bases are not A,C,G,T
-            uint4 sq = load_bytes16(a.seq + gi * a.r1_len + a.bc_off);
+            uint4 sq = load_bytes16_bounded(a.seq + gi * a.r1_len + a.bc_off, (a.n - gi) * a.r1_len - a.bc_off);
             const uint32_t w4[4] = {sq.x, sq.y, sq.z, sq.w};
 #pragma unroll
             for (int wd = 0; wd < 4; wd++) {
@@ -744,7 +764,7 @@ __global__ void __launch_bounds__(THREADS) match_kernel(const Pass1Args a) {
           a.inv_idx[ipos] = (uint32_t)gi;
           a.inv_bc[ipos] = bc[k];
           a.inv_nmask[ipos] = nmask;
-          a.inv_qual[ipos] = load_bytes16(a.qual + gi * a.r1_len + a.bc_off);
+          a.inv_qual[ipos] = load_bytes16_bounded(a.qual + gi * a.r1_len + a.bc_off, (a.n - gi) * a.r1_len - a.bc_off);
           ipos++;
         }
       }
@@ -832,12 +852,13 @@ int launch_pass1(const Pass1Args& a, int n_sms, cudaStream_t st) {
 __global__ void __launch_bounds__(256) pass2_kernel(const Pass2Args a) {
   __shared__ uint32_t scan_a[9];
   __shared__ unsigned long long base_bcast;
-  const uint64_t n_blocks_work = (a.n_invalid + 255) / 256;
+  const uint64_t n_invalid = a.n_invalid_dev ? (*a.n_invalid_dev >> a.n_invalid_dev_shift) : a.n_invalid;
+  const uint64_t n_blocks_work = (n_invalid + 255) / 256;
   for (uint64_t blk = blockIdx.x; blk < n_blocks_work; blk += gridDim.x) {
     const uint64_t e = blk * 256 + threadIdx.x;
     bool emit = false;
     unsigned long long key = 0ull;
-    if (e < a.n_invalid) {
+    if (e < n_invalid) {
       const uint32_t idx = a.inv_idx[e];
       const uint32_t q = a.inv_bc[e];
       const uint32_t nmask = a.inv_nmask[e];
@@ -894,7 +915,7 @@ __global__ void __launch_bounds__(256) pass2_kernel(const Pass2Args a) {
         if (a.corrected) atomicAdd(a.corrected + best_rank, 1u);
         if (a.emit_keys) {
           uint32_t uw = a.umi_out[idx];
-          uint32_t feature = a.feature ? a.feature[idx] : NO_FEATURE;
+          uint32_t feature = a.feature ? checked_feature(a.feature[idx], a.n_features, nullptr) : NO_FEATURE;
           if ((uw & UMI_VALID_BIT) && feature != NO_FEATURE) {
             emit = true;
             key = make_key(a.kl, best_rank, feature, a.lib, uw & UMI_SEQ_MASK);
@@ -916,7 +937,7 @@ __global__ void __launch_bounds__(256) pass2_kernel(const Pass2Args a) {
 int launch_pass2(const Pass2Args& a, cudaStream_t st) {
   if (a.n_invalid == 0) return 0;
   uint64_t blocks = (a.n_invalid + 255) / 256;
-  int grid = (int)std::min<uint64_t>(blocks, 148ull * 64);
+  int grid = (int)std::min<uint64_t>(blocks, (uint64_t)sm_count() * 64);
   pass2_kernel<<<grid, 256, 0, st>>>(a);
   return 1;
 }
@@ -974,7 +995,8 @@ __global__ void __launch_bounds__(FB_THREADS) fb_kernel(const FbArgs a) {
       if (gi >= a.n) break;
       uint32_t out = NO_FEATURE;
       if (fits) {
-        const uint4 sq = load_bytes16(a.r2_seq + gi * a.r2_len + a.fb_off);
+        const uint64_t avail = (a.n - gi) * (uint64_t)a.r2_len - (uint64_t)a.fb_off;  // bytes left in the buffer
+        const uint4 sq = load_bytes16_bounded(a.r2_seq + gi * a.r2_len + a.fb_off, avail);
         const uint32_t sw[4] = {sq.x, sq.y, sq.z, sq.w};
         uint32_t q = 0, nmask = 0;
 #pragma unroll
@@ -1002,7 +1024,7 @@ __global__ void __launch_bounds__(FB_THREADS) fb_kernel(const FbArgs a) {
           const uint32_t slot = atomicAdd(&s_nwork, 1u);
           w_q[slot] = q;
           w_meta[slot] = (uint32_t)(k * FB_THREADS + threadIdx.x) | ((nmask ? (uint32_t)__ffs(nmask) : 0u) << 16);
-          w_qual[slot] = load_bytes16(a.r2_qual + gi * a.r2_len + a.fb_off);
+          w_qual[slot] = load_bytes16_bounded(a.r2_qual + gi * a.r2_len + a.fb_off, avail);
         }
       }
       if (a.feature_out) a.feature_out[gi] = out;
@@ -1053,7 +1075,7 @@ __global__ void __launch_bounds__(FB_THREADS) fb_kernel(const FbArgs a) {
 int launch_fb(const FbArgs& a, cudaStream_t st) {
   if (a.n == 0) return 0;
   uint64_t tiles = (a.n + FB_TILE - 1) / FB_TILE;
-  int grid = (int)std::min<uint64_t>(tiles, 148ull * 3);
+  int grid = (int)std::min<uint64_t>(tiles, (uint64_t)sm_count() * 3);
   size_t smem = (((size_t)3 * a.n_fb + 2 * FB_TILE + 3) & ~(size_t)3) * 4 + (size_t)FB_TILE * 16;
   cudaFuncSetAttribute(fb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   fb_kernel<<<grid, FB_THREADS, smem, st>>>(a);
@@ -1089,7 +1111,7 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(const EmitArgs a) {
 int launch_emit_keys(const EmitArgs& a, cudaStream_t st) {
   if (a.n == 0) return 0;
   uint64_t blocks = (a.n + 255) / 256;
-  int grid = (int)std::min<uint64_t>(blocks, 148ull * 16);
+  int grid = (int)std::min<uint64_t>(blocks, (uint64_t)sm_count() * 16);
   emit_keys_kernel<<<grid, 256, 0, st>>>(a);
   return 1;
 }
@@ -1100,7 +1122,7 @@ __global__ void valid_counts_kernel(const uint32_t* prior, const uint32_t* corre
 }
 int launch_valid_counts(const uint32_t* prior, const uint32_t* corrected, uint32_t* out, uint64_t n, cudaStream_t st) {
   if (n == 0) return 0;
-  int grid = (int)std::min<uint64_t>((n + 255) / 256, 148ull * 16);
+  int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)sm_count() * 16);
   valid_counts_kernel<<<grid, 256, 0, st>>>(prior, corrected, out, n);
   return 1;
 }

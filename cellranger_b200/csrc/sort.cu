@@ -204,7 +204,13 @@ __device__ __forceinline__ void onesweep_tile(const unsigned long long* __restri
         for (int i = 0; i < LBK; i++) {
           if (!done) {
             unsigned long long x = w[i];
+            uint32_t spins = 0;
             while ((x >> 62) == LB_INVALID) {
+              if (++spins > LB_SPIN_LIMIT) {  // watchdog, see common.cuh
+                lb_raise_timeout();
+                x = LB_PREFIX << 62;
+                break;
+              }
               __nanosleep(40);
               x = lb_load(p - (size_t)i * RADIX);
             }
@@ -254,6 +260,15 @@ __global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) radix_onesweep_kerne
 
 }  // namespace
 
+// look-back watchdog flag of this translation unit: copied to *host_out on the stream (and cleared)
+void sort_lb_flag_fetch(unsigned int* host_out, cudaStream_t st) {
+  cudaMemcpyFromSymbolAsync(host_out, lb_timeout_flag, sizeof(unsigned int), 0, cudaMemcpyDeviceToHost, st);
+}
+void sort_lb_flag_clear(cudaStream_t st) {
+  static const unsigned int zero = 0;
+  cudaMemcpyToSymbolAsync(lb_timeout_flag, &zero, sizeof(unsigned int), 0, cudaMemcpyHostToDevice, st);
+}
+
 size_t sort_temp_bytes(uint64_t n) {
   uint64_t tiles = (n + MIN_TILE - 1) / MIN_TILE;
   // histograms + per-pass descriptors + tickets
@@ -276,7 +291,7 @@ int sort_histograms(const unsigned long long* keys, uint64_t n, int end_bit, voi
   const int n_passes = plan_passes(end_bit, begin_bit);
   unsigned long long* hist = reinterpret_cast<unsigned long long*>(temp);
   cudaMemsetAsync(hist, 0, (size_t)MAX_PASSES * RADIX * 8, st);
-  int hgrid = (int)std::min<uint64_t>((n + 511) / 512, 148ull * 4);
+  int hgrid = (int)std::min<uint64_t>((n + 511) / 512, (uint64_t)sm_count() * 4);
   radix_hist_kernel<<<hgrid, 512, 0, st>>>(keys, n, n_passes, begin_bit, hist);
   radix_scan_hist_kernel<<<n_passes, RADIX, 0, st>>>(hist);
   return 2;

@@ -184,7 +184,7 @@ int launch_synth(const crgpu_synth_params* hp, const uint32_t* d_wl, const uint3
   p.gene_cdf = d_gene_cdf;
   p.fb_cdf = d_fb_cdf;
   p.fb_packed = d_fb_packed;
-  int grid = (int)std::min<uint64_t>((n + 255) / 256, 148ull * 16);
+  int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)sm_count() * 16);
   synth_kernel<<<grid, 256, 0, st>>>(p, start, n, r1_seq, r1_qual, feature, r2_seq, r2_qual);
   return 1;
 }

@@ -129,6 +129,69 @@ def test_full_path_matches_oracle(name, n, kw):
     gw.close()
 
 
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg4", "cfg5"])
+def test_full_path_matches_oracle_1m_full_whitelist(name):
+    """BASELINE.json's configs as written except for the read count: 1 M reads against the FULL whitelists
+    (737 280 / 6 794 880 entries; cfg4 with its translated feature-barcode whitelist and Antibody Capture
+    library, cfg5 with 5 % barcode errors and saturated UMIs), every output bit-exact against the oracle:
+    priors, per-read barcode / state / UMI / flags, barcode index, CSC arrays, molecule rows, summaries."""
+    prob = helpers.make_problem(name, 1_000_000)
+    cfg = prob["cfg"]
+    assert cfg.n_whitelist == (737_280 if name == "cfg1" else 6_794_880)
+    if name == "cfg4":
+        assert prob["n_fb"] > 0
+    o = helpers.run_oracle(prob, threads=16)
+    gw = helpers.run_gpu(prob)
+    info = helpers.compare_all(o, gw, prob)
+    assert info["nnz"] > 0 and info["stats"]["reads"] == 1_000_000
+    gw.close()
+    o.close()
+
+
+def test_feature_index_out_of_range_is_an_error():
+    """A feature index the matrix has no row for must not reach a key (it would spill into the barcode-rank
+    bits): the batch is refused with CRGPU_E_INVALID, and a GEX batch without crgpu_features_set is refused too."""
+    import cellranger_b200 as cb
+
+    prob = helpers.make_problem("cfg1", 5000, n_whitelist=3000, n_cells=5)
+    g = prob["gex"]
+    bad = g["feature"].copy()
+    mapped = np.flatnonzero(bad != 0xFFFFFFFF)
+    bad[mapped[7]] = prob["cfg"].n_genes          # first index past the matrix
+    bad[mapped[11]] = 0x7FFFFFFF
+    prob["gex"]["feature"] = bad
+    gw = helpers.run_gpu(prob, run=False)
+    gw.make_shard()
+    gw.barcode_correction()
+    with pytest.raises(cb.CrgpuError, match="feature index"):
+        gw.align_and_count()
+    gw.close()
+    t = prob["tables"]
+    gw = cb.GemWell()
+    wl = gw.add_whitelist(cb.Whitelist.plain(t.whitelist))
+    lib = gw.add_library(wl, cb.ChemistryDef.SC3Pv2())
+    gw.add_reads(lib, g["r1_seq"], g["r1_qual"], g["feature"])
+    with pytest.raises(cb.CrgpuError, match="crgpu_features_set"):
+        gw.make_shard()
+    gw.close()
+
+
+def test_barcode_correction_twice_is_idempotent():
+    """crgpu_pass2 called again (a retry) must not add the corrections, or the corrected reads' keys, twice."""
+    prob = helpers.make_problem("cfg1", 60_000)
+    o = helpers.run_oracle(prob)
+    gw = helpers.run_gpu(prob, run=False)
+    gw.make_shard()
+    gw.barcode_correction()
+    gw.barcode_correction()
+    gw.align_and_count(annotate_reads=True)
+    helpers.compare_all(o, gw, prob)
+    gw.barcode_correction()      # and once more after the count stage
+    gw.align_and_count(annotate_reads=True)
+    helpers.compare_all(o, gw, prob)
+    gw.close()
+
+
 def test_feature_barcode_library_matches_oracle():
     prob = helpers.make_problem("cfg4", 200_000, n_whitelist=100_000, n_cells=200)
     assert prob["n_fb"] > 0
