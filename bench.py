@@ -135,6 +135,158 @@ def cpu_oracle_rate(cfg, tables, sample_reads: int, threads: int, steps: int = 1
     return sample_reads / float(np.mean(times)), float(np.mean(times)), st
 
 
+def csc_fingerprint(m, n_molecules: int) -> dict:
+    """Order-independent 64-bit fingerprint of a (part of a) count matrix: a wrapping sum over the entries of a
+    mix of (barcode content rank, feature, count), plus one over the barcode index. A barcode-owner sharded run
+    is a partition of the single-GPU run, so the per-rank values add up (mod 2^64) to the single-GPU ones."""
+    from cellranger_b200.synth import splitmix64
+
+    cols = np.repeat(m.barcode_rank.astype(np.uint64), np.diff(m.indptr))
+    with np.errstate(over="ignore"):
+        e = splitmix64((cols << np.uint64(32)) | m.indices.astype(np.uint64)) * \
+            (np.uint64(2) * m.data.astype(np.uint64) + np.uint64(1))
+        h_entries = int(e.sum(dtype=np.uint64))
+        h_barcodes = int(splitmix64(m.barcode_rank.astype(np.uint64) ^ np.uint64(0xB5AD4ECEDA1CE2A9)).sum(dtype=np.uint64))
+    return {"entries": h_entries, "barcode_index": h_barcodes, "nnz": int(m.data.shape[0]),
+            "n_barcodes": int(m.barcode_rank.shape[0]), "umis": int(m.data.sum(dtype=np.int64)),
+            "molecules": int(n_molecules)}
+
+
+def combine_fingerprints(parts) -> dict:
+    out = {k: 0 for k in parts[0]}
+    for p in parts:
+        for k, v in p.items():
+            out[k] = (out[k] + v) & ((1 << 64) - 1)
+    return {"csc_hash": f"{out['entries']:016x}{out['barcode_index']:016x}", "nnz": out["nnz"],
+            "n_barcodes": out["n_barcodes"], "umis": out["umis"], "molecules": out["molecules"]}
+
+
+class _DevBytes:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def parity_at_scale(gw, lib, cfg, tables, reads_dev, n_reads, n_targets=200, check_molecules=True, threads=None):
+    """Bit-exact check of single output values at the full bench size. ~n_targets barcodes (cells and ambient)
+    are drawn; every read of the batch whose raw barcode is one of them, one of their 48 Hamming-1 neighbours,
+    or holds a non-ACGT base - a superset of the reads any of them can receive - goes through the CPU oracle
+    with the GPU's GLOBAL priors pushed in (the posterior of a read depends on the priors of all its whitelist
+    neighbours, Posterior::correct_barcode, barcode/src/corrector.rs:125-162). The oracle's matrix columns and
+    molecule rows of the drawn barcodes must equal the GPU's; the priors of the drawn barcodes are recounted
+    from the raw reads. The reads are selected with torch ops on the device arrays (checker plumbing)."""
+    import torch
+
+    from cellranger_b200 import synth
+    from oracle import cro
+
+    t0 = time.perf_counter()
+    dev = torch.device("cuda", gw.device)
+    m = gw.count_matrix()
+    rng = np.random.default_rng(20240607)
+    cells = np.unique(np.asarray(tables.cell_rank, dtype=np.int64))
+    cells = cells[np.isin(cells, m.barcode_rank)]
+    pick_cells = cells[np.linspace(0, len(cells) - 1, min(n_targets // 2, len(cells))).astype(np.int64)]
+    others = m.barcode_rank[~np.isin(m.barcode_rank, cells)].astype(np.int64)
+    pick_amb = rng.choice(others, size=min(n_targets - len(pick_cells), len(others)), replace=False)
+    targets = np.unique(np.concatenate([pick_cells, pick_amb]))
+    t_seq = gw.barcode_seqs(targets.astype(np.uint32))
+    t_packed = synth.pack_2bit(t_seq)
+    L = cfg.bc_len
+    near = [t_packed]
+    for pos in range(L):
+        sh = np.uint64(2 * (L - 1 - pos))
+        for b in range(4):
+            near.append((t_packed & ~(np.uint64(3) << sh)) | (np.uint64(b) << sh))
+    near = torch.as_tensor(np.unique(np.concatenate(near)).astype(np.int64), device=dev)
+    r1_len = cfg.r1_len
+    seq = torch.as_tensor(_DevBytes(reads_dev.r1_seq, n_reads * r1_len, "|u1"), device=dev).view(n_reads, r1_len)
+    qual = torch.as_tensor(_DevBytes(reads_dev.r1_qual, n_reads * r1_len, "|u1"), device=dev).view(n_reads, r1_len)
+    feat = torch.as_tensor(_DevBytes(reads_dev.feature, n_reads, "<i4"), device=dev)
+    lut = torch.full((256,), 4, dtype=torch.int64, device=dev)
+    for ch, v in zip(b"ACGT", range(4)):
+        lut[ch] = v
+    shifts = (torch.arange(L - 1, -1, -1, device=dev, dtype=torch.int64) * 2)
+    picked = []
+    step = 8_000_000
+    for lo in range(0, n_reads, step):
+        codes = lut[seq[lo:lo + step, :L].long()]
+        has_n = (codes == 4).any(dim=1)
+        packed = ((codes & 3) << shifts).sum(dim=1)
+        sel = torch.isin(packed, near) | has_n
+        picked.append(sel.nonzero(as_tuple=False).flatten() + lo)
+        del codes, packed, sel, has_n
+    idx = torch.cat(picked)
+    sub_seq = seq[idx].cpu().numpy()
+    sub_qual = qual[idx].cpu().numpy()
+    sub_feat = feat[idx].cpu().numpy().view(np.uint32)
+    n_sub = int(idx.numel())
+    del idx, picked
+    torch.cuda.empty_cache()
+    t_select = time.perf_counter() - t0
+
+    threads = threads or (os.cpu_count() or 1)
+    o = cro.Oracle()
+    wl = o.add_whitelist(tables.whitelist)
+    olib = o.add_library(wl, 0, cfg.bc_len, cfg.bc_len, cfg.umi_len)
+    o.set_features(np.zeros(cfg.n_genes, dtype=np.int32))
+    o.add_reads(olib, sub_seq, sub_qual, sub_feat)
+    o.pass1(threads)
+    # the priors of the drawn barcodes, recounted from the raw reads: every exact read of a target is in the subset
+    prior_gpu = gw.prior(lib)
+    prior_sub = o.counts(olib, 0, t_seq)
+    priors_equal = bool(np.array_equal(prior_sub, prior_gpu[targets].astype(np.int64)))
+    # ... then the GLOBAL priors (all 200 M reads) replace the subset's
+    nz = np.flatnonzero(prior_gpu)
+    o.prior_clear(olib)
+    o.prior_add(olib, gw.barcode_seqs(nz.astype(np.uint32)), prior_gpu[nz].astype(np.int64))
+    o.pass2(threads)
+    o.count(threads)
+    mo = o.matrix()
+    col_o = {bytes(b): i for i, b in enumerate(mo["barcodes"])}
+    col_g = np.searchsorted(m.barcode_rank, targets)
+    cols_ok, cols_bad, entries = 0, [], 0
+    for t, s_, cg in zip(targets, t_seq, col_g):
+        in_g = cg < len(m.barcode_rank) and m.barcode_rank[cg] == t
+        co = col_o.get(bytes(s_))
+        if not in_g or co is None:
+            ok = (not in_g) and co is None
+        else:
+            a0, a1 = m.indptr[cg], m.indptr[cg + 1]
+            b0, b1 = mo["indptr"][co], mo["indptr"][co + 1]
+            ok = np.array_equal(m.indices[a0:a1], mo["indices"][b0:b1]) and np.array_equal(m.data[a0:a1], mo["data"][b0:b1])
+            entries += int(a1 - a0)
+        cols_ok += bool(ok)
+        if not ok:
+            cols_bad.append(int(t))
+    mol_equal = None
+    n_mol_rows = 0
+    if check_molecules:
+        mg = gw.molecules()                       # (column, library, feature, umi, read_count)
+        keep = np.isin(mg[:, 0], col_g.astype(np.uint32))
+        mg = mg[keep]
+        mg[:, 0] = targets[np.searchsorted(col_g, mg[:, 0])]   # column -> content rank
+        ma = o.molecules()
+        rank_of_col = np.full(len(mo["barcodes"]), -1, dtype=np.int64)
+        for t, s_ in zip(targets, t_seq):
+            co = col_o.get(bytes(s_))
+            if co is not None:
+                rank_of_col[co] = t
+        ra = rank_of_col[ma[:, 0].astype(np.int64)]
+        ma = ma[ra >= 0].astype(np.int64)
+        ma[:, 0] = ra[ra >= 0]
+        mg = mg.astype(np.int64)
+        ka = np.lexsort((ma[:, 4], ma[:, 3], ma[:, 2], ma[:, 1], ma[:, 0]))
+        kg = np.lexsort((mg[:, 4], mg[:, 3], mg[:, 2], mg[:, 1], mg[:, 0]))
+        mol_equal = bool(ma.shape == mg.shape and np.array_equal(ma[ka], mg[kg]))
+        n_mol_rows = int(mg.shape[0])
+    o.close()
+    return {"barcodes_checked": int(len(targets)), "cells": int(len(pick_cells)), "reads_through_oracle": n_sub,
+            "columns_equal": cols_ok == len(targets), "columns_ok": cols_ok, "columns_bad": cols_bad[:8],
+            "entries_checked": entries, "priors_equal": priors_equal, "molecule_rows_equal": mol_equal,
+            "molecule_rows_checked": n_mol_rows, "seconds": round(time.perf_counter() - t0, 1),
+            "select_seconds": round(t_select, 1)}
+
+
 def run_reference(args):
     """The reference arm: the reference's algorithm for this path on the host cores. The Rust crates cannot
     be compiled in this image (no cargo/rustc), so this is the C++ port in oracle/ (kind = "port")."""
@@ -202,10 +354,25 @@ def run_ours(args):
     libs = setup_problem(gw, cfg, tables)
     reads_dev = synth_device.generate_device(gw, tables, rank * n_per, n_per, "gex")
     ext = torch.cuda.ExternalStream(gw.stream(), device=dev)
-    engine = crdist.TorchEngine(gw, len(libs))
-    if world > 1 and not os.environ.get("CRGPU_NO_P2P"):
-        engine.setup_peer_exchange(rank, world, capacity_keys=int(n_per * 1.25))
-    sharded = crdist.ShardedGemWell(engine, rank, world)
+    sharded = None
+    exchange = "none (one GPU)"
+    if world > 1:
+        if os.environ.get("CRGPU_NO_P2P") or os.environ.get("CRGPU_TORCH_DIST"):
+            # the engine protocol of dist.py with torch.distributed collectives (second implementation; the
+            # NCCL all-to-all route when CRGPU_NO_P2P is set)
+            engine = crdist.TorchEngine(gw, len(libs))
+            if not os.environ.get("CRGPU_NO_P2P"):
+                engine.setup_peer_exchange(rank, world, capacity_keys=int(n_per * 1.25))
+            sharded = crdist.ShardedGemWell(engine, rank, world)
+            exchange = "torch.distributed all-reduces + " + ("peer stores" if engine.p2p else "NCCL all_to_all_single")
+        else:
+            # the product path: the whole step inside libcrgpu.so (crgpu_sharded_run); torch only carries the
+            # communicator id to the ranks and the timing reduction
+            box = [cb.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            sharded = crdist.NativeShardedGemWell(gw, rank, world, box[0], capacity_keys=int(n_per * 1.25))
+            exchange = "crgpu_sharded_run: in-library NCCL all-reduces, device owner ranges, NVLink peer stores" + \
+                       (", early scatter" if os.environ.get("CRGPU_EARLY_SCATTER") else "")
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -244,7 +411,7 @@ def run_ours(args):
     launches = (stats["kernel_launches"] - launches0) // max(args.steps, 1)
     value = n_total / (ms * 1e-3)
 
-    if world > 1 and sharded.timing and rank == 0:
+    if world > 1 and getattr(sharded, "timing", False) and rank == 0:
         n_runs = args.warmup + args.steps
         print("dist phases (ms/step, host clock, rank 0): " +
               " ".join(f"{k}={v / n_runs:.2f}" for k, v in sharded.times.items()), file=sys.stderr)
@@ -252,6 +419,42 @@ def run_ours(args):
     step_device()
     phases = gw.phase_times()
     n_keys, n_distinct = stats["keys"], stats["distinct_keys"]
+
+    # ---------------- what was computed: fingerprint, and single values checked against the oracle ----------------
+    def fingerprint():
+        fp = csc_fingerprint(gw.count_matrix(), gw.stats()["molecules"])
+        if dist is None:
+            return combine_fingerprints([fp])
+        parts = [None] * world
+        dist.all_gather_object(parts, fp)
+        return combine_fingerprints(parts)
+
+    result_fp = fingerprint()
+    scale_check = None
+    if world == 1 and not args.no_scale_check:
+        try:
+            scale_check = parity_at_scale(gw, libs[0], cfg, tables, reads_dev, n_per, n_targets=args.scale_check_barcodes)
+        except Exception as e:  # the check must never take the measurement down with it
+            scale_check = {"error": f"{type(e).__name__}: {e}"}
+    # Strong-scaling identity: the 200 M reads of cfg2 (the N=1 workload) split N ways give the matrix of N=1 -
+    # equal fingerprints on the N=1, 2, 4, 8 lines (columns concatenate by owner range, as the reference's chunk
+    # outputs do: barcode_correction.rs:252-262, align_and_count.rs:519-524)
+    identity = None
+    if world == 1:
+        identity = dict(result_fp, workload=f"cfg2, {n_per} reads on 1 GPU (this run)")
+    elif not args.no_identity:
+        n_id = args.reads
+        cfg2 = synth.preset("cfg2", n_id)
+        tables2 = synth.make_tables(cfg2, n_id)
+        lo, hi = (n_id * rank) // world, (n_id * (rank + 1)) // world
+        gw.clear_reads()
+        id_reads = synth_device.generate_device(gw, tables2, lo, hi - lo, "gex")
+        gw.add_reads_device(libs[0], hi - lo, cfg2.r1_len, id_reads.r1_seq, id_reads.r1_qual, id_reads.feature)
+        step_device()
+        identity = dict(fingerprint(), workload=f"cfg2, {n_id} reads split over {world} GPUs")
+        gw.clear_reads()
+        id_reads.close()
+        gw.add_reads_device(libs[0], n_per, cfg.r1_len, reads_dev.r1_seq, reads_dev.r1_qual, reads_dev.feature)
 
     # ---------------- end to end through the public API with host buffers (e2e) ----------------
     e2e = None
@@ -356,6 +559,7 @@ def run_ours(args):
         "phases_ms": phases, "path_hbm_frac": path_frac,
         "counts": {k: stats[k] for k in ("reads", "valid_before", "corrected", "invalid", "keys", "distinct_keys",
                                          "molecules", "nnz", "barcodes")},
+        "result": result_fp, "parity_at_scale": scale_check, "strong_identity": identity, "exchange": exchange,
     }
     print(json.dumps(line))
     gw.close()
@@ -375,6 +579,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-scale-check", action="store_true", help="skip the sampled-barcode oracle check at N=1")
+    ap.add_argument("--scale-check-barcodes", type=int, default=200)
+    ap.add_argument("--no-identity", action="store_true", help="skip the strong-scaling identity run at N>1")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 0)

@@ -202,6 +202,14 @@ class CountMatrix:
         return [f"{int(f) + 1} {int(c) + 1} {int(v)}" for f, c, v in zip(self.indices, cols, self.data)]
 
 
+def comm_unique_id() -> bytes:
+    """128 bytes that identify a new communicator (crgpu_comm_unique_id): rank 0 makes it, every rank gets it."""
+    L = _lib.load()
+    buf = (C.c_uint8 * 128)()
+    check(L.crgpu_comm_unique_id(buf), "crgpu_comm_unique_id")
+    return bytes(buf)
+
+
 class GemWell:
     """One GEM well on one GPU: whitelist tables, library types, read batches and the three stages."""
 
@@ -487,6 +495,37 @@ class GemWell:
         n = C.c_uint64()
         check(self.L.crgpu_exchange_finish(self._ctx, C.byref(n)), "crgpu_exchange_finish")
         return int(n.value)
+
+    # ---- the sharded run inside the library (NCCL communicator, device owner ranges, fused exchange) ----
+    def comm_init(self, unique_id: bytes, n_ranks: int, rank: int, exchange_capacity_keys: int):
+        """Collective over the ranks (one process per GPU): joins the communicator created from `unique_id`
+        (comm_unique_id() on rank 0, handed to every rank by the host) and maps every rank's receive buffer."""
+        buf = (C.c_uint8 * len(unique_id)).from_buffer_copy(unique_id)
+        check(self.L.crgpu_comm_init(self._ctx, buf, int(n_ranks), int(rank), C.c_uint64(int(exchange_capacity_keys))),
+              "crgpu_comm_init")
+
+    def sharded_run(self):
+        """One step of the sharded path, collective: pass 1, all-reduce of the priors, pass 2, all-reduce of the
+        corrected counts, owner ranges, key exchange over peer memory, count on the owned barcode range."""
+        check(self.L.crgpu_sharded_run(self._ctx), "crgpu_sharded_run")
+
+    def owner_bounds(self) -> np.ndarray:
+        out = np.zeros(17, dtype=np.uint32)
+        check(self.L.crgpu_owner_bounds_get(self._ctx, ptr(out), 17), "crgpu_owner_bounds_get")
+        return out[: self.shard_stats()["n_ranks"] + 1]
+
+    def shard_stats(self) -> dict:
+        out = (C.c_uint64 * 4)()
+        check(self.L.crgpu_shard_stats(self._ctx, out))
+        return {"sent_remote_keys": int(out[0]), "received_keys": int(out[1]), "n_ranks": int(out[2]), "rank": int(out[3])}
+
+    def owner_bounds_compute(self, counts, n_parts: int) -> np.ndarray:
+        """Owner ranges for a vector of per-rank read counts, with the device arithmetic of the sharded run."""
+        c = np.ascontiguousarray(counts, dtype=np.uint32)
+        out = np.zeros(n_parts + 1, dtype=np.uint32)
+        check(self.L.crgpu_owner_bounds_compute(self._ctx, ptr(c), C.c_uint64(c.shape[0]), int(n_parts), ptr(out)),
+              "crgpu_owner_bounds_compute")
+        return out
 
     def set_owned_range(self, lo: int, hi: int):
         check(self.L.crgpu_set_owned_range(self._ctx, C.c_uint32(lo), C.c_uint32(hi)))

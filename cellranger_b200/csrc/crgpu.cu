@@ -8,181 +8,20 @@
 #include <string>
 #include <vector>
 
-#include "../../include/crgpu.h"
-#include "kernels.h"
+#include "ctx.h"
 
 void launch_split_counter(unsigned long long* packed, unsigned long long* keys_total, unsigned long long* inv_total,
                           cudaStream_t st);
 void launch_merge_counter(unsigned long long* packed, const unsigned long long* keys_total, cudaStream_t st);
 
-namespace {
-
-thread_local std::string g_err;
+static thread_local std::string g_err;
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
 
-#define CU(call)                                                                                          \
-  do {                                                                                                    \
-    cudaError_t e__ = (call);                                                                             \
-    if (e__ != cudaSuccess)                                                                               \
-      return fail(CRGPU_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" + \
-                                    std::to_string(__LINE__) + ")");                                      \
-  } while (0)
-
-#define CHECK_KERNEL()                      \
-  do {                                      \
-    cudaError_t e__ = cudaPeekAtLastError(); \
-    if (e__ != cudaSuccess) return fail(CRGPU_E_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e__)); \
-  } while (0)
-
-// grow-only device buffer
-struct DevBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-  int ensure(size_t bytes) {
-    if (bytes <= cap) return CRGPU_OK;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    size_t want = bytes + bytes / 16 + 256;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) {
-      p = nullptr;
-      return fail(CRGPU_E_NOMEM, std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e));
-    }
-    cap = want;
-    return CRGPU_OK;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
-  template <typename T>
-  T* as() const {
-    return static_cast<T*>(p);
-  }
-};
-
-struct HostWhitelist {
-  int L = 0;
-  uint32_t W = 0;
-  bool is_trans = false;
-  DevWhitelist dev;
-  std::vector<DevBuf> bufs;
-};
-
-struct Library {
-  crgpu_library_def def;
-  DevBuf prior, corrected, valid;  // u32[n_content]
-  // feature-barcode table
-  std::vector<uint32_t> fb_keys, fb_index;
-  DevBuf d_fb_keys, d_fb_index;
-};
-
-struct Batch {
-  int lib = 0;
-  uint64_t n = 0;
-  int r1_len = 0, r2_len = 0;
-  bool on_device = false;
-  const uint8_t *r1_seq = nullptr, *r1_qual = nullptr, *r2_seq = nullptr, *r2_qual = nullptr;
-  const uint32_t* feature = nullptr;  // device pointers (borrowed or owned)
-  DevBuf own_seq, own_qual, own_feat, own_r2s, own_r2q;
-  DevBuf feature_res;  // resolved features of a feature-barcode batch
-  DevBuf inv_idx, inv_bc, inv_nmask, inv_qual;
-  uint64_t n_invalid = 0;
-  uint64_t base = 0;
-};
-
-// fixed slots at the end of the 1024-word counter block
-constexpr int CTR_KEYS_PASS1 = 1022;   // keys_total as pass 1 left it (pass 2 restarts from here when re-run)
-constexpr int CTR_BAD_FEATURE = 1023;  // reads whose feature index has no row in the matrix
-
-int bits_for(uint64_t n_values) {  // bits to hold values 0..n_values-1
-  int b = 0;
-  while (b < 63 && (1ull << b) < n_values) b++;
-  return b;
-}
-
-}  // namespace
-
-struct crgpu_ctx {
-  int device = 0;
-  int n_sms = 148;
-  cudaStream_t stream = nullptr;
-  double threshold = 0.975;
-  double max_expected_errors = 1.7976931348623157e308;
-  int filter_umis = 1;
-
-  // content space
-  int L = 0;
-  std::vector<uint32_t> content;  // sorted packed content sequences
-  std::vector<HostWhitelist*> wls;
-  std::vector<Library*> libs;
-  int n_features = 0;
-  std::vector<int32_t> feature_type;
-  std::vector<uint8_t> fb_seqs;
-  int fb_stride = 0;
-  bool have_fb = false;
-  DevBuf d_fb_counts, d_feat_dist;
-
-  std::vector<Batch*> batches;
-  std::vector<Batch*> batch_pool;  // retired batches whose device buffers are reused
-  uint64_t n_reads = 0;
-
-  KeyLayout kl{};
-  bool layout_ready = false;
-  int stage = 0;  // 0 nothing, 1 pass1 done, 2 pass2 done, 3 count done
-
-  DevBuf bc_out, umi_out, umi_proc, flags;
-  DevBuf keys, keys_alt, sort_temp;
-  DevBuf counters;  // [0] packed scratch, [1] keys_total, [2..] per-batch invalid totals, [CTR_*] below
-  unsigned long long* sorted = nullptr;
-  uint64_t n_keys = 0;
-  bool keys_external = false;
-  unsigned long long* key_src = nullptr;  // where crgpu_count finds the keys (nullptr = the keys buffer)
-
-  // dedup
-  DevBuf dkeys, c0, best, inc, low, key2, key2_alt, lb_desc, tickets, scalars, ent_rank, ent_feature, ent_count, mol;
-  DevBuf col_of_rank, barcode_rank, indptr, mol_rows, min_read, rep_raw, ls_slots, summary, fastq_text, fastq_tmp;
-  uint64_t n_distinct = 0, n_mol = 0, nnz = 0, n_barcodes = 0;
-  uint32_t own_lo = 0, own_hi = 0xFFFFFFFFu;
-  bool annotated = false;
-
-  // fused exchange over peer memory
-  void* xchg_buf = nullptr;     // this rank's receive buffer (cudaMalloc, exported through CUDA IPC)
-  void* xchg_cursor = nullptr;  // u64[2]: keys received, overflow flag
-  uint64_t xchg_capacity = 0;
-  int xchg_ranks = 0, xchg_rank = -1;
-  unsigned long long* peer_buf[CRGPU_MAX_PARTS] = {nullptr};
-  unsigned long long* peer_cursor[CRGPU_MAX_PARTS] = {nullptr};
-  bool peer_opened[CRGPU_MAX_PARTS] = {false};
-  // early part of the exchange (keys of pass 1, sent on a second stream while pass 2 runs)
-  cudaStream_t xchg_stream = nullptr;
-  cudaEvent_t xchg_ready = nullptr, xchg_done = nullptr;
-  bool xchg_early = false;
-  uint64_t xchg_early_keys = 0;
-  uint32_t xchg_early_bounds[CRGPU_MAX_PARTS + 1] = {0};
-
-  uint64_t stats[CRGPU_STAT_COUNT] = {0};
-  uint64_t launches = 0;
-
-  // phase timing (events come from a pool: none is created or destroyed in the steady state)
-  std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> phases;
-  std::vector<cudaEvent_t> event_pool;
-  std::string phase_names;
-
-  // scratch of crgpu_correct_barcodes (grow-only, so that the plugin seam allocates nothing per call)
-  DevBuf cb_seq, cb_qual, cb_bc, cb_umi, cb_keys, cb_ctr, cb_idx, cb_ibc, cb_inm, cb_iq;
-  std::vector<uint32_t> cb_host;
-};
-
-namespace {
-
-int phase_event(crgpu_ctx* c, cudaEvent_t* e) {
+static int phase_event(crgpu_ctx* c, cudaEvent_t* e) {
   if (!c->event_pool.empty()) {
     *e = c->event_pool.back();
     c->event_pool.pop_back();
@@ -217,6 +56,8 @@ void phases_clear(crgpu_ctx* c, const char* prefix) {
   }
   c->phases.swap(keep);
 }
+
+namespace {
 
 bool pack_ascii(const uint8_t* s, int L, uint32_t* out) {
   uint32_t r = 0;
@@ -378,6 +219,7 @@ void crgpu_ctx_destroy(crgpu_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  shard_release(c);
   auto free_batch = [](Batch* b) {
     b->own_seq.release(); b->own_qual.release(); b->own_feat.release(); b->own_r2s.release(); b->own_r2q.release();
     b->feature_res.release(); b->inv_idx.release(); b->inv_bc.release(); b->inv_nmask.release(); b->inv_qual.release();
@@ -414,6 +256,9 @@ void crgpu_ctx_destroy(crgpu_ctx* c) {
       cudaIpcCloseMemHandle(c->peer_buf[r]);
       cudaIpcCloseMemHandle(c->peer_cursor[r]);
     }
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (auto e : c->copy_ev)
+    if (e) cudaEventDestroy(e);
   if (c->xchg_stream) cudaStreamDestroy(c->xchg_stream);
   if (c->xchg_ready) cudaEventDestroy(c->xchg_ready);
   if (c->xchg_done) cudaEventDestroy(c->xchg_done);
@@ -666,6 +511,7 @@ int crgpu_reads_add(crgpu_ctx* c, int lib, const crgpu_read_batch* rb, int* out_
   b->r1_len = rb->r1_len;
   b->r2_len = d.is_feature_barcode ? rb->r2_len : 0;
   b->on_device = rb->on_device != 0;
+  b->host_pending = false;
   b->base = c->n_reads;
   b->n_invalid = 0;
   if (b->on_device) {
@@ -683,28 +529,32 @@ int crgpu_reads_add(crgpu_ctx* c, int lib, const crgpu_read_batch* rb, int* out_
     c->batch_pool.push_back(b);      \
     return rc;                       \
   }
+    // device copies are allocated now; the bytes cross in crgpu_pass1, chunk by chunk under the kernels
     ENSURE_OR_RETURN(b->own_seq.ensure(sb + 16));
     ENSURE_OR_RETURN(b->own_qual.ensure(sb + 16));
-    CU(cudaMemcpyAsync(b->own_seq.p, rb->r1_seq, sb, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(b->own_qual.p, rb->r1_qual, sb, cudaMemcpyHostToDevice, c->stream));
     b->r1_seq = b->own_seq.as<uint8_t>();
     b->r1_qual = b->own_qual.as<uint8_t>();
+    b->h_r1_seq = rb->r1_seq;
+    b->h_r1_qual = rb->r1_qual;
     b->feature = nullptr;
+    b->h_feature = nullptr;
     b->r2_seq = b->r2_qual = nullptr;
+    b->h_r2_seq = b->h_r2_qual = nullptr;
     if (!d.is_feature_barcode) {
       ENSURE_OR_RETURN(b->own_feat.ensure((size_t)rb->n * 4 + 16));
-      CU(cudaMemcpyAsync(b->own_feat.p, rb->feature, (size_t)rb->n * 4, cudaMemcpyHostToDevice, c->stream));
       b->feature = b->own_feat.as<uint32_t>();
+      b->h_feature = rb->feature;
     } else {
       size_t rb2 = (size_t)rb->n * rb->r2_len;
       ENSURE_OR_RETURN(b->own_r2s.ensure(rb2 + 16));
       ENSURE_OR_RETURN(b->own_r2q.ensure(rb2 + 16));
-#undef ENSURE_OR_RETURN
-      CU(cudaMemcpyAsync(b->own_r2s.p, rb->r2_seq, rb2, cudaMemcpyHostToDevice, c->stream));
-      CU(cudaMemcpyAsync(b->own_r2q.p, rb->r2_qual, rb2, cudaMemcpyHostToDevice, c->stream));
       b->r2_seq = b->own_r2s.as<uint8_t>();
       b->r2_qual = b->own_r2q.as<uint8_t>();
+      b->h_r2_seq = rb->r2_seq;
+      b->h_r2_qual = rb->r2_qual;
     }
+#undef ENSURE_OR_RETURN
+    b->host_pending = rb->n > 0;
   }
   c->n_reads += rb->n;
   c->batches.push_back(b);
@@ -830,7 +680,57 @@ int crgpu_pass1(crgpu_ctx* c) {
     a.n_features = (uint32_t)c->n_features;
     a.bad_feature = ctr + CTR_BAD_FEATURE;
     launch_merge_counter(ctr, ctr + 1, c->stream);
-    c->launches += 1 + launch_pass1(a, c->n_sms, c->stream);
+    c->launches += 1;
+    if (!b->host_pending) {
+      c->launches += launch_pass1(a, c->n_sms, c->stream);
+    } else {
+      // A host batch crosses PCIe here, in chunks on the copy stream; the pass-1 kernel of a chunk waits for its
+      // event only, so all but the last chunk's kernel run under the copies that follow. The copy of the whole
+      // batch is what bounds an end-to-end step (12 GB at ~55 GB/s for 200 M reads); the kernels hide behind it.
+      if (!c->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->copy_ev[0], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->copy_ev[1], cudaEventDisableTiming));
+      }
+      uint64_t chunk = getenv("CRGPU_H2D_CHUNK") ? strtoull(getenv("CRGPU_H2D_CHUNK"), nullptr, 10) : (4ull << 20);
+      chunk = std::max<uint64_t>(4096, chunk & ~4095ull);  // keeps every chunk 16-byte aligned for any read length
+      // the device buffers were last read by kernels of the context stream (an earlier step): order the copies
+      // behind them
+      CU(cudaEventRecord(c->copy_ev[0], c->stream));
+      CU(cudaStreamWaitEvent(c->copy_stream, c->copy_ev[0], 0));
+      const bool is_fb = l->def.is_feature_barcode != 0;
+      if (is_fb) {
+        const size_t rb2 = (size_t)b->n * b->r2_len;
+        CU(cudaMemcpyAsync(b->own_r2s.p, b->h_r2_seq, rb2, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaMemcpyAsync(b->own_r2q.p, b->h_r2_qual, rb2, cudaMemcpyHostToDevice, c->copy_stream));
+      }
+      int k = 0;
+      for (uint64_t first = 0; first < b->n; first += chunk, k++) {
+        const uint64_t cn = std::min<uint64_t>(chunk, b->n - first);
+        const size_t off = (size_t)first * b->r1_len, bytes = (size_t)cn * b->r1_len;
+        CU(cudaMemcpyAsync(b->own_seq.as<uint8_t>() + off, b->h_r1_seq + off, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaMemcpyAsync(b->own_qual.as<uint8_t>() + off, b->h_r1_qual + off, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        if (!is_fb)
+          CU(cudaMemcpyAsync(b->own_feat.as<uint32_t>() + first, b->h_feature + first, (size_t)cn * 4,
+                             cudaMemcpyHostToDevice, c->copy_stream));
+        cudaEvent_t ev = c->copy_ev[k & 1];
+        CU(cudaEventRecord(ev, c->copy_stream));
+        CU(cudaStreamWaitEvent(c->stream, ev, 0));
+        Pass1Args ac = a;
+        ac.n = cn;
+        ac.idx_base = first;
+        ac.seq = a.seq + off;
+        ac.qual = a.qual + off;
+        ac.feature = a.feature ? a.feature + first : nullptr;
+        ac.bc_out = a.bc_out + first;
+        ac.umi_out = a.umi_out + first;
+        c->launches += launch_pass1(ac, c->n_sms, c->stream);
+        CHECK_KERNEL();
+      }
+      // the caller's buffers have been read once this returns (the contract of crgpu_reads_add)
+      CU(cudaStreamSynchronize(c->copy_stream));
+      b->host_pending = false;
+    }
     launch_split_counter(ctr, ctr + 1, ctr + 2 + bi, c->stream);
     c->launches += 1;
     CHECK_KERNEL();

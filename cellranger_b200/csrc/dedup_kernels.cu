@@ -921,10 +921,9 @@ struct PeerTargets {
   unsigned long long capacity;
 };
 
-__global__ void __launch_bounds__(PX_THREADS) owner_scatter_peers_kernel(const unsigned long long* __restrict__ keys,
-                                                                        uint64_t n, int rank_shift, OwnerBounds ob,
-                                                                        PeerTargets pt,
-                                                                        unsigned long long* __restrict__ sent) {
+__device__ __forceinline__ void owner_scatter_peers_body(const unsigned long long* __restrict__ keys, uint64_t n,
+                                                         int rank_shift, const OwnerBounds& ob, const PeerTargets& pt,
+                                                         unsigned long long* __restrict__ sent) {
   __shared__ unsigned long long s_keys[PX_CHUNK];
   __shared__ uint32_t s_cnt[CRGPU_MAX_PARTS], s_off[CRGPU_MAX_PARTS + 1], s_fill[CRGPU_MAX_PARTS];
   __shared__ unsigned long long s_base[CRGPU_MAX_PARTS];
@@ -991,6 +990,31 @@ __global__ void __launch_bounds__(PX_THREADS) owner_scatter_peers_kernel(const u
     }
     __syncthreads();
   }
+  // the keys were stored into other GPUs' memory: make them visible system-wide before the kernel retires (the
+  // owners read them after a cross-rank barrier that is ordered behind this kernel)
+  __threadfence_system();
+}
+
+__global__ void __launch_bounds__(PX_THREADS) owner_scatter_peers_kernel(const unsigned long long* __restrict__ keys,
+                                                                        uint64_t n, int rank_shift, OwnerBounds ob,
+                                                                        PeerTargets pt,
+                                                                        unsigned long long* __restrict__ sent) {
+  owner_scatter_peers_body(keys, n, rank_shift, ob, pt, sent);
+}
+
+// The same with everything that used to need the host read on the device: the key range [*begin_dev, *end_dev)
+// (begin_dev may be null = 0) and the owner bounds, so that the sharded step enqueues it without a round trip.
+__global__ void __launch_bounds__(PX_THREADS) owner_scatter_peers_dev_kernel(
+    const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ begin_dev,
+    const unsigned long long* __restrict__ end_dev, int rank_shift, const uint32_t* __restrict__ bounds_dev, int n_parts,
+    PeerTargets pt, unsigned long long* __restrict__ sent) {
+  __shared__ OwnerBounds ob;
+  if (threadIdx.x <= CRGPU_MAX_PARTS) ob.b[threadIdx.x] = threadIdx.x <= n_parts ? bounds_dev[threadIdx.x] : 0xFFFFFFFFu;
+  if (threadIdx.x == 0) ob.n = n_parts;
+  __syncthreads();
+  const unsigned long long first = begin_dev ? *begin_dev : 0ull;
+  const unsigned long long last = *end_dev;
+  owner_scatter_peers_body(keys + first, last > first ? last - first : 0ull, rank_shift, ob, pt, sent);
 }
 
 int run_owner_scatter_peers(const unsigned long long* keys, uint64_t n, int rank_shift, const uint32_t* bounds,
@@ -1012,6 +1036,151 @@ int run_owner_scatter_peers(const unsigned long long* keys, uint64_t n, int rank
   owner_scatter_peers_kernel<<<grid, PX_THREADS, 0, st>>>(keys, n, rank_shift, ob, pt, d_sent);
   return 1;
 }
+
+int run_owner_scatter_peers_dev(const unsigned long long* keys, const unsigned long long* begin_dev,
+                                const unsigned long long* end_dev, uint64_t n_max, int rank_shift,
+                                const uint32_t* bounds_dev, int n_parts, unsigned long long* const* peer_buf,
+                                unsigned long long* const* peer_cursor, unsigned long long capacity,
+                                unsigned long long* d_sent, cudaStream_t st) {
+  PeerTargets pt;
+  for (int i = 0; i < CRGPU_MAX_PARTS; i++) {
+    pt.buf[i] = i < n_parts ? peer_buf[i] : nullptr;
+    pt.cursor[i] = i < n_parts ? peer_cursor[i] : nullptr;
+  }
+  pt.capacity = capacity;
+  cudaMemsetAsync(d_sent, 0, CRGPU_MAX_PARTS * 8, st);
+  if (!n_max) return 0;
+  uint64_t chunks = (n_max + PX_CHUNK - 1) / PX_CHUNK;
+  int grid = (int)std::min<uint64_t>(chunks, (uint64_t)sm_count() * 4);
+  owner_scatter_peers_dev_kernel<<<grid, PX_THREADS, 0, st>>>(keys, begin_dev, end_dev, rank_shift, bounds_dev, n_parts,
+                                                             pt, d_sent);
+  return 1;
+}
+
+// ---------------------------------------------------------------------------
+// Owner ranges on the device: contiguous content-rank ranges [bounds[r], bounds[r+1]) holding about equal numbers
+// of valid reads - what ShardReader::make_chunks does for the reference's barcode-range chunks
+// (cr_lib/src/stages/align_and_count.rs:519-524). With csum the inclusive prefix sum of the per-rank totals
+// (summed over the library types) and target_r = (total * r) / G:  bounds[r] = min(first i with csum[i] >=
+// target_r, ...) + 1, made non-decreasing; bounds[0] = 0, bounds[G] = n. Same arithmetic as owner_bounds() in
+// cellranger_b200/dist.py, which the tests compare it with.
+// ---------------------------------------------------------------------------
+constexpr int OB_THREADS = 1024;
+constexpr int OB_PER_THREAD = 32;
+constexpr int OB_CHUNK = OB_THREADS * OB_PER_THREAD;  // 32768 ranks per block
+
+struct CountVectors {
+  const uint32_t* v[CRGPU_MAX_LIBS];
+  int n;
+};
+
+__device__ __forceinline__ unsigned long long ob_block_reduce(unsigned long long x, unsigned long long* s_warp) {
+  for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, d);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = x;
+  __syncthreads();
+  unsigned long long t = 0;
+  for (int w = 0; w < OB_THREADS / 32; w++) t += s_warp[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(OB_THREADS) ob_partial_kernel(CountVectors cv, uint32_t n,
+                                                                unsigned long long* __restrict__ partial) {
+  __shared__ unsigned long long s_warp[OB_THREADS / 32];
+  const uint64_t first = (uint64_t)blockIdx.x * OB_CHUNK + (uint64_t)threadIdx.x * OB_PER_THREAD;
+  unsigned long long sum = 0;
+  for (int k = 0; k < OB_PER_THREAD; k++) {
+    const uint64_t i = first + k;
+    if (i < n)
+      for (int l = 0; l < cv.n; l++) sum += cv.v[l][i];
+  }
+  const unsigned long long tot = ob_block_reduce(sum, s_warp);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(OB_THREADS) ob_cuts_kernel(CountVectors cv, uint32_t n, uint32_t n_chunks,
+                                                             const unsigned long long* __restrict__ partial, int n_parts,
+                                                             uint32_t* __restrict__ bounds) {
+  __shared__ unsigned long long s_warp[OB_THREADS / 32];
+  __shared__ unsigned long long s_total, s_before;
+  __shared__ uint32_t s_chunk, s_cut;
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (uint32_t c = 0; c < n_chunks; c++) t += partial[c];
+    s_total = t;
+  }
+  __syncthreads();
+  uint32_t prev = 0;
+  for (int r = 1; r < n_parts; r++) {
+    const unsigned long long target = (s_total * (unsigned long long)r) / (unsigned long long)n_parts;
+    if (threadIdx.x == 0) {  // the chunk in which the inclusive prefix sum first reaches the target
+      unsigned long long run = 0;
+      uint32_t c = 0;
+      while (c < n_chunks && run + partial[c] < target) run += partial[c++];
+      s_chunk = c;
+      s_before = run;
+      s_cut = 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    uint32_t cut = n;  // no index reaches the target (cannot happen for target <= total): searchsorted returns n
+    if (s_chunk < n_chunks) {
+      const uint64_t first = (uint64_t)s_chunk * OB_CHUNK + (uint64_t)threadIdx.x * OB_PER_THREAD;
+      unsigned long long v[OB_PER_THREAD], sum = 0;
+      for (int k = 0; k < OB_PER_THREAD; k++) {
+        const uint64_t i = first + k;
+        unsigned long long x = 0;
+        if (i < n)
+          for (int l = 0; l < cv.n; l++) x += cv.v[l][i];
+        v[k] = x;
+        sum += x;
+      }
+      // exclusive prefix of the thread sums over the block
+      unsigned long long inc = sum;
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d) inc += o;
+      }
+      __syncthreads();
+      if (lane == 31) s_warp[warp] = inc;
+      __syncthreads();
+      unsigned long long wsum = 0;
+      for (int w = 0; w < warp; w++) wsum += s_warp[w];
+      unsigned long long run = s_before + wsum + inc - sum;
+      for (int k = 0; k < OB_PER_THREAD; k++) {
+        run += v[k];
+        if (first + k < n && run >= target) {
+          atomicMin(&s_cut, (uint32_t)(first + k));
+          break;
+        }
+      }
+      __syncthreads();
+      if (s_cut != 0xFFFFFFFFu) cut = s_cut;
+    }
+    uint32_t b = cut + 1u < n ? cut + 1u : n;  // searchsorted(...) + 1, clamped
+    if (b < prev) b = prev;                    // non-decreasing
+    prev = b;
+    if (threadIdx.x == 0) bounds[r] = b;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    bounds[0] = 0;
+    bounds[n_parts] = n;
+  }
+}
+
+// scratch: ceil(n / OB_CHUNK) u64
+int run_owner_bounds(const uint32_t* const* vectors, int n_vectors, uint32_t n, int n_parts, unsigned long long* scratch,
+                     uint32_t* bounds_dev, cudaStream_t st) {
+  CountVectors cv;
+  cv.n = n_vectors;
+  for (int l = 0; l < CRGPU_MAX_LIBS; l++) cv.v[l] = l < n_vectors ? vectors[l] : nullptr;
+  const uint32_t n_chunks = (uint32_t)(((uint64_t)n + OB_CHUNK - 1) / OB_CHUNK);
+  if (n_chunks) ob_partial_kernel<<<n_chunks, OB_THREADS, 0, st>>>(cv, n, scratch);
+  ob_cuts_kernel<<<1, OB_THREADS, 0, st>>>(cv, n, n_chunks, scratch, n_parts, bounds_dev);
+  return n_chunks ? 2 : 1;
+}
+size_t owner_bounds_scratch_bytes(uint32_t n) { return ((size_t)n / OB_CHUNK + 2) * 8; }
 
 // per-read barcode states of a batch (local statistics; the histograms may hold global counts)
 __global__ void state_counts_kernel(const uint32_t* __restrict__ bc_out, uint64_t n, unsigned long long* out4) {

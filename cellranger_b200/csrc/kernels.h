@@ -3,7 +3,8 @@
 #include "common.cuh"
 
 struct Pass1Args {
-  uint64_t n;
+  uint64_t n;         // reads of this launch: a whole batch, or one chunk of it (seq / qual / feature / bc_out /
+  uint64_t idx_base;  // umi_out then point at the chunk, and idx_base is its first read's index in the batch)
   int r1_len;
   const uint8_t* seq;
   const uint8_t* qual;
@@ -167,6 +168,15 @@ int run_owner_partition(const unsigned long long* keys, uint64_t n, int rank_shi
 int run_owner_scatter_peers(const unsigned long long* keys, uint64_t n, int rank_shift, const uint32_t* bounds,
                             int n_parts, unsigned long long* const* peer_buf, unsigned long long* const* peer_cursor,
                             unsigned long long capacity, unsigned long long* d_sent, cudaStream_t st);
+int run_owner_scatter_peers_dev(const unsigned long long* keys, const unsigned long long* begin_dev,
+                                const unsigned long long* end_dev, uint64_t n_max, int rank_shift,
+                                const uint32_t* bounds_dev, int n_parts, unsigned long long* const* peer_buf,
+                                unsigned long long* const* peer_cursor, unsigned long long capacity,
+                                unsigned long long* d_sent, cudaStream_t st);
+// owner ranges balanced by read count, computed on the device into bounds_dev[n_parts + 1]
+int run_owner_bounds(const uint32_t* const* vectors, int n_vectors, uint32_t n, int n_parts, unsigned long long* scratch,
+                     uint32_t* bounds_dev, cudaStream_t st);
+size_t owner_bounds_scratch_bytes(uint32_t n);
 int launch_state_counts(const uint32_t* bc_out, uint64_t n, unsigned long long* out4, cudaStream_t st);
 
 struct AnnotateArgs {

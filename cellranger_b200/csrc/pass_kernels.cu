@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(THREADS) pass1_staged_kernel(const Pass1Args a
     for (int k = 0; k < RPT; k++) {
       if ((p_flags >> k) & 1u) __stcs(a.keys + kpos++, p_key[k]);
       if ((p_flags >> (8 + k)) & 1u) {
-        a.inv_idx[ipos] = (uint32_t)(p_first + tid + k * THREADS);
+        a.inv_idx[ipos] = (uint32_t)(a.idx_base + p_first + tid + k * THREADS);
         a.inv_bc[ipos] = p_bc[k];
         a.inv_nmask[ipos] = p_nmask[k];
         a.inv_qual[ipos] = p_bcq[k];
@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(256) pass1_generic_kernel(const Pass1Args a) {
       if (res.emit_key) a.keys[(base & 0xFFFFFFFFull) + off_key] = res.key;
       if (res.invalid) {
         uint64_t ipos = (base >> 32) + off_inv;
-        a.inv_idx[ipos] = (uint32_t)gi;
+        a.inv_idx[ipos] = (uint32_t)(a.idx_base + gi);
         a.inv_bc[ipos] = bc;
         a.inv_nmask[ipos] = nmask;
         uint4 qq;
@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(THREADS) match_kernel(const Pass1Args a) {
                 if (bad & (0x80u << (8 * by))) nmask |= 1u << (wd * 4 + by);
             }
           }
-          a.inv_idx[ipos] = (uint32_t)gi;
+          a.inv_idx[ipos] = (uint32_t)(a.idx_base + gi);
           a.inv_bc[ipos] = bc[k];
           a.inv_nmask[ipos] = nmask;
           a.inv_qual[ipos] = load_bytes16_bounded(a.qual + gi * a.r1_len + a.bc_off, (a.n - gi) * a.r1_len - a.bc_off);

@@ -16,8 +16,14 @@ stages/align_and_count.rs:519-524); priors are summed over every chunk in the MA
      access - grouping by owner plus one NCCL all-to-all
   6. dedup + counting, shard-local; the matrix is the concatenation of the ranks' column blocks
 
-`ShardedGemWell` only talks to an *engine* (the GPU GemWell through TorchEngine below); the host
-logic — owner ranges, split sizes, the exchange — is what the world_size-2 gloo tests cover.
+The product path is `NativeShardedGemWell`: every step above happens inside libcrgpu.so
+(`crgpu_comm_init` / `crgpu_sharded_run`, cellranger_b200/csrc/shard.cu) on the context stream - NCCL
+all-reduces, owner ranges from a device scan, peer stores, an on-stream barrier - and this module only calls it.
+
+`ShardedGemWell` is the same protocol written against an abstract *engine*, with torch.distributed doing the
+collectives: the world_size-2 gloo tests on CPU drive it with a CPU reference engine defined in the tests (host logic: owner ranges,
+split sizes, the exchange), the GPU tests drive it through `TorchEngine` as a second, independent implementation
+that the native path must agree with (and as the NCCL all-to-all route for GPUs without peer access).
 """
 from __future__ import annotations
 
@@ -234,3 +240,20 @@ class ShardedGemWell:
         e.set_owned_range(int(self.bounds[self.rank]), int(self.bounds[self.rank + 1]))
         e.align_and_count()
         t = self._t("count", t)
+
+
+class NativeShardedGemWell:
+    """The sharded run behind the C ABI: this class holds no logic of the step. `unique_id` comes from
+    cellranger_b200.comm_unique_id() on rank 0 and reaches the other ranks through the host's own channel
+    (torch.distributed.broadcast_object_list under torchrun, an argument of mp.spawn in the tests)."""
+
+    def __init__(self, gw, rank: int, world: int, unique_id: bytes, capacity_keys: int):
+        self.gw, self.rank, self.world = gw, rank, world
+        gw.comm_init(unique_id, world, rank, capacity_keys)
+        self.bounds = None
+        self.exchange_bytes = 0
+
+    def run(self):
+        self.gw.sharded_run()
+        self.bounds = self.gw.owner_bounds()
+        self.exchange_bytes = self.gw.shard_stats()["sent_remote_keys"] * 8

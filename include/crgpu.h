@@ -193,6 +193,56 @@ int crgpu_exchange_finish(crgpu_ctx* ctx, uint64_t* out_received);
 /* restrict the matrix columns this context owns to content ranks [lo, hi) */
 int crgpu_set_owned_range(crgpu_ctx* ctx, uint32_t lo, uint32_t hi);
 
+/* ---- The sharded run behind the boundary ----
+ * What a stage `main` of the reference would call (one call per stage, no scripting language in the step:
+ * cr_lib/src/stages/align_and_count.rs:552-789 is one Rust function). The library owns the communicator (NCCL,
+ * loaded at run time; none of this is needed - or loaded - for a single GPU), the owner ranges and the key
+ * exchange; everything of a step is enqueued on the context stream, with one host round trip (the received key
+ * count) before the count stage:
+ *
+ *   pass 1 -> all-reduce(sum) of the priors and exact feature-barcode counts   (priors are global per library
+ *             type, cr_lib/src/stages/make_shard.rs:303-358)
+ *          -> pass 2 -> all-reduce(sum) of the corrected-read counts (barcode_correction.rs:401-407)
+ *          -> owner ranges of contiguous content ranks balanced by valid reads, computed on the device (the
+ *             analogue of ShardReader::make_chunks, align_and_count.rs:519-524)
+ *          -> every key stored straight into its owner's receive buffer over NVLink (peer pointers: same
+ *             process, or CUDA IPC across processes) -> on-stream barrier -> count on the owned range.
+ * With CRGPU_EARLY_SCATTER=1 in the environment the owner ranges are taken from the (global) priors alone and
+ * the keys of pass 1 travel on a second stream while pass 2 runs.
+ *
+ * Per-process form (one process per GPU, e.g. under torchrun or MPI): rank 0 calls crgpu_comm_unique_id and
+ * hands the 128 bytes to every rank by whatever means the host has; every rank then calls crgpu_comm_init
+ * (collective) once and crgpu_sharded_run (collective) per step. exchange_capacity_keys = the most keys this
+ * rank may own (CRGPU_E_LIMIT from crgpu_sharded_run when exceeded). */
+#define CRGPU_COMM_ID_BYTES 128
+int crgpu_comm_unique_id(void* out_id);
+int crgpu_comm_init(crgpu_ctx* ctx, const void* id, int32_t n_ranks, int32_t rank, uint64_t exchange_capacity_keys);
+int crgpu_sharded_run(crgpu_ctx* ctx);
+/* owner ranges of the last sharded run (n_ranks + 1 values) and its exchange statistics:
+ * out4 = {keys this rank stored into other ranks' buffers, keys this rank received (its own included),
+ *         n_ranks, rank} */
+int crgpu_owner_bounds_get(crgpu_ctx* ctx, uint32_t* out_bounds, int32_t cap);
+int crgpu_shard_stats(crgpu_ctx* ctx, uint64_t out4[4]);
+/* owner ranges for a vector of per-rank read counts, on the device, with the arithmetic of the sharded run
+ * (exposed for tests and for hosts that keep their own exchange): counts u32[n] host -> out_bounds[n_parts+1] */
+int crgpu_owner_bounds_compute(crgpu_ctx* ctx, const uint32_t* host_counts, uint64_t n, int32_t n_parts,
+                               uint32_t* out_bounds);
+
+/* Single-process form: one context per device and one host thread per device inside the library. Set each
+ * device's whitelist / libraries / features / reads through crgpu_group_ctx(group, i) exactly as for a single
+ * context (the same whitelist and libraries on every device; the reads split in any way), then crgpu_group_run
+ * does the whole step on all devices. The matrix is the concatenation of the devices' column blocks in device
+ * order (barcode ranges are contiguous and ascending, as the reference's chunk outputs are when joined,
+ * barcode_correction.rs:252-262): crgpu_group_matrix_get returns it as one CSC. */
+typedef struct crgpu_group crgpu_group;
+int crgpu_group_create(const int32_t* devices, int32_t n_devices, uint64_t exchange_capacity_keys, crgpu_group** out);
+crgpu_ctx* crgpu_group_ctx(crgpu_group* group, int32_t i);
+int crgpu_group_size(crgpu_group* group);
+int crgpu_group_run(crgpu_group* group);
+int crgpu_group_matrix_dims(crgpu_group* group, uint64_t* n_barcodes, uint64_t* nnz, uint64_t* n_features);
+int crgpu_group_matrix_get(crgpu_group* group, uint32_t* barcode_rank, int64_t* indptr, uint32_t* indices, int32_t* data);
+void crgpu_group_destroy(crgpu_group* group);
+
 /* ---- Stage ALIGN_AND_COUNT (dedup part) + matrix ----
  * DupBuilder::observe, correct_umis, determine_low_support_umigenes, BarcodeDupMarker::{new,process}
  * (tx_annotation/src/mark_dups.rs:19-59,87-108,116-170,201-363), BcUmiInfo::feature_counts

@@ -527,3 +527,39 @@ def test_write_mex_matches_matrix(tmp_path):
     feats = gzip.open(out / "features.tsv.gz", "rt").read().split("\n")
     assert len(feats) - 1 == m.n_features and feats[0].split("\t")[2] == "Gene Expression"
     gw.close()
+
+
+def test_bench_parity_at_scale_check_works_and_detects_a_wrong_count():
+    """bench.py's sampled-barcode oracle check (run at the 200 M bench size by `bench.py`): green on a correct run
+    of 1.5 M device-generated reads, and red when the GPU's matrix is tampered with."""
+    import bench
+    import cellranger_b200 as cb
+    from cellranger_b200 import synth, synth_device
+
+    n = 1_500_000
+    cfg = synth.preset("cfg2", n)
+    tables = synth.make_tables(cfg, n)
+    gw = cb.GemWell()
+    libs = bench.setup_problem(gw, cfg, tables)
+    reads = synth_device.generate_device(gw, tables, 0, n, "gex")
+    gw.add_reads_device(libs[0], n, cfg.r1_len, reads.r1_seq, reads.r1_qual, reads.feature)
+    gw.run()
+    res = bench.parity_at_scale(gw, libs[0], cfg, tables, reads, n, n_targets=60)
+    assert res["columns_equal"] and res["priors_equal"] and res["molecule_rows_equal"], res
+    assert res["barcodes_checked"] >= 50 and res["entries_checked"] > 1000 and res["reads_through_oracle"] < n // 2
+    # a checker that cannot fail proves nothing: hand it a matrix with one count changed
+    real = gw.count_matrix
+
+    def tampered(pinned=False):
+        m = real()
+        cells = np.unique(np.asarray(tables.cell_rank))
+        col = int(np.searchsorted(m.barcode_rank, cells[0]))
+        m.data[m.indptr[col]] += 1
+        return m
+
+    gw.count_matrix = tampered
+    bad = bench.parity_at_scale(gw, libs[0], cfg, tables, reads, n, n_targets=60, check_molecules=False)
+    assert not bad["columns_equal"] and bad["columns_ok"] == bad["barcodes_checked"] - 1
+    gw.count_matrix = real
+    reads.close()
+    gw.close()

@@ -89,3 +89,21 @@ def test_bench_reference_arm_line_has_the_contract_keys():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["config"]["workload"].startswith("cfg2")
+
+
+def test_csc_fingerprint_adds_up_over_column_blocks():
+    """bench.py's result fingerprint: the per-rank values of a barcode-owner sharded run (contiguous column blocks)
+    add up to the fingerprint of the whole matrix; a changed count, feature or barcode changes it."""
+    import bench
+
+    def cm(rank, indptr, indices, data):
+        return api.CountMatrix(np.array(rank, dtype=np.uint32), np.array(indptr, dtype=np.int64),
+                               np.array(indices, dtype=np.uint32), np.array(data, dtype=np.int32), 10)
+
+    whole = bench.combine_fingerprints([bench.csc_fingerprint(cm([3, 9, 12], [0, 2, 3, 3], [0, 5, 2], [1, 4, 7]), 5)])
+    parts = bench.combine_fingerprints([bench.csc_fingerprint(cm([3], [0, 2], [0, 5], [1, 4]), 2),
+                                        bench.csc_fingerprint(cm([9, 12], [0, 1, 1], [2], [7]), 3)])
+    assert whole == parts and whole["nnz"] == 3 and whole["n_barcodes"] == 3 and whole["umis"] == 12
+    for other in (cm([3, 9, 12], [0, 2, 3, 3], [0, 5, 2], [1, 4, 8]), cm([3, 9, 12], [0, 2, 3, 3], [0, 6, 2], [1, 4, 7]),
+                  cm([3, 9, 13], [0, 2, 3, 3], [0, 5, 2], [1, 4, 7]), cm([3, 9, 12], [0, 1, 3, 3], [0, 5, 2], [1, 4, 7])):
+        assert bench.combine_fingerprints([bench.csc_fingerprint(other, 5)])["csc_hash"] != whole["csc_hash"]
