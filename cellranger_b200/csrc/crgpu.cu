@@ -788,6 +788,9 @@ int crgpu_fb_counts_dev(crgpu_ctx* c, unsigned long long** out, int32_t* n) {
 int crgpu_pass2(crgpu_ctx* c) {
   if (!c) return fail(CRGPU_E_INVALID, "ctx is NULL");
   if (c->stage < 1) return fail(CRGPU_E_INVALID, "crgpu_pass1 must run first");
+  if (c->stage >= 3)
+    return fail(CRGPU_E_INVALID, "crgpu_pass2 after crgpu_count needs crgpu_pass1 first: the count stage sorts the key "
+                                 "buffer in place, the keys pass 1 emitted are gone");
   CU(cudaSetDevice(c->device));
   int rc;
   phases_clear(c, "pass2");

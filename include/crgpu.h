@@ -141,7 +141,10 @@ int crgpu_fb_counts_dev(crgpu_ctx* ctx, unsigned long long** out_dev_u64, int32_
 
 /* ---- Stage BARCODE_CORRECTION: Posterior::correct_barcode over the invalid reads ----
  * barcode/src/corrector.rs:111-165 driven as cr_lib/src/stages/barcode_correction.rs:76-99,327-345;
- * feature-barcode correction with feat_dist (feature_extraction.rs:34-117, feature_checker.rs:8-50). */
+ * feature-barcode correction with feat_dist (feature_extraction.rs:34-117, feature_checker.rs:8-50).
+ * May be repeated (a retry): it restarts from the state crgpu_pass1 left - no corrected reads, the key list ending
+ * where pass 1 ended. After crgpu_count it is refused (CRGPU_E_INVALID) until crgpu_pass1 has run again, because
+ * the count stage sorts the key buffer in place. */
 int crgpu_pass2(crgpu_ctx* ctx);
 
 /* Corrector plugin seam, batch form of trait CorrectBarcode (barcode/src/corrector.rs:73-81):
