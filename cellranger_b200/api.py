@@ -634,6 +634,14 @@ class GemWell:
         return {"total_reads": total, "valid_before": valid_before, "corrected": corrected,
                 "corrected_bc": frac(corrected), "good_bc": frac(valid_before + corrected)}
 
+    def barcode_diversity(self, library: int = 0) -> dict:
+        """BarcodeDiversityMetrics (cr_lib/src/stages/barcode_correction.rs:428-441): barcodes_detected and
+        effective_barcode_diversity = inverse Simpson index of the valid-barcode read counts
+        (SimpleHistogram::effective_diversity, metric/src/histogram.rs:161-171)."""
+        n, d = C.c_uint64(), C.c_double()
+        check(self.L.crgpu_barcode_diversity(self._ctx, library, C.byref(n), C.byref(d)), "crgpu_barcode_diversity")
+        return {"barcodes_detected": int(n.value), "effective_barcode_diversity": float(d.value)}
+
     def write_mex(self, folder: str, software_version: str = "Cell Ranger cellranger_b200", gem_group: int = 1):
         """raw_feature_bc_matrix/{matrix.mtx.gz, barcodes.tsv.gz, features.tsv.gz}
         (MtxWriter, cr_lib/src/stages/write_matrix_market.rs:41-120)."""

@@ -1286,7 +1286,7 @@ int crgpu_count(crgpu_ctx* c) {
   b.scalars = c->scalars.as<unsigned long long>();
   b.sort_temp = c->sort_temp.p;
   b.sort_temp_bytes = c->sort_temp.cap;
-  {
+  if (getenv("CRGPU_LS_GLOBAL") && atoi(getenv("CRGPU_LS_GLOBAL"))) {  // the global slot table of the round-1 pre-filter
     int slot_bits = 16;
     while (slot_bits < 30 && (1ull << slot_bits) < 8 * cap) slot_bits++;
     if ((rc = c->ls_slots.ensure(((size_t)1 << slot_bits) / 4))) return rc;
@@ -1550,6 +1550,27 @@ int crgpu_barcode_summary(crgpu_ctx* c, int lib, uint32_t* out) {
   CHECK_KERNEL();
   CU(cudaMemcpyAsync(out, c->summary.p, c->n_barcodes * 16, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  return CRGPU_OK;
+}
+
+int crgpu_barcode_diversity(crgpu_ctx* c, int lib, uint64_t* barcodes_detected, double* effective_diversity) {
+  if (!c || lib < 0 || lib >= (int)c->libs.size()) return fail(CRGPU_E_INVALID, "bad argument");
+  if (c->stage < 2) return fail(CRGPU_E_INVALID, "crgpu_pass2 must run first");
+  CU(cudaSetDevice(c->device));
+  unsigned long long* d4 = c->scalars.as<unsigned long long>() + 52;
+  unsigned long long h[4] = {0, 0, 0, 0};
+  c->launches += launch_diversity(c->libs[lib]->valid.as<uint32_t>(), c->content.size(), d4, c->stream);
+  CHECK_KERNEL();
+  CU(cudaMemcpyAsync(h, d4, 32, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (barcodes_detected) *barcodes_detected = h[0];
+  if (effective_diversity) {
+    // s.powi(2) / s2 in f64 as the reference computes it; the integer sums are exact, so this equals the
+    // reference's value whenever its own f64 accumulation is exact (sum c^2 < 2^53), in any iteration order
+    const double s = (double)h[1];
+    const double s2 = (double)h[2] + (double)h[3] * 18446744073709551616.0;
+    *effective_diversity = (s * s) / s2;  // NaN for an empty histogram, like 0/0 in the reference
+  }
   return CRGPU_OK;
 }
 

@@ -660,6 +660,116 @@ __global__ void __launch_bounds__(256) ls_collect_kernel(const unsigned long lon
   }
 }
 
+// ---- the same pre-filter in shared memory ----
+// The (rank, library, umi) groups never cross a barcode, and the distinct-key table is sorted by barcode: a block
+// takes the barcodes that START in its tile of the table (the last one may run far past the tile; a tile in the
+// middle of a long barcode has nothing to do), marks their keys in a 2-bit filter in shared memory, and reads the
+// keys a second time (out of L2) to collect the ones whose slot was visited twice. No global atomics but one per
+// warp of candidates, no 150 MB slot table to clear and to miss in L2. 32 slots per key of the range (at most
+// LF_MAX_SLOTS): about 3 % of the keys are false candidates, the exact regrouping downstream drops them.
+constexpr int LF_THREADS = 512;
+constexpr int LF_TILE = 4096;
+constexpr int LF_MAX_SLOTS = 1 << 18;  // 2 bits each: 64 KB
+constexpr int LF_MIN_SLOTS = 1 << 12;
+
+__device__ __forceinline__ uint32_t lf_hash(unsigned long long key, const KeyLayout& kl, const FieldMasks& fm) {
+  const unsigned long long umi = key & ((1ull << fm.ubits) - 1ull);
+  const unsigned long long lib = (key >> kl.lib_shift) & ((1ull << fm.lbits) - 1ull);
+  const unsigned long long rank = key >> kl.rank_shift;
+  unsigned long long g = ((rank << fm.lbits | lib) << fm.ubits) | umi;
+  g ^= g >> 31;
+  g *= 0x9E3779B97F4A7C15ull;
+  g ^= g >> 29;
+  g *= 0xBF58476D1CE4E5B9ull;
+  return (uint32_t)(g >> 32);
+}
+
+__global__ void __launch_bounds__(LF_THREADS) ls_filter_kernel(const unsigned long long* __restrict__ dkeys, uint64_t m,
+                                                               KeyLayout kl, unsigned long long* __restrict__ cand,
+                                                               unsigned long long* __restrict__ n_cand) {
+  extern __shared__ uint32_t lf_slots[];  // LF_MAX_SLOTS / 16 words
+  __shared__ unsigned long long s_lo, s_hi;
+  const FieldMasks fm = field_masks(kl);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint64_t t_lo = (uint64_t)blockIdx.x * LF_TILE;
+  const uint64_t t_hi = t_lo + LF_TILE < m ? t_lo + LF_TILE : m;
+  if (tid == 0) {
+    s_lo = ~0ull;
+    s_hi = ~0ull;
+  }
+  __syncthreads();
+  // first barcode start inside the tile
+  {
+    unsigned long long first = ~0ull;
+    for (uint64_t j = t_lo + tid; j < t_hi; j += LF_THREADS) {
+      const bool start = j == 0 || (dkeys[j] >> kl.rank_shift) != (dkeys[j - 1] >> kl.rank_shift);
+      if (start && j < first) first = j;
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, first, d);
+      first = o < first ? o : first;
+    }
+    if (lane == 0 && first != ~0ull) atomicMin(&s_lo, first);
+  }
+  __syncthreads();
+  const uint64_t lo = s_lo;
+  if (lo == ~0ull) return;  // the tile lies inside a barcode that an earlier tile owns (block-uniform)
+  // end of the barcode that holds the tile's last key
+  uint64_t hi = m;
+  if (t_hi < m) {
+    const unsigned long long last_rank = dkeys[t_hi - 1] >> kl.rank_shift;
+    for (uint64_t base = t_hi;; base += LF_THREADS) {
+      const uint64_t j = base + tid;
+      const bool differs = j >= m || (dkeys[j] >> kl.rank_shift) != last_rank;
+      const uint32_t mk = __ballot_sync(0xFFFFFFFFu, differs);
+      if (mk && lane == 0) atomicMin(&s_hi, (unsigned long long)(base + (tid & ~31) + (__ffs(mk) - 1)));
+      __syncthreads();
+      const unsigned long long found = s_hi;
+      if (found != ~0ull) {
+        hi = found < m ? found : m;
+        break;
+      }
+      __syncthreads();
+    }
+  }
+  const uint64_t range = hi - lo;
+  uint32_t n_slots = LF_MIN_SLOTS;
+  while (n_slots < (uint32_t)LF_MAX_SLOTS && (uint64_t)n_slots < 32ull * range) n_slots <<= 1;
+  for (uint32_t i = tid; i < n_slots / 16; i += LF_THREADS) lf_slots[i] = 0u;
+  __syncthreads();
+  for (uint64_t j = lo + tid; j < hi; j += LF_THREADS) {
+    const uint32_t h = lf_hash(dkeys[j], kl, fm) & (n_slots - 1u);
+    const uint32_t bit = 1u << (2u * (h & 15u));
+    const uint32_t old = atomicOr(&lf_slots[h >> 4], bit);
+    if (old & bit) atomicOr(&lf_slots[h >> 4], bit << 1);
+  }
+  __syncthreads();
+  const uint64_t rounds = (range + LF_THREADS - 1) / LF_THREADS;  // warp-uniform trip count: ballots inside
+  for (uint64_t r = 0; r < rounds; r++) {
+    const uint64_t j = lo + r * LF_THREADS + tid;
+    bool hit = false;
+    unsigned long long k = 0ull;
+    if (j < hi) {
+      k = dkeys[j];
+      const uint32_t h = lf_hash(k, kl, fm) & (n_slots - 1u);
+      hit = (lf_slots[h >> 4] >> (2u * (h & 15u) + 1u)) & 1u;
+    }
+    const uint32_t mk = __ballot_sync(0xFFFFFFFFu, hit);
+    if (mk) {
+      unsigned long long base = 0ull;
+      if (lane == 0) base = atomicAdd(n_cand, (unsigned long long)__popc(mk));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (hit) {
+        const unsigned long long umi = k & ((1ull << fm.ubits) - 1ull);
+        const unsigned long long lib = (k >> kl.lib_shift) & ((1ull << fm.lbits) - 1ull);
+        const unsigned long long feat = (k >> kl.feature_shift) & ((1ull << fm.fbits) - 1ull);
+        const unsigned long long rank = k >> kl.rank_shift;
+        cand[base + __popc(mk & ((1u << lane) - 1u))] = (((rank << fm.lbits | lib) << fm.ubits | umi) << fm.fbits) | feat;
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ uint64_t lower_bound_u64(const unsigned long long* a, uint64_t n, unsigned long long v) {
   uint64_t lo = 0, hi = n;
   while (lo < hi) {
@@ -1266,17 +1376,26 @@ int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
   mark("count.dedup.low_support");
   // 3. low-support filter: candidates by hashing (rank, library, umi), exact regrouping of those only
   if (b.filter_umis) {
-    int slot_bits = 16;
-    const int slot_cap = getenv("CRGPU_LS_SLOTCAP") ? atoi(getenv("CRGPU_LS_SLOTCAP")) : 29;
-    const int region_bits = ls_region_bits_host();
-    while (slot_bits < slot_cap && (1ull << slot_bits) < 8 * m) slot_bits++;
-    const size_t slot_bytes = ((size_t)1 << slot_bits) / 4;  // 2 bits per slot
-    if (b.slots_bytes < slot_bytes) return -1;
-    cudaMemsetAsync(b.slots, 0, slot_bytes, st);
-    ls_mark_kernel<<<grid_for(m, 256, 32), 256, 0, st>>>(b.dkeys, m, b.kl, b.slots, slot_bits, region_bits);
-    ls_collect_kernel<<<grid_for(m, 256, 16), 256, 0, st>>>(b.dkeys, m, b.kl, b.slots, slot_bits, region_bits, b.key2,
-                                                                 b.scalars + 9);
-    launches += 2;
+    if (getenv("CRGPU_LS_GLOBAL") && atoi(getenv("CRGPU_LS_GLOBAL"))) {
+      // the round-1 pre-filter (global 2-bit slot table), kept for A/B measurements
+      int slot_bits = 16;
+      const int slot_cap = getenv("CRGPU_LS_SLOTCAP") ? atoi(getenv("CRGPU_LS_SLOTCAP")) : 29;
+      const int region_bits = ls_region_bits_host();
+      while (slot_bits < slot_cap && (1ull << slot_bits) < 8 * m) slot_bits++;
+      const size_t slot_bytes = ((size_t)1 << slot_bits) / 4;  // 2 bits per slot
+      if (b.slots_bytes < slot_bytes) return -1;
+      cudaMemsetAsync(b.slots, 0, slot_bytes, st);
+      ls_mark_kernel<<<grid_for(m, 256, 32), 256, 0, st>>>(b.dkeys, m, b.kl, b.slots, slot_bits, region_bits);
+      ls_collect_kernel<<<grid_for(m, 256, 16), 256, 0, st>>>(b.dkeys, m, b.kl, b.slots, slot_bits, region_bits, b.key2,
+                                                                   b.scalars + 9);
+      launches += 2;
+    } else {
+      const size_t smem = (size_t)LF_MAX_SLOTS / 4;
+      cudaFuncSetAttribute(ls_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      ls_filter_kernel<<<(unsigned)((m + LF_TILE - 1) / LF_TILE), LF_THREADS, smem, st>>>(b.dkeys, m, b.kl, b.key2,
+                                                                                        b.scalars + 9);
+      launches += 1;
+    }
     unsigned long long n_cand = 0;
     cudaMemcpyAsync(&n_cand, b.scalars + 9, 8, cudaMemcpyDeviceToHost, st);
     cudaStreamSynchronize(st);
@@ -1501,6 +1620,46 @@ int run_barcode_summary(DedupBuffers& b, uint64_t m, uint32_t lib, const uint32_
   summary_keys_kernel<<<grid_for(m, 256, 8), 256, 0, st>>>(b.dkeys, b.c0, b.best, b.inc, b.low, m, b.kl, lib,
                                                                 col_of_rank, out4);
   return 2;
+}
+
+// ---------------------------------------------------------------------------
+// BarcodeDiversityMetrics of BARCODE_CORRECTION's join (cr_lib/src/stages/barcode_correction.rs:428-441):
+// barcodes_detected = entries of the corrected barcode histogram, effective_barcode_diversity = its inverse
+// Simpson index (sum c)^2 / sum c^2 (SimpleHistogram::effective_diversity, metric/src/histogram.rs:161-171).
+// The sums are taken exactly in integers (sum c^2 in 128 bits) and converted once.
+// out4: [0] barcodes with a count, [1] sum c, [2] low and [3] high word of sum c^2
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) diversity_kernel(const uint32_t* __restrict__ counts, uint64_t n,
+                                                        unsigned long long* __restrict__ out4) {
+  unsigned long long nz = 0, s = 0;
+  unsigned __int128 s2 = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long c = counts[i];
+    nz += c != 0ull;
+    s += c;
+    s2 += (unsigned __int128)(c * c);
+  }
+  unsigned long long lo = (unsigned long long)s2, hi = (unsigned long long)(s2 >> 64);
+  for (int d = 16; d > 0; d >>= 1) {
+    nz += __shfl_xor_sync(0xFFFFFFFFu, nz, d);
+    s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
+    const unsigned long long olo = __shfl_xor_sync(0xFFFFFFFFu, lo, d), ohi = __shfl_xor_sync(0xFFFFFFFFu, hi, d);
+    const unsigned long long nlo = lo + olo;
+    hi += ohi + (nlo < lo ? 1ull : 0ull);
+    lo = nlo;
+  }
+  if ((threadIdx.x & 31) == 0 && nz) {
+    atomicAdd(out4 + 0, nz);
+    atomicAdd(out4 + 1, s);
+    const unsigned long long old = atomicAdd(out4 + 2, lo);
+    atomicAdd(out4 + 3, hi + (old + lo < old ? 1ull : 0ull));
+  }
+}
+int launch_diversity(const uint32_t* counts, uint64_t n, unsigned long long* out4, cudaStream_t st) {
+  cudaMemsetAsync(out4, 0, 32, st);
+  if (!n) return 0;
+  diversity_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(counts, n, out4);
+  return 1;
 }
 
 int run_molecule_rows(DedupBuffers& b, const uint32_t* col_of_rank, uint64_t n_mol, uint32_t* out5, cudaStream_t st) {

@@ -177,6 +177,7 @@ int run_owner_scatter_peers_dev(const unsigned long long* keys, const unsigned l
 int run_owner_bounds(const uint32_t* const* vectors, int n_vectors, uint32_t n, int n_parts, unsigned long long* scratch,
                      uint32_t* bounds_dev, cudaStream_t st);
 size_t owner_bounds_scratch_bytes(uint32_t n);
+int launch_diversity(const uint32_t* counts, uint64_t n, unsigned long long* out4, cudaStream_t st);
 int launch_state_counts(const uint32_t* bc_out, uint64_t n, unsigned long long* out4, cudaStream_t st);
 
 struct AnnotateArgs {

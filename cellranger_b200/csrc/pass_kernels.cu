@@ -859,10 +859,11 @@ __global__ void __launch_bounds__(256) pass2_kernel(const Pass2Args a) {
     bool emit = false;
     unsigned long long key = 0ull;
     if (e < n_invalid) {
-      const uint32_t idx = a.inv_idx[e];
-      const uint32_t q = a.inv_bc[e];
-      const uint32_t nmask = a.inv_nmask[e];
-      const uint4 qq = a.inv_qual[e];
+      // the side list streams through once: keep it from displacing the whitelist tables in L2
+      const uint32_t idx = __ldcs(a.inv_idx + e);
+      const uint32_t q = __ldcs(a.inv_bc + e);
+      const uint32_t nmask = __ldcs(a.inv_nmask + e);
+      const uint4 qq = __ldcs(a.inv_qual + e);
       const uint32_t qw[4] = {qq.x, qq.y, qq.z, qq.w};
       const int L = a.wl.L;
       unsigned long long m;
@@ -911,11 +912,11 @@ __global__ void __launch_bounds__(256) pass2_kernel(const Pass2Args a) {
         accept = ee_ok && (__ddiv_rn(best, total) >= a.threshold);
       }
       if (accept) {
-        a.bc_out[idx] = (ST_VALID_AFTER << BC_STATE_SHIFT) | best_rank;
+        __stcs(a.bc_out + idx, (ST_VALID_AFTER << BC_STATE_SHIFT) | best_rank);
         if (a.corrected) atomicAdd(a.corrected + best_rank, 1u);
         if (a.emit_keys) {
-          uint32_t uw = a.umi_out[idx];
-          uint32_t feature = a.feature ? checked_feature(a.feature[idx], a.n_features, nullptr) : NO_FEATURE;
+          uint32_t uw = __ldcs(a.umi_out + idx);
+          uint32_t feature = a.feature ? checked_feature(__ldcs(a.feature + idx), a.n_features, nullptr) : NO_FEATURE;
           if ((uw & UMI_VALID_BIT) && feature != NO_FEATURE) {
             emit = true;
             key = make_key(a.kl, best_rank, feature, a.lib, uw & UMI_SEQ_MASK);
@@ -928,7 +929,7 @@ __global__ void __launch_bounds__(256) pass2_kernel(const Pass2Args a) {
       uint32_t off = block_exclusive_scan<256>(emit ? 1u : 0u, &tot, scan_a);
       if (threadIdx.x == 0) base_bcast = tot ? atomicAdd(a.counters, (unsigned long long)tot) : 0ull;
       __syncthreads();
-      if (emit) a.keys[base_bcast + off] = key;
+      if (emit) __stcs(a.keys + base_bcast + off, key);
       __syncthreads();
     }
   }

@@ -312,6 +312,12 @@ int crgpu_matrix_write_mex(crgpu_ctx* ctx, const char* folder, const char* softw
  * reads > 0. Needs crgpu_count() first. */
 int crgpu_barcode_summary(crgpu_ctx* ctx, int library, uint32_t* out);
 
+/* BarcodeDiversityMetrics of one library type (BARCODE_CORRECTION join, cr_lib/src/stages/barcode_correction.rs:
+ * 428-441): barcodes_detected = valid barcodes with at least one read (raw valid + corrected),
+ * effective_barcode_diversity = inverse Simpson index of their read counts (SimpleHistogram::effective_diversity,
+ * metric/src/histogram.rs:161-171). After a sharded run the counts are the global ones on every rank. */
+int crgpu_barcode_diversity(crgpu_ctx* ctx, int library, uint64_t* barcodes_detected, double* effective_diversity);
+
 /* UmiCount rows (cr_types/src/types.rs:148-160), sorted by (barcode, library, feature, umi):
  * out5[5*i..] = {barcode column index, library, feature, umi 2-bit, read_count} */
 int crgpu_molecules_count(crgpu_ctx* ctx, uint64_t* n);

@@ -443,6 +443,26 @@ def test_barcode_correction_metrics_match_oracle_counts():
     gw.close()
 
 
+def test_barcode_diversity_matches_histogram_formula():
+    """barcodes_detected / effective_barcode_diversity of BARCODE_CORRECTION's join (barcode_correction.rs:428-441):
+    (sum c)^2 / sum c^2 over the corrected barcode histogram, here from the oracle's raw-valid + corrected counts
+    with the reference's own f64 expression (histogram.rs:161-171)."""
+    prob = helpers.make_problem("cfg1", 80_000)
+    o = helpers.run_oracle(prob)
+    gw = helpers.run_gpu(prob, annotate=False)
+    wl = prob["tables"].whitelist
+    c = (o.counts(0, 0, wl) + o.counts(0, 1, wl)).astype(np.float64)
+    c = c[c > 0]
+    s, s2 = 0.0, 0.0
+    for x in c:  # literally the loop of effective_diversity()
+        s += x
+        s2 += x ** 2
+    d = gw.barcode_diversity(0)
+    assert d["barcodes_detected"] == len(c)
+    assert d["effective_barcode_diversity"] == s ** 2 / s2
+    gw.close()
+
+
 def _fastq_text(seq, qual, rng, trailing_newline=True):
     """4-line FASTQ records with headers of varying length (what bcl2fastq writes, roughly)."""
     parts = []
