@@ -1230,18 +1230,24 @@ int crgpu_count(crgpu_ctx* c) {
   const uint64_t nk = c->n_keys;
   const uint64_t cap = std::max<uint64_t>(nk, 1);
   if ((rc = c->sort_temp.ensure(sort_temp_bytes(cap)))) return rc;
+  // Default: the radix sort covers every key bit (8 passes for a 62-bit key) and rle_kernel encodes the runs.
+  // CRGPU_FINISH_SORT=1 sorts only the bits above the UMI (5 passes) and leaves the UMI bits to the per-segment
+  // shared-memory kernels of finish_kernels.cu, fused with the run-length encoding: bit-exact, but measured slower
+  // on B200 (3 passes + RLE = 3.7 ms against 7.6 ms at 168 M keys; DESIGN.md section 4 has the ncu numbers).
+  const bool finish_umi = finish_supported(c->kl.umi_bits) && getenv("CRGPU_FINISH_SORT") && atoi(getenv("CRGPU_FINISH_SORT"));
+  const int sort_begin = finish_umi ? c->kl.umi_bits : 0;
   if ((rc = phase_begin(c, "count.sort.hist"))) return rc;
   unsigned long long* key_src = c->key_src ? c->key_src : c->keys.as<unsigned long long>();
-  c->launches += sort_histograms(key_src, nk, c->kl.total_bits, c->sort_temp.p, c->stream);
+  c->launches += sort_histograms(key_src, nk, c->kl.total_bits, c->sort_temp.p, c->stream, sort_begin);
   CHECK_KERNEL();
   if ((rc = phase_end(c))) return rc;
   {
-    std::string nm = "count.sort.onesweep_x" + std::to_string(sort_num_passes(c->kl.total_bits));
+    std::string nm = "count.sort.onesweep_x" + std::to_string(sort_num_passes(c->kl.total_bits - sort_begin));
     if ((rc = phase_begin(c, nm.c_str()))) return rc;
   }
   unsigned long long* sorted = key_src;
   c->launches += sort_passes(key_src, c->keys_alt.as<unsigned long long>(), nk,
-                             c->kl.total_bits, c->sort_temp.p, &sorted, c->stream);
+                             c->kl.total_bits, c->sort_temp.p, &sorted, c->stream, sort_begin);
   CHECK_KERNEL();
   if ((rc = phase_end(c))) return rc;
   if ((rc = phase_begin(c, "count.dedup.alloc"))) return rc;
@@ -1261,6 +1267,8 @@ int crgpu_count(crgpu_ctx* c) {
   DedupBuffers b;
   memset(&b, 0, sizeof(b));
   b.sorted = sorted;
+  b.sorted_alt = sorted == key_src ? c->keys_alt.as<unsigned long long>() : key_src;
+  b.finish_umi = finish_umi ? 1 : 0;
   b.n_keys = nk;
   b.kl = c->kl;
   b.umi_correction_mask = 0;
@@ -1334,13 +1342,15 @@ int crgpu_count(crgpu_ctx* c) {
   CU(cudaStreamSynchronize(c->stream));
   c->nnz = c->n_mol ? hs[1] : 0;
   if ((rc = phase_end(c))) return rc;
-  unsigned int lb_flags[2] = {0u, 0u};
+  unsigned int lb_flags[3] = {0u, 0u, 0u};
   sort_lb_flag_fetch(&lb_flags[0], c->stream);
   dedup_lb_flag_fetch(&lb_flags[1], c->stream);
+  finish_lb_flag_fetch(&lb_flags[2], c->stream);
   CU(cudaStreamSynchronize(c->stream));
-  if (lb_flags[0] | lb_flags[1]) {
+  if (lb_flags[0] | lb_flags[1] | lb_flags[2]) {
     sort_lb_flag_clear(c->stream);
     dedup_lb_flag_clear(c->stream);
+    finish_lb_flag_clear(c->stream);
     return fail(CRGPU_E_CUDA, "chained-scan watchdog: a tile waited for a predecessor that never became resident "
                               "(blocks were not dispatched in index order); results of this call are invalid - "
                               "set CRGPU_TICKETS=1 for ticket-ordered tiles");

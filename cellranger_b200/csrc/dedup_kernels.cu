@@ -11,6 +11,7 @@
 //   UMIs    distinct correction targets that are not low support    BarcodeDupMarker::process :280-363
 //           → UmiCount rows → per (barcode, feature) counts (cr_types/src/types.rs:180-188)
 #include <algorithm>
+#include <cstdio>
 
 #include "kernels.h"
 
@@ -1319,18 +1320,18 @@ int launch_state_counts(const uint32_t* bc_out, uint64_t n, unsigned long long* 
 }
 
 // debug verification (CRGPU_VERIFY=1): order violations in a key array; strict = equal neighbours count too
-__global__ void order_violations_kernel(const unsigned long long* __restrict__ a, uint64_t n, int strict,
+__global__ void order_violations_kernel(const unsigned long long* __restrict__ a, uint64_t n, int strict, int shift,
                                         unsigned long long* out) {
   unsigned long long bad = 0;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x + 1; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-    bad += strict ? (a[i] <= a[i - 1]) : (a[i] < a[i - 1]);
+    bad += strict ? ((a[i] >> shift) <= (a[i - 1] >> shift)) : ((a[i] >> shift) < (a[i - 1] >> shift));
   for (int d = 16; d > 0; d >>= 1) bad += __shfl_xor_sync(0xFFFFFFFFu, bad, d);
   if ((threadIdx.x & 31) == 0 && bad) atomicAdd(out, bad);
 }
-int launch_order_violations(const unsigned long long* a, uint64_t n, int strict, unsigned long long* out,
+int launch_order_violations(const unsigned long long* a, uint64_t n, int strict, int shift, unsigned long long* out,
                             cudaStream_t st) {
   if (n < 2) return 0;
-  order_violations_kernel<<<grid_for(n), 256, 0, st>>>(a, n, strict, out);
+  order_violations_kernel<<<grid_for(n), 256, 0, st>>>(a, n, strict, shift, out);
   return 1;
 }
 
@@ -1345,17 +1346,25 @@ int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
   cudaMemsetAsync(b.scalars, 0, 16 * 8, st);
   mark("count.dedup.rle");
   // 1. run-length encode: distinct keys + raw counts (head positions parked in `best`)
-  launches += run_rle<true>(b.sorted, b.n_keys, 0, b.dkeys, b.best, ss.desc, ss.ticket, b.scalars + 0, st);
+  if (b.verify && b.finish_umi)  // before the finishing sort rearranges the long segments
+    launches += launch_order_violations(b.sorted, b.n_keys, 0, b.kl.umi_bits, b.scalars + 10, st);
+  if (b.finish_umi)
+    launches += run_finish(b.sorted, b.sorted_alt, b.n_keys, b.kl.umi_bits, b.dkeys, b.c0, ss.desc, b.scalars + 0, st,
+                           b.mark, b.mark_user);
+  else
+    launches += run_rle<true>(b.sorted, b.n_keys, 0, b.dkeys, b.best, ss.desc, ss.ticket, b.scalars + 0, st);
   unsigned long long m = 0;
   cudaMemcpyAsync(&m, b.scalars + 0, 8, cudaMemcpyDeviceToHost, st);
   cudaStreamSynchronize(st);
   *n_distinct_host = m;
   if (m == 0) return launches;
-  run_lengths_kernel<<<grid_for(m), 256, 0, st>>>(b.best, m, b.n_keys, b.c0);
-  launches++;
+  if (!b.finish_umi) {
+    run_lengths_kernel<<<grid_for(m), 256, 0, st>>>(b.best, m, b.n_keys, b.c0);
+    launches++;
+  }
   if (b.verify) {
-    launches += launch_order_violations(b.sorted, b.n_keys, 0, b.scalars + 10, st);
-    launches += launch_order_violations(b.dkeys, m, 1, b.scalars + 11, st);
+    if (!b.finish_umi) launches += launch_order_violations(b.sorted, b.n_keys, 0, 0, b.scalars + 10, st);
+    launches += launch_order_violations(b.dkeys, m, 1, 0, b.scalars + 11, st);
   }
   // 2. UMI correction targets + incoming counts
   mark("count.dedup.correct_umis");
@@ -1399,6 +1408,8 @@ int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
     unsigned long long n_cand = 0;
     cudaMemcpyAsync(&n_cand, b.scalars + 9, 8, cudaMemcpyDeviceToHost, st);
     cudaStreamSynchronize(st);
+    if (getenv("CRGPU_DEBUG")) fprintf(stderr, "[crgpu] low-support candidates: %llu of %llu distinct keys\n", n_cand, m);
+    mark("count.dedup.low_support.regroup");
     if (n_cand) {
       unsigned long long* sorted2 = nullptr;
       // grouping by (rank, library, umi) only needs the bits above the feature field

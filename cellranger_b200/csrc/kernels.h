@@ -116,10 +116,22 @@ int sort_histograms(const unsigned long long* keys, uint64_t n, int end_bit, voi
 int sort_passes(unsigned long long* keys, unsigned long long* alt, uint64_t n, int end_bit, void* temp,
                 unsigned long long** out, cudaStream_t st, int begin_bit = 0);
 
+// ---- per-segment UMI sort + run-length encoding (finish_kernels.cu) ----
+// keys sorted on the bits above the UMI -> the distinct-key table (dkeys, c0) in full key order
+bool finish_supported(int umi_bits);
+int run_finish(unsigned long long* keys, unsigned long long* alt, uint64_t n, int umi_bits, unsigned long long* dkeys,
+               uint32_t* c0, unsigned long long* desc, unsigned long long* total_out, cudaStream_t st,
+               void (*mark)(void*, const char*) = nullptr, void* mark_user = nullptr);
+size_t finish_desc_bytes(uint64_t n);
+void finish_lb_flag_fetch(unsigned int* host_out, cudaStream_t st);
+void finish_lb_flag_clear(cudaStream_t st);
+
 // ---- dedup / count (dedup_kernels.cu) ----
 struct DedupBuffers {
   // inputs
-  const unsigned long long* sorted;  // [n_keys]
+  unsigned long long* sorted;      // [n_keys] sorted keys: on every bit, or (finish_umi) on the bits above the UMI
+  unsigned long long* sorted_alt;  // the spare buffer of the sort (scratch of the finishing sort)
+  int finish_umi;                  // 1: the UMI bits are still to be sorted, per segment (finish_kernels.cu)
   uint64_t n_keys;
   KeyLayout kl;
   uint32_t umi_correction_mask;  // bit lib set: UMI correction enabled for that library
