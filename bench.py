@@ -275,8 +275,8 @@ def parity_at_scale(gw, lib, cfg, tables, reads_dev, n_reads, n_targets=200, che
         ma = ma[ra >= 0].astype(np.int64)
         ma[:, 0] = ra[ra >= 0]
         mg = mg.astype(np.int64)
-        ka = np.lexsort((ma[:, 4], ma[:, 3], ma[:, 2], ma[:, 1], ma[:, 0]))
-        kg = np.lexsort((mg[:, 4], mg[:, 3], mg[:, 2], mg[:, 1], mg[:, 0]))
+        ka = np.lexsort((ma[:, 5], ma[:, 4], ma[:, 3], ma[:, 2], ma[:, 1], ma[:, 0]))
+        kg = np.lexsort((mg[:, 5], mg[:, 4], mg[:, 3], mg[:, 2], mg[:, 1], mg[:, 0]))
         mol_equal = bool(ma.shape == mg.shape and np.array_equal(ma[ka], mg[kg]))
         n_mol_rows = int(mg.shape[0])
     o.close()

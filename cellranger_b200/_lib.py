@@ -33,7 +33,7 @@ class LibraryDef(C.Structure):
 class ReadBatch(C.Structure):
     _fields_ = [("n", C.c_uint64), ("r1_len", C.c_int32), ("r1_seq", C.c_void_p), ("r1_qual", C.c_void_p),
                 ("feature", C.c_void_p), ("r2_len", C.c_int32), ("r2_seq", C.c_void_p), ("r2_qual", C.c_void_p),
-                ("on_device", C.c_int32)]
+                ("on_device", C.c_int32), ("select_key", C.c_void_p)]
 
 
 class SynthParams(C.Structure):

@@ -291,8 +291,10 @@ class GemWell:
         check(self.L.crgpu_features_set(self._ctx, fr.n_features, ptr(ft), ptr(seqs), stride), "crgpu_features_set")
         self.feature_reference = fr
 
-    def add_reads(self, library: int, r1_seq, r1_qual, feature=None, r2_seq=None, r2_qual=None) -> int:
-        """Host arrays: r1_seq/r1_qual (n, r1_len) uint8, feature uint32[n] (GEX) or r2_* (feature barcode)."""
+    def add_reads(self, library: int, r1_seq, r1_qual, feature=None, r2_seq=None, r2_qual=None, select_key=None) -> int:
+        """Host arrays: r1_seq/r1_qual (n, r1_len) uint8, feature uint32[n] (GEX) or r2_* (feature barcode);
+        select_key: optional uint64[n], UmiSelectKey{utype, qname} per read as one order-preserving word (bit 63
+        = NonTxomic, low bits = rank of the qname; tx_annotation/src/mark_dups.rs:110-152)."""
         r1_seq = np.ascontiguousarray(r1_seq, dtype=np.uint8)
         r1_qual = np.ascontiguousarray(r1_qual, dtype=np.uint8)
         if r1_seq.ndim != 2 or r1_seq.shape != r1_qual.shape:
@@ -314,6 +316,12 @@ class GemWell:
             rb.r2_len = r2_seq.shape[1]
             rb.r2_seq, rb.r2_qual = r2_seq.ctypes.data, r2_qual.ctypes.data
             keep += [r2_seq, r2_qual]
+        if select_key is not None:
+            select_key = np.ascontiguousarray(select_key, dtype=np.uint64)
+            if select_key.shape != (n,):
+                raise ValueError("select_key must have one entry per read")
+            rb.select_key = select_key.ctypes.data
+            keep.append(select_key)
         rb.on_device = 0
         out = C.c_int(-1)
         check(self.L.crgpu_reads_add(self._ctx, library, C.byref(rb), C.byref(out)), "crgpu_reads_add")
@@ -659,10 +667,12 @@ class GemWell:
               "crgpu_matrix_write_mex")
 
     def molecules(self) -> np.ndarray:
-        """UmiCount rows: (barcode column, library, feature, umi 2-bit, read_count)."""
+        """UmiCount rows in molecule_info order (by barcode, then library_idx, feature_idx, umi, read_count;
+        cr_types/src/types.rs:152-160): (barcode column, library_idx, feature_idx, umi 2-bit, read_count,
+        umi_type with 1 = Txomic, 0 = NonTxomic)."""
         n = C.c_uint64()
         check(self.L.crgpu_molecules_count(self._ctx, C.byref(n)))
-        out = np.zeros((n.value, 5), dtype=np.uint32)
+        out = np.zeros((n.value, 6), dtype=np.uint32)
         check(self.L.crgpu_molecules_get(self._ctx, ptr(out)), "crgpu_molecules_get")
         return out
 

@@ -222,6 +222,7 @@ void crgpu_ctx_destroy(crgpu_ctx* c) {
   shard_release(c);
   auto free_batch = [](Batch* b) {
     b->own_seq.release(); b->own_qual.release(); b->own_feat.release(); b->own_r2s.release(); b->own_r2q.release();
+    b->own_select.release();
     b->feature_res.release(); b->inv_idx.release(); b->inv_bc.release(); b->inv_nmask.release(); b->inv_qual.release();
     delete b;
   };
@@ -239,7 +240,7 @@ void crgpu_ctx_destroy(crgpu_ctx* c) {
                    &c->keys_alt, &c->sort_temp, &c->counters, &c->dkeys, &c->c0, &c->best, &c->inc, &c->low, &c->key2,
                    &c->key2_alt, &c->lb_desc, &c->tickets, &c->scalars, &c->ent_rank, &c->ent_feature, &c->ent_count,
                    &c->mol, &c->col_of_rank, &c->barcode_rank, &c->indptr, &c->mol_rows, &c->min_read, &c->rep_raw, &c->summary, &c->fastq_text, &c->fastq_tmp,
-                   &c->ls_slots};
+                   &c->ls_slots, &c->mol_idx, &c->mol_sort, &c->mol_sort_alt};
   for (auto* b : all) b->release();
   for (auto& p : c->phases) {
     cudaEventDestroy(p.second.first);
@@ -520,6 +521,8 @@ int crgpu_reads_add(crgpu_ctx* c, int lib, const crgpu_read_batch* rb, int* out_
     b->feature = d.is_feature_barcode ? nullptr : rb->feature;
     b->r2_seq = d.is_feature_barcode ? rb->r2_seq : nullptr;
     b->r2_qual = d.is_feature_barcode ? rb->r2_qual : nullptr;
+    b->select = reinterpret_cast<const unsigned long long*>(rb->select_key);
+    b->h_select = nullptr;
   } else {
     int rc;
     size_t sb = (size_t)rb->n * rb->r1_len;
@@ -553,9 +556,17 @@ int crgpu_reads_add(crgpu_ctx* c, int lib, const crgpu_read_batch* rb, int* out_
       b->h_r2_seq = rb->r2_seq;
       b->h_r2_qual = rb->r2_qual;
     }
+    b->select = nullptr;
+    b->h_select = nullptr;
+    if (rb->select_key) {
+      ENSURE_OR_RETURN(b->own_select.ensure((size_t)rb->n * 8 + 16));
+      b->select = b->own_select.as<unsigned long long>();
+      b->h_select = reinterpret_cast<const unsigned long long*>(rb->select_key);
+    }
 #undef ENSURE_OR_RETURN
     b->host_pending = rb->n > 0;
   }
+  if (b->select) c->have_select = true;
   c->n_reads += rb->n;
   c->batches.push_back(b);
   c->stage = 0;
@@ -616,6 +627,7 @@ int crgpu_reads_clear(crgpu_ctx* c) {
   c->n_reads = 0;
   c->stage = 0;
   c->annotated = false;
+  c->have_select = false;
   return CRGPU_OK;
 }
 
@@ -712,6 +724,9 @@ int crgpu_pass1(crgpu_ctx* c) {
         CU(cudaMemcpyAsync(b->own_qual.as<uint8_t>() + off, b->h_r1_qual + off, bytes, cudaMemcpyHostToDevice, c->copy_stream));
         if (!is_fb)
           CU(cudaMemcpyAsync(b->own_feat.as<uint32_t>() + first, b->h_feature + first, (size_t)cn * 4,
+                             cudaMemcpyHostToDevice, c->copy_stream));
+        if (b->h_select)
+          CU(cudaMemcpyAsync(b->own_select.as<unsigned long long>() + first, b->h_select + first, (size_t)cn * 8,
                              cudaMemcpyHostToDevice, c->copy_stream));
         cudaEvent_t ev = c->copy_ev[k & 1];
         CU(cudaEventRecord(ev, c->copy_stream));
@@ -1259,6 +1274,7 @@ int crgpu_count(crgpu_ctx* c) {
   if ((rc = c->key2.ensure(cap * 8))) return rc;
   if ((rc = c->key2_alt.ensure(cap * 8))) return rc;
   if ((rc = c->mol.ensure(cap * 4))) return rc;
+  if ((rc = c->mol_idx.ensure(cap * 4))) return rc;
   if ((rc = c->ent_rank.ensure(cap * 4))) return rc;
   if ((rc = c->ent_feature.ensure(cap * 4))) return rc;
   if ((rc = c->ent_count.ensure(cap * 4))) return rc;
@@ -1305,6 +1321,7 @@ int crgpu_count(crgpu_ctx* c) {
   b.ent_feature = c->ent_feature.as<uint32_t>();
   b.ent_count = c->ent_count.as<uint32_t>();
   b.mol = c->mol.as<uint32_t>();
+  b.mol_idx = c->mol_idx.as<uint32_t>();
   b.cap = cap;
   uint64_t m = 0;
   {
@@ -1382,7 +1399,7 @@ int crgpu_annotate_reads(crgpu_ctx* c) {
   const uint64_t m = c->n_distinct;
   if ((rc = c->umi_proc.ensure(c->n_reads * 4 + 16))) return rc;
   if ((rc = c->flags.ensure(c->n_reads + 16))) return rc;
-  if ((rc = c->min_read.ensure(std::max<uint64_t>(m, 1) * 4))) return rc;
+  if ((rc = c->min_read.ensure(std::max<uint64_t>(m, 1) * 8))) return rc;  // UmiSelectKey word per distinct key
   if ((rc = c->rep_raw.ensure(std::max<uint64_t>(m, 1) * 4))) return rc;
   DedupBuffers b;
   memset(&b, 0, sizeof(b));
@@ -1390,7 +1407,7 @@ int crgpu_annotate_reads(crgpu_ctx* c) {
   b.dkeys = c->dkeys.as<unsigned long long>();
   b.best = c->best.as<uint32_t>();
   b.low = c->low.as<uint8_t>();
-  c->launches += run_annotate_prepare(b, m, c->min_read.as<uint32_t>(), c->rep_raw.as<uint32_t>(), c->stream);
+  c->launches += run_annotate_prepare(b, m, c->min_read.as<unsigned long long>(), c->rep_raw.as<uint32_t>(), c->stream);
   for (int pass = 0; pass < 2; pass++) {
     for (auto* bt : c->batches) {
       Library* l = c->libs[bt->lib];
@@ -1404,11 +1421,12 @@ int crgpu_annotate_reads(crgpu_ctx* c) {
       a.flags_out = c->flags.as<uint8_t>() + bt->base;
       a.lib = (uint32_t)bt->lib;
       a.read_base = bt->base;
+      a.select = bt->select;
       if (pass == 0)
-        c->launches += run_annotate_min(b, m, a, c->min_read.as<uint32_t>(), c->stream);
+        c->launches += run_annotate_min(b, m, a, c->min_read.as<unsigned long long>(), c->stream);
       else
-        c->launches += run_annotate_final(b, m, a, c->min_read.as<uint32_t>(), c->rep_raw.as<uint32_t>(), nullptr,
-                                          c->stream);
+        c->launches += run_annotate_final(b, m, a, c->min_read.as<unsigned long long>(), c->rep_raw.as<uint32_t>(),
+                                          nullptr, c->stream);
       CHECK_KERNEL();
     }
   }
@@ -1591,21 +1609,57 @@ int crgpu_molecules_count(crgpu_ctx* c, uint64_t* n) {
   return CRGPU_OK;
 }
 
-int crgpu_molecules_get(crgpu_ctx* c, uint32_t* out5) {
-  if (!c || !out5) return fail(CRGPU_E_INVALID, "bad argument");
+int crgpu_molecules_get(crgpu_ctx* c, uint32_t* out6) {
+  if (!c || !out6) return fail(CRGPU_E_INVALID, "bad argument");
   if (c->stage < 3) return fail(CRGPU_E_INVALID, "crgpu_count must run first");
   if (!c->n_mol) return CRGPU_OK;
+  if (c->have_select && !c->annotated)
+    return fail(CRGPU_E_INVALID, "a batch carries select keys: UmiCount::utype is the type of the representative read, "
+                                 "crgpu_annotate_reads must run before crgpu_molecules_get");
   CU(cudaSetDevice(c->device));
   int rc;
-  if ((rc = c->mol_rows.ensure(c->n_mol * 20))) return rc;
+  if ((rc = c->mol_rows.ensure(c->n_mol * 24))) return rc;
+  // UmiCount sorts by (library_idx, feature_idx, umi) inside a barcode; the keys carry the feature above the
+  // library. The two orders agree when every library's features lie above those of the libraries before it (one
+  // library; GEX genes first and a feature-barcode library behind them): otherwise the rows are re-sorted.
+  int reorder = 0;
+  for (size_t l1 = 0; l1 < c->libs.size(); l1++)  // two libraries over the same features: feature-major != library-major
+    for (size_t l2 = l1 + 1; l2 < c->libs.size(); l2++) {
+      const crgpu_library_def &d1 = c->libs[l1]->def, &d2 = c->libs[l2]->def;
+      if ((d1.is_feature_barcode ? d1.feature_type : 0) == (d2.is_feature_barcode ? d2.feature_type : 0)) reorder = 1;
+    }
+  if (c->libs.size() > 1 && !reorder) {
+    int last_lib = -1;
+    for (int f = 0; f < c->n_features && !reorder; f++) {
+      int lib_of = -1;
+      for (size_t l = 0; l < c->libs.size(); l++) {
+        const crgpu_library_def& d = c->libs[l]->def;
+        if ((d.is_feature_barcode ? d.feature_type : 0) == c->feature_type[f]) lib_of = (int)l;
+      }
+      if (lib_of < 0) continue;
+      if (lib_of < last_lib) reorder = 1;
+      last_lib = std::max(last_lib, lib_of);
+    }
+  }
+  if (reorder) {
+    if ((rc = c->mol_sort.ensure(c->n_mol * 8 + 16))) return rc;
+    if ((rc = c->mol_sort_alt.ensure(c->n_mol * 8 + 16))) return rc;
+    if ((rc = c->sort_temp.ensure(sort_temp_bytes(c->n_mol)))) return rc;
+  }
   DedupBuffers b;
   memset(&b, 0, sizeof(b));
   b.kl = c->kl;
   b.key2 = c->key2.as<unsigned long long>();
   b.mol = c->mol.as<uint32_t>();
-  c->launches += run_molecule_rows(b, c->col_of_rank.as<uint32_t>(), c->n_mol, c->mol_rows.as<uint32_t>(), c->stream);
+  b.mol_idx = c->mol_idx.as<uint32_t>();
+  const bool typed = c->have_select && c->annotated;
+  c->launches += run_molecule_rows(b, c->col_of_rank.as<uint32_t>(), c->n_mol,
+                                   typed ? c->min_read.as<unsigned long long>() : nullptr,
+                                   typed ? c->rep_raw.as<uint32_t>() : nullptr, reorder,
+                                   c->mol_sort.as<unsigned long long>(), c->mol_sort_alt.as<unsigned long long>(),
+                                   c->sort_temp.p, c->sort_temp.cap, c->mol_rows.as<uint32_t>(), c->stream);
   CHECK_KERNEL();
-  CU(cudaMemcpyAsync(out5, c->mol_rows.p, c->n_mol * 20, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(out6, c->mol_rows.p, c->n_mol * 24, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return CRGPU_OK;
 }

@@ -81,6 +81,9 @@ struct Batch {
   bool host_pending = false;
   const uint8_t *h_r1_seq = nullptr, *h_r1_qual = nullptr, *h_r2_seq = nullptr, *h_r2_qual = nullptr;
   const uint32_t* h_feature = nullptr;
+  const unsigned long long* h_select = nullptr;
+  const unsigned long long* select = nullptr;  // device: UmiSelectKey word per read, or nullptr
+  DevBuf own_select;
   const uint8_t *r1_seq = nullptr, *r1_qual = nullptr, *r2_seq = nullptr, *r2_qual = nullptr;
   const uint32_t* feature = nullptr;  // device pointers (borrowed or owned)
   DevBuf own_seq, own_qual, own_feat, own_r2s, own_r2q;
@@ -142,6 +145,8 @@ struct crgpu_ctx {
   // dedup
   DevBuf dkeys, c0, best, inc, low, key2, key2_alt, lb_desc, tickets, scalars, ent_rank, ent_feature, ent_count, mol;
   DevBuf col_of_rank, barcode_rank, indptr, mol_rows, min_read, rep_raw, ls_slots, summary, fastq_text, fastq_tmp;
+  DevBuf mol_idx, mol_sort, mol_sort_alt;  // distinct-key index of each molecule; scratch of the row reordering
+  bool have_select = false;                // some batch carries UmiSelectKey words
   uint64_t n_distinct = 0, n_mol = 0, nnz = 0, n_barcodes = 0;
   uint32_t own_lo = 0, own_hi = 0xFFFFFFFFu;
   bool annotated = false;

@@ -835,8 +835,8 @@ __global__ void __launch_bounds__(256) low_support_kernel(const unsigned long lo
 __global__ void __launch_bounds__(CP_THREADS) molecules_compact_kernel(
     const unsigned long long* __restrict__ dkeys, const uint32_t* __restrict__ c0, const uint32_t* __restrict__ best,
     const unsigned long long* __restrict__ inc, const uint8_t* __restrict__ low, uint64_t m,
-    unsigned long long* __restrict__ mol_key, uint32_t* __restrict__ mol_reads, unsigned long long* desc,
-    uint32_t* ticket, unsigned long long* total_out, unsigned long long* low_reads_out) {
+    unsigned long long* __restrict__ mol_key, uint32_t* __restrict__ mol_reads, uint32_t* __restrict__ mol_idx,
+    unsigned long long* desc, uint32_t* ticket, unsigned long long* total_out, unsigned long long* low_reads_out) {
   __shared__ uint32_t scan_s[CP_THREADS / 32 + 1];
   __shared__ unsigned long long bcast;
   __shared__ uint32_t tile_s;
@@ -888,6 +888,7 @@ __global__ void __launch_bounds__(CP_THREADS) molecules_compact_kernel(
   const CpPlace pl = cp_place(cnt, tile, n_tiles, desc, total_out, scan_s, &bcast);
   __shared__ unsigned long long st_k[CP_TILE];
   __shared__ uint32_t st_r[CP_TILE];
+  __shared__ uint16_t st_i[CP_TILE];  // position of the molecule's distinct key inside the tile
   uint32_t o = pl.off;
 #pragma unroll
   for (int i = 0; i < CP_ITEMS; i++)
@@ -895,12 +896,15 @@ __global__ void __launch_bounds__(CP_THREADS) molecules_compact_kernel(
       const uint64_t j = first + i;
       st_k[o] = dkeys[j];
       st_r[o] = (uint32_t)((b[i] == (uint32_t)j ? c0[j] : 0u) + (in[i] & INC_READS_MASK));
+      st_i[o] = (uint16_t)(threadIdx.x * CP_ITEMS + i);
       o++;
     }
   __syncthreads();
+  const uint64_t tile_first = (uint64_t)tile * CP_TILE;
   for (uint32_t i = threadIdx.x; i < pl.total; i += CP_THREADS) {
     mol_key[pl.excl + i] = st_k[i];
     mol_reads[pl.excl + i] = st_r[i];
+    if (mol_idx) mol_idx[pl.excl + i] = (uint32_t)(tile_first + st_i[i]);
   }
 }
 
@@ -1427,8 +1431,8 @@ int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
     cudaMemsetAsync(ss.desc, 0, tiles * 8, st);
     cudaMemsetAsync(ss.ticket, 0, 4, st);
     molecules_compact_kernel<<<(unsigned)tiles, CP_THREADS, 0, st>>>(b.dkeys, b.c0, b.best, b.inc, b.low, m, b.key2,
-                                                                    b.mol, ss.desc, tile_ticket(ss.ticket), b.scalars + 2,
-                                                                    b.scalars + 6);
+                                                                    b.mol, b.mol_idx, ss.desc, tile_ticket(ss.ticket),
+                                                                    b.scalars + 2, b.scalars + 6);
     launches++;
   }
   return launches;
@@ -1502,18 +1506,68 @@ __global__ void __launch_bounds__(THREADS) inclusive_scan_i64_kernel(long long* 
   }
 }
 
+// UmiType of a molecule as molecule_info stores it (1 Txomic, 0 NonTxomic): the type of its representative read,
+// i.e. bit 63 of the smallest UmiSelectKey word of the representative raw key (rep_raw, or the key itself)
+__device__ __forceinline__ uint32_t molecule_utype(uint32_t d, const unsigned long long* __restrict__ min_key,
+                                                   const uint32_t* __restrict__ rep_raw) {
+  if (!min_key) return 1u;
+  const uint32_t r = rep_raw[d] == 0xFFFFFFFFu ? d : rep_raw[d];
+  return (min_key[r] >> 63) ? 0u : 1u;
+}
+
 __global__ void molecules_kernel(const unsigned long long* __restrict__ mol_key, const uint32_t* __restrict__ mol_reads,
-                                 uint64_t n_mol, KeyLayout kl, const uint32_t* __restrict__ col_of_rank,
-                                 uint32_t* __restrict__ out5) {
+                                 const uint32_t* __restrict__ mol_idx, uint64_t n_mol, KeyLayout kl,
+                                 const uint32_t* __restrict__ col_of_rank, const unsigned long long* __restrict__ min_key,
+                                 const uint32_t* __restrict__ rep_raw, uint32_t* __restrict__ out6) {
   const FieldMasks fm = field_masks(kl);
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_mol; i += (uint64_t)gridDim.x * blockDim.x) {
     unsigned long long k = mol_key[i];
     uint32_t rank = (uint32_t)(k >> kl.rank_shift);
-    out5[5 * i + 0] = col_of_rank[rank];
-    out5[5 * i + 1] = (uint32_t)((k >> kl.lib_shift) & ((1ull << fm.lbits) - 1ull));
-    out5[5 * i + 2] = (uint32_t)((k >> kl.feature_shift) & ((1ull << fm.fbits) - 1ull));
-    out5[5 * i + 3] = (uint32_t)(k & ((1ull << fm.ubits) - 1ull));
-    out5[5 * i + 4] = mol_reads[i];
+    out6[6 * i + 0] = col_of_rank[rank];
+    out6[6 * i + 1] = (uint32_t)((k >> kl.lib_shift) & ((1ull << fm.lbits) - 1ull));
+    out6[6 * i + 2] = (uint32_t)((k >> kl.feature_shift) & ((1ull << fm.fbits) - 1ull));
+    out6[6 * i + 3] = (uint32_t)(k & ((1ull << fm.ubits) - 1ull));
+    out6[6 * i + 4] = mol_reads[i];
+    out6[6 * i + 5] = mol_idx ? molecule_utype(mol_idx[i], min_key, rep_raw) : 1u;
+  }
+}
+
+// (rank | feature | library | umi) <-> (rank | library | feature | umi): the order UmiCount sorts in
+__device__ __forceinline__ unsigned long long key_lib_major(unsigned long long k, const KeyLayout& kl, const FieldMasks& fm) {
+  const unsigned long long umi = k & ((1ull << fm.ubits) - 1ull);
+  const unsigned long long lib = (k >> kl.lib_shift) & ((1ull << fm.lbits) - 1ull);
+  const unsigned long long feat = (k >> kl.feature_shift) & ((1ull << fm.fbits) - 1ull);
+  const unsigned long long rank = k >> kl.rank_shift;
+  return (((rank << fm.lbits | lib) << fm.fbits | feat) << fm.ubits) | umi;
+}
+__global__ void molecules_remap_kernel(const unsigned long long* __restrict__ mol_key, uint64_t n_mol, KeyLayout kl,
+                                       unsigned long long* __restrict__ out) {
+  const FieldMasks fm = field_masks(kl);
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_mol; i += (uint64_t)gridDim.x * blockDim.x)
+    out[i] = key_lib_major(mol_key[i], kl, fm);
+}
+// rows from the re-sorted (library-major) keys: each finds its molecule by binary search in the key-ordered table
+__global__ void molecules_reordered_kernel(const unsigned long long* __restrict__ sorted_lm,
+                                           const unsigned long long* __restrict__ mol_key,
+                                           const uint32_t* __restrict__ mol_reads, const uint32_t* __restrict__ mol_idx,
+                                           uint64_t n_mol, KeyLayout kl, const uint32_t* __restrict__ col_of_rank,
+                                           const unsigned long long* __restrict__ min_key,
+                                           const uint32_t* __restrict__ rep_raw, uint32_t* __restrict__ out6) {
+  const FieldMasks fm = field_masks(kl);
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_mol; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long lm = sorted_lm[i];
+    const unsigned long long umi = lm & ((1ull << fm.ubits) - 1ull);
+    const unsigned long long feat = (lm >> fm.ubits) & ((1ull << fm.fbits) - 1ull);
+    const unsigned long long lib = (lm >> (fm.ubits + fm.fbits)) & ((1ull << fm.lbits) - 1ull);
+    const unsigned long long rank = lm >> (fm.ubits + fm.fbits + fm.lbits);
+    const unsigned long long k = (rank << kl.rank_shift) | (feat << kl.feature_shift) | (lib << kl.lib_shift) | umi;
+    const uint64_t j = lower_bound_u64(mol_key, n_mol, k);
+    out6[6 * i + 0] = col_of_rank[(uint32_t)rank];
+    out6[6 * i + 1] = (uint32_t)lib;
+    out6[6 * i + 2] = (uint32_t)feat;
+    out6[6 * i + 3] = (uint32_t)umi;
+    out6[6 * i + 4] = mol_reads[j];
+    out6[6 * i + 5] = mol_idx ? molecule_utype(mol_idx[j], min_key, rep_raw) : 1u;
   }
 }
 
@@ -1673,19 +1727,30 @@ int launch_diversity(const uint32_t* counts, uint64_t n, unsigned long long* out
   return 1;
 }
 
-int run_molecule_rows(DedupBuffers& b, const uint32_t* col_of_rank, uint64_t n_mol, uint32_t* out5, cudaStream_t st) {
+int run_molecule_rows(DedupBuffers& b, const uint32_t* col_of_rank, uint64_t n_mol, const unsigned long long* min_key,
+                      const uint32_t* rep_raw, int reorder, unsigned long long* sort_a, unsigned long long* sort_b,
+                      void* sort_temp, size_t sort_temp_bytes, uint32_t* out6, cudaStream_t st) {
   if (!n_mol) return 0;
-  molecules_kernel<<<grid_for(n_mol), 256, 0, st>>>(b.key2, b.mol, n_mol, b.kl, col_of_rank, out5);
-  return 1;
+  if (!reorder) {
+    molecules_kernel<<<grid_for(n_mol), 256, 0, st>>>(b.key2, b.mol, b.mol_idx, n_mol, b.kl, col_of_rank, min_key, rep_raw,
+                                                      out6);
+    return 1;
+  }
+  molecules_remap_kernel<<<grid_for(n_mol), 256, 0, st>>>(b.key2, n_mol, b.kl, sort_a);
+  unsigned long long* sorted = nullptr;
+  int launches = 1 + sort_keys(sort_a, sort_b, n_mol, b.kl.total_bits, sort_temp, sort_temp_bytes, &sorted, st);
+  molecules_reordered_kernel<<<grid_for(n_mol), 256, 0, st>>>(sorted, b.key2, b.mol, b.mol_idx, n_mol, b.kl, col_of_rank,
+                                                              min_key, rep_raw, out6);
+  return launches + 1;
 }
 
 // ---------------------------------------------------------------------------
 // per-read DupInfo (optional): BarcodeDupMarker::process (mark_dups.rs:280-363)
 // ---------------------------------------------------------------------------
-__global__ void annotate_prepare_kernel(const uint32_t* __restrict__ best, uint64_t m, uint32_t* __restrict__ min_read,
-                                        uint32_t* __restrict__ rep_raw) {
+__global__ void annotate_prepare_kernel(const uint32_t* __restrict__ best, uint64_t m,
+                                        unsigned long long* __restrict__ min_key, uint32_t* __restrict__ rep_raw) {
   for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < m; j += (uint64_t)gridDim.x * blockDim.x) {
-    min_read[j] = 0xFFFFFFFFu;
+    min_key[j] = ~0ull;
     rep_raw[j] = 0xFFFFFFFFu;
   }
 }
@@ -1708,19 +1773,25 @@ __device__ __forceinline__ bool read_key(const AnnotateArgs& a, const KeyLayout&
   return true;
 }
 
+// UmiSelectKey word of read i: the caller's, or (Txomic, qname ordered like the global read index)
+__device__ __forceinline__ unsigned long long select_word(const AnnotateArgs& a, uint64_t i) {
+  return a.select ? a.select[i] : (unsigned long long)(a.read_base + i);
+}
+
+// the smallest UmiSelectKey of every raw key: old_min.min(ann_key), mark_dups.rs:147-151
 __global__ void annotate_min_kernel(const unsigned long long* __restrict__ dkeys, uint64_t m, KeyLayout kl,
-                                    AnnotateArgs a, uint32_t* __restrict__ min_read) {
+                                    AnnotateArgs a, unsigned long long* __restrict__ min_key) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < a.n; i += (uint64_t)gridDim.x * blockDim.x) {
     unsigned long long key;
     if (!read_key(a, kl, i, &key)) continue;
     uint64_t j = lower_bound_u64(dkeys, m, key);
-    atomicMin(min_read + j, (uint32_t)(a.read_base + i));
+    atomicMin(min_key + j, select_word(a, i));
   }
 }
 
 __global__ void annotate_final_kernel(const unsigned long long* __restrict__ dkeys, uint64_t m, KeyLayout kl,
                                       AnnotateArgs a, const uint32_t* __restrict__ best,
-                                      const uint8_t* __restrict__ low, const uint32_t* __restrict__ min_read,
+                                      const uint8_t* __restrict__ low, const unsigned long long* __restrict__ min_key,
                                       const uint32_t* __restrict__ rep_raw) {
   const unsigned long long umask = (1ull << kl.umi_bits) - 1ull;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < a.n; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -1733,7 +1804,10 @@ __global__ void annotate_final_kernel(const unsigned long long* __restrict__ dke
       bool corrected = d != (uint32_t)j;
       bool is_low = low[d] != 0;
       uint32_t rep = rep_raw[d] == 0xFFFFFFFFu ? d : rep_raw[d];
-      bool is_rep = rep == (uint32_t)j && min_read[j] == (uint32_t)(a.read_base + i);
+      // is_min_qname: the read's header equals the qname of the corrected key's UmiSelectKey (mark_dups.rs:300-303);
+      // the key's select key is the one of raw key `rep` (:248-268), and only its own reads can carry that qname
+      const unsigned long long q63 = 0x7FFFFFFFFFFFFFFFull;
+      bool is_rep = rep == (uint32_t)j && (min_key[j] & q63) == (select_word(a, i) & q63);
       fl |= 2u | (corrected ? 4u : 0u) | (is_low ? 8u : 0u) | ((!is_low && is_rep) ? 16u : 0u);
       uw = (uw & ~UMI_SEQ_MASK) | (uint32_t)(dkeys[d] & umask);
     }
@@ -1742,21 +1816,21 @@ __global__ void annotate_final_kernel(const unsigned long long* __restrict__ dke
   }
 }
 
-int run_annotate_prepare(DedupBuffers& b, uint64_t m, uint32_t* min_read, uint32_t* rep_raw, cudaStream_t st) {
+int run_annotate_prepare(DedupBuffers& b, uint64_t m, unsigned long long* min_key, uint32_t* rep_raw, cudaStream_t st) {
   if (!m) return 0;
-  annotate_prepare_kernel<<<grid_for(m), 256, 0, st>>>(b.best, m, min_read, rep_raw);
+  annotate_prepare_kernel<<<grid_for(m), 256, 0, st>>>(b.best, m, min_key, rep_raw);
   annotate_rep_kernel<<<grid_for(m), 256, 0, st>>>(b.best, m, rep_raw);
   return 2;
 }
-int run_annotate_min(DedupBuffers& b, uint64_t m, const AnnotateArgs& a, uint32_t* min_read, cudaStream_t st) {
+int run_annotate_min(DedupBuffers& b, uint64_t m, const AnnotateArgs& a, unsigned long long* min_key, cudaStream_t st) {
   if (!a.n || !m) return 0;
-  annotate_min_kernel<<<grid_for(a.n, 256, 32), 256, 0, st>>>(b.dkeys, m, b.kl, a, min_read);
+  annotate_min_kernel<<<grid_for(a.n, 256, 32), 256, 0, st>>>(b.dkeys, m, b.kl, a, min_key);
   return 1;
 }
-int run_annotate_final(DedupBuffers& b, uint64_t m, const AnnotateArgs& a, const uint32_t* min_read,
+int run_annotate_final(DedupBuffers& b, uint64_t m, const AnnotateArgs& a, const unsigned long long* min_key,
                        const uint32_t* rep_raw, unsigned long long*, cudaStream_t st) {
   if (!a.n) return 0;
-  annotate_final_kernel<<<grid_for(a.n, 256, 32), 256, 0, st>>>(b.dkeys, m, b.kl, a, b.best, b.low, min_read,
+  annotate_final_kernel<<<grid_for(a.n, 256, 32), 256, 0, st>>>(b.dkeys, m, b.kl, a, b.best, b.low, min_key,
                                                                      rep_raw);
   return 1;
 }

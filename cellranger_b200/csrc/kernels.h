@@ -159,7 +159,8 @@ struct DedupBuffers {
   uint32_t* ent_feature;  // [cap]
   uint32_t* ent_count;    // [cap]
   // molecules: read count (c2) of each; their keys end up in key2
-  uint32_t* mol;  // [cap]
+  uint32_t* mol;      // [cap]
+  uint32_t* mol_idx;  // [cap] index of each molecule in the distinct-key table (nullptr: not kept)
   uint64_t cap;
 };
 int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st);
@@ -194,6 +195,7 @@ int launch_state_counts(const uint32_t* bc_out, uint64_t n, unsigned long long* 
 
 struct AnnotateArgs {
   uint64_t n;
+  const unsigned long long* select;  // UmiSelectKey word per read, or nullptr (= the global read index, Txomic)
   const uint32_t* bc_out;
   const uint32_t* umi_out;  // raw packed UMI words
   uint32_t* umi_proc;       // out: processed (corrected) UMI words
@@ -202,12 +204,20 @@ struct AnnotateArgs {
   uint32_t lib;
   uint64_t read_base;  // global index of read 0 of this batch
 };
-int run_molecule_rows(DedupBuffers& b, const uint32_t* col_of_rank, uint64_t n_mol, uint32_t* out5, cudaStream_t st);
+// UmiCount rows {column, library, feature, umi, read_count, umi_type}. min_key / rep_raw: the per-distinct-key
+// tables of the annotation (nullptr: every molecule Txomic). reorder != 0: the rows are re-sorted into
+// (barcode, library, feature, umi) order through sort_a / sort_b (n_mol keys each) - needed only when the key
+// order (feature above library) is not already that order.
+int run_molecule_rows(DedupBuffers& b, const uint32_t* col_of_rank, uint64_t n_mol, const unsigned long long* min_key,
+                      const uint32_t* rep_raw, int reorder, unsigned long long* sort_a, unsigned long long* sort_b,
+                      void* sort_temp, size_t sort_temp_bytes, uint32_t* out6, cudaStream_t st);
 int run_barcode_summary(DedupBuffers& b, uint64_t n_distinct, uint32_t lib, const uint32_t* barcode_rank,
                         const uint32_t* valid, const uint32_t* col_of_rank, uint64_t n_bc, uint32_t* out4, cudaStream_t st);
-int run_annotate_prepare(DedupBuffers& b, uint64_t n_distinct, uint32_t* min_read, uint32_t* rep_raw, cudaStream_t st);
-int run_annotate_min(DedupBuffers& b, uint64_t n_distinct, const AnnotateArgs& a, uint32_t* min_read, cudaStream_t st);
-int run_annotate_final(DedupBuffers& b, uint64_t n_distinct, const AnnotateArgs& a, const uint32_t* min_read,
+int run_annotate_prepare(DedupBuffers& b, uint64_t n_distinct, unsigned long long* min_key, uint32_t* rep_raw,
+                         cudaStream_t st);
+int run_annotate_min(DedupBuffers& b, uint64_t n_distinct, const AnnotateArgs& a, unsigned long long* min_key,
+                     cudaStream_t st);
+int run_annotate_final(DedupBuffers& b, uint64_t n_distinct, const AnnotateArgs& a, const unsigned long long* min_key,
                        const uint32_t* rep_raw, unsigned long long* read_stats, cudaStream_t st);
 
 // ---- synth (synth.cu) ----

@@ -109,6 +109,14 @@ typedef struct crgpu_read_batch {
   const uint8_t* r2_seq;
   const uint8_t* r2_qual;
   int32_t on_device;
+  /* optional (NULL: every read is UmiType::Txomic and its qname orders like its index in the context):
+   * UmiSelectKey{utype, qname} of each read (tx_annotation/src/mark_dups.rs:110-114) as one order-preserving word -
+   * bit 63 = 1 for UmiType::NonTxomic (Txomic < NonTxomic, umi/src/lib.rs:101-107), bits 0..62 = the rank of the
+   * read's qname among the qnames of the GEM well (any strictly order-preserving map of the header bytes; equal
+   * headers - the mates of one pair - get equal words). The read with the smallest word stands for its
+   * (UMI, feature): DupInfo::is_umi_count, and UmiCount::utype of the molecule. Same memory space as the other
+   * arrays of the batch. */
+  const uint64_t* select_key;
 } crgpu_read_batch;
 int crgpu_reads_add(crgpu_ctx* ctx, int library, const crgpu_read_batch* batch, int* out_batch);
 /* FASTQ front end: the read loop of MAKE_SHARD slices barcode / UMI ranges out of FASTQ records
@@ -318,10 +326,14 @@ int crgpu_barcode_summary(crgpu_ctx* ctx, int library, uint32_t* out);
  * metric/src/histogram.rs:161-171). After a sharded run the counts are the global ones on every rank. */
 int crgpu_barcode_diversity(crgpu_ctx* ctx, int library, uint64_t* barcodes_detected, double* effective_diversity);
 
-/* UmiCount rows (cr_types/src/types.rs:148-160), sorted by (barcode, library, feature, umi):
- * out5[5*i..] = {barcode column index, library, feature, umi 2-bit, read_count} */
+/* UmiCount rows (cr_types/src/types.rs:148-160) in the order ALIGN_AND_COUNT hands them to molecule_info: by
+ * barcode, and inside a barcode as umi_counts.sort() leaves them (stages/align_and_count.rs:314) - library_idx,
+ * feature_idx, umi, read_count. out6[6*i..] = {barcode column index, library_idx, feature_idx, umi 2-bit,
+ * read_count, umi_type as molecule_info stores it (UmiType::to_u32: 1 = Txomic, 0 = NonTxomic)}; probe_idx is
+ * None on this path (no probe alignments). umi_type is that of the representative read, so when a batch
+ * carries select keys crgpu_annotate_reads must have run; without select keys every molecule is Txomic. */
 int crgpu_molecules_count(crgpu_ctx* ctx, uint64_t* n);
-int crgpu_molecules_get(crgpu_ctx* ctx, uint32_t* out5);
+int crgpu_molecules_get(crgpu_ctx* ctx, uint32_t* out6);
 
 /* ---- Synthetic workload generator (bench / tests; see cellranger_b200/synth.py) ---- */
 typedef struct crgpu_synth_params {

@@ -107,6 +107,7 @@ struct CountMatrix {  // feature x barcode, CSC: one column per valid barcode, s
 
 struct UmiCount {
   uint32_t barcode_column, library_idx, feature_idx, umi /* 2 bit / base */, read_count;
+  uint32_t umi_type;  // as molecule_info stores it: 1 = Txomic, 0 = NonTxomic
 };
 
 struct BarcodeSummary {
@@ -191,7 +192,7 @@ class GemWell {
   // host arrays: r1_seq / r1_qual = n * r1_len ASCII, feature = gene index per read (CRGPU_NO_FEATURE = unmapped)
   int add_reads(int library, uint64_t n, int r1_len, const uint8_t* r1_seq, const uint8_t* r1_qual,
                 const uint32_t* feature, int r2_len = 0, const uint8_t* r2_seq = nullptr,
-                const uint8_t* r2_qual = nullptr) {
+                const uint8_t* r2_qual = nullptr, const uint64_t* select_key = nullptr) {
     crgpu_read_batch b;
     std::memset(&b, 0, sizeof(b));
     b.n = n;
@@ -202,6 +203,7 @@ class GemWell {
     b.r2_len = r2_len;
     b.r2_seq = r2_seq;
     b.r2_qual = r2_qual;
+    b.select_key = select_key;  // UmiSelectKey{utype, qname} per read as one word, or nullptr
     int id = -1;
     check(crgpu_reads_add(ctx_, library, &b, &id), "crgpu_reads_add");
     batch_sizes_.push_back(n);
@@ -251,10 +253,11 @@ class GemWell {
   std::vector<UmiCount> molecules() {
     uint64_t n = 0;
     check(crgpu_molecules_count(ctx_, &n), "crgpu_molecules_count");
-    std::vector<uint32_t> raw(n * 5);
+    std::vector<uint32_t> raw(n * 6);
     if (n) check(crgpu_molecules_get(ctx_, raw.data()), "crgpu_molecules_get");
     std::vector<UmiCount> out(n);
-    for (uint64_t i = 0; i < n; i++) out[i] = {raw[5 * i], raw[5 * i + 1], raw[5 * i + 2], raw[5 * i + 3], raw[5 * i + 4]};
+    for (uint64_t i = 0; i < n; i++)
+      out[i] = {raw[6 * i], raw[6 * i + 1], raw[6 * i + 2], raw[6 * i + 3], raw[6 * i + 4], raw[6 * i + 5]};
     return out;
   }
   // rows for the barcodes with at least one read in `library`, in barcode order

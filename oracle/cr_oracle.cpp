@@ -265,9 +265,8 @@ static std::unordered_set<UG, UGHash> determine_low_support(const UGCounts& coun
   return low;
 }
 
-// UmiSelectKey{utype, qname}: every synthetic read is UmiType::Txomic and the
-// qname is the fixed-width decimal global read index, so the key order is the
-// read-index order (mark_dups.rs:110-152).
+// UmiSelectKey{utype, qname} (mark_dups.rs:110-152) as the order-preserving word Ctx::select_key holds per read
+// (without caller-supplied keys: every read Txomic, the qname ordered like the global read index).
 typedef std::unordered_map<UG, uint64_t, UGHash> UGMinKey;
 
 // BarcodeDupMarker — mark_dups.rs:183-364
@@ -449,7 +448,7 @@ struct ReadOut {
 };
 
 struct Molecule {
-  uint32_t bc_idx, lib, feature, umi, read_count;
+  uint32_t bc_idx, lib, feature, umi, read_count, utype;  // utype as UmiType::to_u32: 1 Txomic, 0 NonTxomic
 };
 
 struct Ctx {
@@ -459,6 +458,10 @@ struct Ctx {
   std::vector<int> feature_type;  // per feature: owning feature-type id (0 = gene)
   std::vector<Batch> batches;
   uint64_t n_reads = 0;
+  // UmiSelectKey per read (mark_dups.rs:110-114) as one order-preserving word: bit 63 = UmiType (0 Txomic <
+  // 1 NonTxomic, the derive(Ord) order of umi/src/lib.rs:101-107), low bits = the rank of the qname. Empty: every
+  // read is Txomic and its qname orders like its global read index.
+  std::vector<uint64_t> select_key;
   double threshold = 0.975;
   double max_expected_errors = 1.7976931348623157e308;  // f64::MAX, corrector.rs:104-106
   bool filter_umis = true;                              // lib/rust/cr_lib/src/aligner.rs:270
@@ -595,6 +598,7 @@ struct BcResult {
 static void process_barcode(Ctx& c, const std::vector<uint64_t>& reads, const std::vector<int>& read_lib,
                             BcResult* res) {
   std::map<int, DupMarker> marker;  // keyed by library type
+  auto select_key = [&](uint64_t g) { return c.select_key.empty() ? g : c.select_key[g]; };
   for (size_t k = 0; k < reads.size(); k++) {
     uint64_t g = reads[k];
     const ReadOut& o = c.out[g];
@@ -602,23 +606,25 @@ static void process_barcode(Ctx& c, const std::vector<uint64_t>& reads, const st
       DupMarker& m = marker[read_lib[k]];
       UG key{c.umi_out[g], o.feature};
       m.counts[key] += 1;
+      const uint64_t sk = select_key(g);  // old_min.min(ann_key), mark_dups.rs:147-151
       auto it = m.min_key.find(key);
       if (it == m.min_key.end())
-        m.min_key.emplace(key, g);
+        m.min_key.emplace(key, sk);
       else
-        it->second = std::min(it->second, g);
+        it->second = std::min(it->second, sk);
     } else {
       marker[read_lib[k]];  // dup_builder.entry(lib).or_default()
     }
   }
   for (auto& kv : marker) kv.second.build(c.filter_umis, c.libs[kv.first].umi_correction);
-  struct UC {
-    uint32_t lib, feature, umi, read_count;
+  struct UC {  // UmiCount, ordered as its derive(Ord) orders it (cr_types/src/types.rs:152-160)
+    uint32_t lib, feature, umi, read_count, utype_ord;  // utype_ord: 0 Txomic < 1 NonTxomic
     bool operator<(const UC& o) const {
       if (lib != o.lib) return lib < o.lib;
       if (feature != o.feature) return feature < o.feature;
       if (umi != o.umi) return umi < o.umi;
-      return read_count < o.read_count;
+      if (read_count != o.read_count) return read_count < o.read_count;
+      return utype_ord < o.utype_ord;
     }
   };
   std::vector<UC> umi_counts;
@@ -633,7 +639,9 @@ static void process_barcode(Ctx& c, const std::vector<uint64_t>& reads, const st
     bool is_corrected = ci != m.corrections.end();
     UG ck{corrected, raw.gene};
     bool low = m.low_support.count(ck) > 0;
-    bool is_min = m.min_key.at(ck) == g;
+    // is_min_qname compares the header with the qname of the key's UmiSelectKey (mark_dups.rs:300-303)
+    const uint64_t sk = select_key(g);
+    bool is_min = (m.min_key.at(ck) & 0x7FFFFFFFFFFFFFFFull) == (sk & 0x7FFFFFFFFFFFFFFFull);
     uint64_t rc = m.counts.at(ck);
     bool is_umi_count = !low && is_min;
     o.has_dup = 1;
@@ -642,13 +650,16 @@ static void process_barcode(Ctx& c, const std::vector<uint64_t>& reads, const st
     o.is_umi_count = is_umi_count;
     o.read_count = (uint32_t)rc;
     c.umi_out[g] = corrected;
-    if (is_umi_count) umi_counts.push_back(UC{(uint32_t)read_lib[k], raw.gene, encode_2bit_u32(corrected), (uint32_t)rc});
+    // umi_type is the one of the read that carries the count (mark_dups.rs:322-326)
+    if (is_umi_count)
+      umi_counts.push_back(UC{(uint32_t)read_lib[k], raw.gene, encode_2bit_u32(corrected), (uint32_t)rc, (uint32_t)(sk >> 63)});
   }
   std::sort(umi_counts.begin(), umi_counts.end());
   std::map<uint32_t, uint32_t> fc;
   for (auto& u : umi_counts) fc[u.feature] += 1;
   res->feature_counts.assign(fc.begin(), fc.end());
-  for (auto& u : umi_counts) res->molecules.push_back(Molecule{0, u.lib, u.feature, u.umi, u.read_count});
+  for (auto& u : umi_counts)
+    res->molecules.push_back(Molecule{0, u.lib, u.feature, u.umi, u.read_count, u.utype_ord ? 0u : 1u});
 }
 
 static void count_stage(Ctx& c, int threads) {
@@ -796,6 +807,7 @@ void cro_reset_reads(void* p) {
   c.out.clear();
   c.bc_content.clear();
   c.umi_out.clear();
+  c.select_key.clear();
   for (auto& l : c.libs) {
     l.prior.clear();
     l.corrected_counts.clear();
@@ -884,15 +896,22 @@ void cro_matrix_get(void* p, int bc_len, uint8_t* barcodes, int64_t* indptr, uin
   }
 }
 uint64_t cro_n_molecules(void* p) { return ((Ctx*)p)->molecules.size(); }
-void cro_molecules_get(void* p, uint32_t* out5) {
+// rows in the order ALIGN_AND_COUNT emits them: by barcode, then umi_counts.sort() (align_and_count.rs:314)
+void cro_molecules_get(void* p, uint32_t* out6) {
   Ctx& c = *(Ctx*)p;
   for (size_t k = 0; k < c.molecules.size(); k++) {
-    out5[5 * k + 0] = c.molecules[k].bc_idx;
-    out5[5 * k + 1] = c.molecules[k].lib;
-    out5[5 * k + 2] = c.molecules[k].feature;
-    out5[5 * k + 3] = c.molecules[k].umi;
-    out5[5 * k + 4] = c.molecules[k].read_count;
+    out6[6 * k + 0] = c.molecules[k].bc_idx;
+    out6[6 * k + 1] = c.molecules[k].lib;
+    out6[6 * k + 2] = c.molecules[k].feature;
+    out6[6 * k + 3] = c.molecules[k].umi;
+    out6[6 * k + 4] = c.molecules[k].read_count;
+    out6[6 * k + 5] = c.molecules[k].utype;
   }
+}
+// one UmiSelectKey word per read, in the order the reads were added (n must equal the read count); n = 0 clears
+void cro_set_select_keys(void* p, const uint64_t* keys, uint64_t n) {
+  Ctx& c = *(Ctx*)p;
+  c.select_key.assign(keys, keys + n);
 }
 
 // ---- single-function entry points for the reference's known-answer tests ----

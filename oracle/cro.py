@@ -200,10 +200,17 @@ class Oracle:
         return dict(barcodes=barcodes, indptr=indptr, indices=indices, data=data)
 
     def molecules(self) -> np.ndarray:
+        """UmiCount rows in the order ALIGN_AND_COUNT emits them (by barcode, then umi_counts.sort()):
+        (barcode column, library_idx, feature_idx, umi 2-bit, read_count, umi_type as in molecule_info)."""
         n = int(self.L.cro_n_molecules(self.ctx))
-        out = np.zeros((n, 5), dtype=np.uint32)
+        out = np.zeros((n, 6), dtype=np.uint32)
         self.L.cro_molecules_get(self.ctx, _p(out))
         return out
+
+    def set_select_keys(self, keys):
+        """UmiSelectKey per read as one word: bit 63 = 1 for NonTxomic, low bits = rank of the qname."""
+        k = np.ascontiguousarray(keys, dtype=np.uint64)
+        self.L.cro_set_select_keys(self.ctx, _p(k), C.c_uint64(k.shape[0]))
 
 
 # ---- single-function known-answer entry points ----

@@ -32,10 +32,26 @@ def test_library_builds_and_exports_every_symbol():
     assert not missing, f"symbols declared in crgpu.h but not exported: {missing}"
 
 
-def test_struct_sizes_match_header():
-    # crgpu_library_def: 10 x int32; crgpu_read_batch: see header
+def test_struct_sizes_match_header(tmp_path):
+    """The ctypes mirrors of the ABI structs against what a C compiler makes of include/crgpu.h (size and the
+    offset of every pointer field)."""
+    import subprocess
+
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "crgpu.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(crgpu_library_def), '
+                   'sizeof(crgpu_read_batch), offsetof(crgpu_read_batch, r1_seq), offsetof(crgpu_read_batch, feature), '
+                   'offsetof(crgpu_read_batch, r2_seq), offsetof(crgpu_read_batch, on_device), '
+                   'offsetof(crgpu_read_batch, select_key), sizeof(crgpu_synth_params)); return 0; }\n')
+    exe = tmp_path / "layout"
+    res = subprocess.run(["gcc", "-std=c99", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
+    rb = _lib.ReadBatch
+    assert got == [C.sizeof(_lib.LibraryDef), C.sizeof(rb), rb.r1_seq.offset, rb.feature.offset, rb.r2_seq.offset,
+                   rb.on_device.offset, rb.select_key.offset, C.sizeof(_lib.SynthParams)]
     assert C.sizeof(_lib.LibraryDef) == 40
-    assert C.sizeof(_lib.ReadBatch) == 8 + 8 + 8 * 3 + 8 + 8 * 2 + 8
 
 
 def test_no_cpu_fallback_without_device():

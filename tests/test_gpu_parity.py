@@ -443,6 +443,110 @@ def test_barcode_correction_metrics_match_oracle_counts():
     gw.close()
 
 
+def test_select_keys_choose_the_representative_read_and_the_umi_type():
+    """UmiSelectKey{utype, qname} (tx_annotation/src/mark_dups.rs:110-152,248-268,300-326) through
+    crgpu_read_batch.select_key: random qname ranks and a random Txomic / NonTxomic bit per read. The representative
+    read of every molecule (is_umi_count) and UmiCount::utype must follow the smallest (utype, qname), not the
+    read index."""
+    import cellranger_b200 as cb
+
+    prob = helpers.make_problem("cfg1", 120_000, n_whitelist=20_000, n_cells=30)
+    g = prob["gex"]
+    n = prob["n_gex"]
+    rng = np.random.default_rng(42)
+    keys = rng.permutation(n).astype(np.uint64) | (rng.integers(0, 2, size=n).astype(np.uint64) << np.uint64(63))
+    o = helpers.run_oracle(prob, stages=False)
+    o.set_select_keys(keys)
+    o.run(4)
+    cfg, t = prob["cfg"], prob["tables"]
+    gw = cb.GemWell()
+    wl = gw.add_whitelist(cb.Whitelist.plain(t.whitelist))
+    lib = gw.add_library(wl, cb.ChemistryDef(cfg.name, 0, cfg.bc_len, cfg.bc_len, cfg.umi_len))
+    gw.set_feature_reference(cb.FeatureReference(cfg.n_genes))
+    gw.add_reads(lib, g["r1_seq"], g["r1_qual"], g["feature"], select_key=keys)
+    gw.make_shard()
+    gw.barcode_correction()
+    gw.align_and_count()
+    with pytest.raises(cb.CrgpuError, match="crgpu_annotate_reads"):
+        gw.molecules()  # umi_type needs the representative reads
+    gw.align_and_count(annotate_reads=True)
+    info = helpers.compare_all(o, gw, prob)
+    mol = gw.molecules()
+    assert 0 < int((mol[:, 5] == 0).sum()) < len(mol)  # both types occur
+    # and it differs from the default choice (lowest read index) somewhere
+    ref = helpers.run_gpu(prob)
+    assert not np.array_equal(ref.reads(0)["flags"], gw.reads(0)["flags"])
+    assert np.array_equal(ref.count_matrix().data, gw.count_matrix().data)  # the matrix does not depend on it
+    assert info["molecules"] == len(mol)
+    ref.close()
+    gw.close()
+
+
+def test_molecule_rows_are_library_major_when_libraries_are_not_in_feature_order():
+    """UmiCount sorts by library_idx before feature_idx (cr_types/src/types.rs:152-160). Here the Antibody Capture
+    library is library 0 although its features are the LAST rows of the matrix, so the key order (feature above
+    library) is not the row order: the rows must come out re-sorted, exactly as the oracle's umi_counts.sort()."""
+    import cellranger_b200 as cb
+    from oracle import cro
+
+    prob = helpers.make_problem("cfg4", 120_000, n_whitelist=50_000, n_cells=60)
+    cfg, t = prob["cfg"], prob["tables"]
+    ftype, fb_seqs = helpers.feature_tables(prob)
+    g, f = prob["gex"], prob["fb"]
+    o = cro.Oracle()
+    wl_fb = o.add_whitelist(t.trans, trans=t.whitelist)
+    lib_fb = o.add_library(wl_fb, 0, cfg.bc_len, cfg.bc_len, cfg.umi_len, umi_correction=True, is_fb=True, ftype=1,
+                           fb_offset=cfg.fb_offset, fb_len=cfg.fb_len)
+    wl_gex = o.add_whitelist(t.whitelist)
+    lib_gex = o.add_library(wl_gex, 0, cfg.bc_len, cfg.bc_len, cfg.umi_len)
+    o.set_features(ftype, fb_seqs)
+    o.add_reads(lib_fb, f["r1_seq"], f["r1_qual"], None, f["r2_seq"], f["r2_qual"])
+    o.add_reads(lib_gex, g["r1_seq"], g["r1_qual"], g["feature"])
+    o.run(4)
+    gw = cb.GemWell()
+    # the first whitelist defines the content space: the translation whitelist maps onto the plain one's sequences
+    w_fb = gw.add_whitelist(cb.Whitelist.trans(t.trans, t.whitelist))
+    chem = cb.ChemistryDef(cfg.name, 0, cfg.bc_len, cfg.bc_len, cfg.umi_len)
+    l_fb = gw.add_library(w_fb, chem, umi_correction=True, feature_type=1, fb_offset=cfg.fb_offset, fb_length=cfg.fb_len)
+    w_gex = gw.add_whitelist(cb.Whitelist.plain(t.whitelist))
+    l_gex = gw.add_library(w_gex, chem)
+    fr = cb.FeatureReference(cfg.n_genes)
+    for i in range(cfg.n_fb_features):
+        fr.add_feature_barcode(f"FB{i}", bytes(t.fb_seqs[i]).decode(), 1, "5P" + "N" * cfg.fb_offset + "(BC)")
+    gw.set_feature_reference(fr)
+    gw.add_reads(l_fb, f["r1_seq"], f["r1_qual"], None, f["r2_seq"], f["r2_qual"])
+    gw.add_reads(l_gex, g["r1_seq"], g["r1_qual"], g["feature"])
+    gw.run(annotate_reads=True)
+    a, b = o.molecules(), gw.molecules()
+    assert a.shape == b.shape and len(a) > 1000
+    assert np.array_equal(a, b), "UmiCount rows: values or order"
+    # library-major inside a barcode: somewhere a row of library 1 with a LOWER feature follows a row of library 0
+    same_bc = b[1:, 0] == b[:-1, 0]
+    assert np.any(same_bc & (b[1:, 1] > b[:-1, 1]) & (b[1:, 2] < b[:-1, 2]))
+    mo, mg = o.matrix(), gw.count_matrix()
+    assert np.array_equal(mo["indptr"], mg.indptr) and np.array_equal(mo["indices"], mg.indices)
+    assert np.array_equal(mo["data"], mg.data)
+    gw.close()
+
+
+def test_finish_sort_path_matches_oracle(monkeypatch):
+    """CRGPU_FINISH_SORT=1: radix sort on the bits above the UMI only, UMI bits sorted per segment in shared memory
+    (pairwise / bucketed / pre-sorted long segments) fused with the run-length encoding. Same results as the default
+    path on a case with short, medium (hundreds of reads) and long (tens of thousands) segments."""
+    monkeypatch.setenv("CRGPU_FINISH_SORT", "1")
+    monkeypatch.setenv("CRGPU_VERIFY", "1")
+    for name, n, kw in (("cfg5", 600_000, {"n_whitelist": 100_000, "n_cells": 6}), ("cfg2", 400_000, {"n_whitelist": 200_000, "n_cells": 40}),
+                        ("cfg1", 3000, {"n_whitelist": 5000, "n_cells": 10})):
+        prob = helpers.make_problem(name, n, **kw)
+        o = helpers.run_oracle(prob, threads=8)
+        gw = helpers.run_gpu(prob)
+        helpers.compare_all(o, gw, prob)
+        st = gw.stats()
+        assert st["sort_violations"] == 0 and st["rle_violations"] == 0
+        gw.close()
+        o.close()
+
+
 def test_barcode_diversity_matches_histogram_formula():
     """barcodes_detected / effective_barcode_diversity of BARCODE_CORRECTION's join (barcode_correction.rs:428-441):
     (sum c)^2 / sum c^2 over the corrected barcode histogram, here from the oracle's raw-valid + corrected counts
