@@ -677,6 +677,107 @@ class GemWell:
         return out
 
 
+MAX_READS_BARCODE_COMPATIBILITY = 1_000_000   # check_barcodes_compatibility.rs:79
+MIN_BARCODE_SIMILARITY = 0.1                  # lib/bin/parameters.toml
+
+
+class WhitelistHistogram:
+    """A device histogram over the entries of one whitelist (sorted raw sequences), filled by
+    sample_valid_barcodes (cr_lib/src/stages/check_barcodes_compatibility.rs:98-120)."""
+
+    def __init__(self, gw: "GemWell", whitelist: int):
+        self.gw, self.whitelist = gw, whitelist
+        n = C.c_uint64()
+        check(gw.L.crgpu_whitelist_entries(gw.ctx, whitelist, C.byref(n)), "crgpu_whitelist_entries")
+        self.n = int(n.value)
+        p = C.c_void_p()
+        check(gw.L.crgpu_dev_alloc(gw.ctx, C.c_uint64(max(self.n, 1) * 4), C.byref(p)), "crgpu_dev_alloc")
+        self.dev = p.value
+        check(gw.L.crgpu_dev_memset(gw.ctx, C.c_void_p(self.dev), 0, C.c_uint64(self.n * 4)), "crgpu_dev_memset")
+        self.reads = 0
+        self.reads_in_whitelist = 0
+
+    def observe(self, seqs, bc_offset: int = 0) -> int:
+        """seqs: (n, stride) uint8 ASCII records holding the barcode at bc_offset. At most
+        MAX_READS_BARCODE_COMPATIBILITY reads are looked at in total, as in the reference. Returns the reads matched."""
+        a = ascii_matrix(seqs)
+        room = MAX_READS_BARCODE_COMPATIBILITY - self.reads
+        a = np.ascontiguousarray(a[:max(room, 0)])
+        if a.shape[0] == 0:
+            return 0
+        m = C.c_uint64()
+        check(self.gw.L.crgpu_sample_valid_barcodes(self.gw.ctx, self.whitelist, ptr(a), C.c_uint64(a.shape[0]),
+                                                    int(a.shape[1]), int(bc_offset), 0, C.c_void_p(self.dev),
+                                                    C.byref(m)), "crgpu_sample_valid_barcodes")
+        self.reads += a.shape[0]
+        self.reads_in_whitelist += int(m.value)
+        return int(m.value)
+
+    def fraction(self) -> float:
+        """WhitelistMatchStats::fraction (detect_chemistry/whitelist_filter.rs:61-110): matched / reads with a barcode."""
+        return self.reads_in_whitelist / self.reads if self.reads else 0.0
+
+    def counts(self) -> np.ndarray:
+        return self.gw.read_device(self.dev, (self.n,), np.uint32)
+
+    def nx(self, fraction: float) -> int:
+        out = C.c_uint32()
+        check(self.gw.L.crgpu_hist_nx(self.gw.ctx, C.c_void_p(self.dev), C.c_uint64(self.n), C.c_double(fraction),
+                                      C.byref(out)), "crgpu_hist_nx")
+        return int(out.value)
+
+    def robust_cosine_similarity(self, other: "WhitelistHistogram", translate_whitelist: int = -1) -> float:
+        out = C.c_double()
+        check(self.gw.L.crgpu_robust_cosine_similarity(self.gw.ctx, C.c_void_p(self.dev), C.c_void_p(other.dev),
+                                                       C.c_uint64(self.n), int(translate_whitelist), C.byref(out)),
+              "crgpu_robust_cosine_similarity")
+        return float(out.value)
+
+    def close(self):
+        if self.dev:
+            self.gw.L.crgpu_dev_free(self.gw.ctx, C.c_void_p(self.dev))
+            self.dev = 0
+
+
+def check_barcodes_compatibility(gw: "GemWell", plain_whitelist: int, translation_whitelist: Optional[int],
+                                 gex_reads, other_reads: dict, bc_offset: int = 0, check_library_compatibility=True,
+                                 min_barcode_similarity: float = MIN_BARCODE_SIMILARITY) -> dict:
+    """CHECK_BARCODES_COMPATIBILITY's main for two or more library types (check_barcodes_compatibility.rs:161-262):
+    gel-bead barcode histograms of the Gene Expression reads and of every other library type's reads against the
+    plain whitelist, robust cosine similarity with and without translation, `libraries_to_translate`, and the
+    insufficient-overlap error. gex_reads / other_reads[name]: (n, stride) ASCII read arrays (or lists of them)."""
+    def hist_of(reads):
+        h = WhitelistHistogram(gw, plain_whitelist)
+        for part in (reads if isinstance(reads, (list, tuple)) else [reads]):
+            h.observe(part, bc_offset)
+        return h
+
+    gex = hist_of(gex_reads)
+    out = {"libraries_to_translate": [], "similarity": {}, "gex_fraction_in_whitelist": gex.fraction()}
+    try:
+        for name, reads in other_reads.items():
+            h = hist_of(reads)
+            try:
+                sim = gex.robust_cosine_similarity(h)
+                rec = {"without_translation": sim, "with_translation": None, "fraction_in_whitelist": h.fraction()}
+                if translation_whitelist is not None:
+                    tsim = gex.robust_cosine_similarity(h, translation_whitelist)
+                    rec["with_translation"] = tsim
+                    if tsim > sim:  # :243-246
+                        out["libraries_to_translate"].append(name)
+                        sim = tsim
+                rec["similarity"] = sim
+                out["similarity"][name] = rec
+                if check_library_compatibility and not sim >= min_barcode_similarity:  # :248-253
+                    raise ValueError(f"Barcodes from the [Gene Expression] library and the [{name}] library have "
+                                     f"insufficient overlap (similarity {sim:.4f} < {min_barcode_similarity}).")
+            finally:
+                h.close()
+    finally:
+        gex.close()
+    return out
+
+
 class BarcodeCorrector:
     """BarcodeCorrector::new(whitelist, bc_counts, strategy) — barcode/src/corrector.rs:15-71 — in batch
     form: correct_barcodes() takes many invalid (or unchecked) segments at once."""

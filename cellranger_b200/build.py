@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libcrgpu.so")
-SOURCES = ["crgpu.cu", "shard.cu", "pass_kernels.cu", "sort.cu", "dedup_kernels.cu", "finish_kernels.cu", "synth.cu", "fastq.cu", "mex_writer.cpp"]
+SOURCES = ["crgpu.cu", "shard.cu", "pass_kernels.cu", "sort.cu", "dedup_kernels.cu", "finish_kernels.cu", "compat.cu", "synth.cu", "fastq.cu", "mex_writer.cpp"]
 HEADERS = ["common.cuh", "kernels.h", "ctx.h", "nccl_dl.h", os.path.join(ROOT, "include", "crgpu.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -335,6 +335,31 @@ int crgpu_barcode_diversity(crgpu_ctx* ctx, int library, uint64_t* barcodes_dete
 int crgpu_molecules_count(crgpu_ctx* ctx, uint64_t* n);
 int crgpu_molecules_get(crgpu_ctx* ctx, uint32_t* out6);
 
+/* ---- Other users of the resident whitelist ----
+ * CHECK_BARCODES_COMPATIBILITY (cr_lib/src/stages/check_barcodes_compatibility.rs:98-262) and the whitelist match
+ * rate of chemistry detection (cr_lib/src/detect_chemistry/whitelist_filter.rs:61-110,162-193). Both look every
+ * read's barcode up with Whitelist::match_to_whitelist (barcode/src/whitelist.rs:526-545): an exact hit, or - for a
+ * barcode with exactly one N - the first of A,C,G,T at that position that gives a hit.
+ *
+ * crgpu_sample_valid_barcodes: sample_valid_barcodes(). seqs = n records of `stride` bytes with the barcode at
+ * bc_offset (host, or device with on_device != 0); dev_hist = device uint32[crgpu_whitelist_entries] (from
+ * crgpu_dev_alloc, zeroed with crgpu_dev_memset) indexed by the entry's position in the sorted raw sequences of
+ * `whitelist`, ACCUMULATED into (several FASTQs of one library type merge, :197-204); *n_in_whitelist = matched
+ * reads of this call, so n_in_whitelist / n is WhitelistMatchStats::fraction(). The caller stops at
+ * MAX_READS_BARCODE_COMPATIBILITY = 1 000 000 reads as the reference does (:79,114).
+ * crgpu_hist_nx: stats::nx::nx (stats/src/nx.rs:6-38) over the non-zero counts; 0 for an empty histogram.
+ * crgpu_robust_cosine_similarity: robust_cosine_similarity(a, b) (:122-158) with counts capped at their N92.5;
+ * translate_whitelist >= 0 maps b's keys through that translation whitelist first (this_hist.map_key(translate),
+ * :241-242; the plain whitelist must be the context's first whitelist). A library is to be translated when the
+ * translated similarity is the larger one (:243-246); the caller compares with min_barcode_similarity (0.1). */
+int crgpu_whitelist_entries(crgpu_ctx* ctx, int whitelist, uint64_t* n_entries);
+int crgpu_dev_memset(crgpu_ctx* ctx, void* dev, int value, uint64_t bytes);
+int crgpu_sample_valid_barcodes(crgpu_ctx* ctx, int whitelist, const uint8_t* seqs, uint64_t n, int32_t stride,
+                                int32_t bc_offset, int on_device, uint32_t* dev_hist, uint64_t* n_in_whitelist);
+int crgpu_hist_nx(crgpu_ctx* ctx, const uint32_t* dev_hist, uint64_t n, double fraction, uint32_t* out);
+int crgpu_robust_cosine_similarity(crgpu_ctx* ctx, const uint32_t* dev_hist_a, const uint32_t* dev_hist_b, uint64_t n,
+                                   int translate_whitelist, double* out);
+
 /* ---- Synthetic workload generator (bench / tests; see cellranger_b200/synth.py) ---- */
 typedef struct crgpu_synth_params {
   uint64_t seed_mix, seed_mol;
