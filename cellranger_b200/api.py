@@ -330,40 +330,78 @@ class GemWell:
         return out.value
 
     def add_reads_device(self, library: int, n: int, r1_len: int, r1_seq: int, r1_qual: int, feature: int = 0,
-                         r2_len: int = 0, r2_seq: int = 0, r2_qual: int = 0) -> int:
+                         r2_len: int = 0, r2_seq: int = 0, r2_qual: int = 0, select_key: int = 0) -> int:
         """Device pointers (ints), borrowed until clear_reads()."""
         rb = ReadBatch()
         rb.n, rb.r1_len, rb.r1_seq, rb.r1_qual = n, r1_len, r1_seq, r1_qual
         rb.feature = feature or None
         rb.r2_len, rb.r2_seq, rb.r2_qual = r2_len, r2_seq or None, r2_qual or None
+        rb.select_key = select_key or None
         rb.on_device = 1
         out = C.c_int(-1)
         check(self.L.crgpu_reads_add(self._ctx, library, C.byref(rb), C.byref(out)), "crgpu_reads_add")
         self._batches.append((library, n))
         return out.value
 
-    def add_fastq(self, library: int, r1_fastq, feature=None, read_len: Optional[int] = None) -> dict:
-        """One chunk of uncompressed R1 FASTQ text (bytes or uint8 array, whole 4-line records) as a read batch:
-        crgpu_fastq_extract slices the first `read_len` bases / qualities of every record on the device
-        (RnaProcessor::process_read, cr_types/src/rna_read.rs:363-467), `feature` (uint32 per record, from
-        the aligner) goes along as in add_reads. Returns {batch, n_records, n_short, n_malformed}."""
-        text = np.frombuffer(r1_fastq, dtype=np.uint8) if isinstance(r1_fastq, (bytes, bytearray, memoryview)) \
-            else np.ascontiguousarray(r1_fastq, dtype=np.uint8)
-        d = self._libs[library]
-        rl = int(read_len or max(d.bc_offset + d.bc_length, d.umi_offset + d.umi_length))
+    @staticmethod
+    def _fastq_bytes(fastq) -> np.ndarray:
+        """FASTQ text as a uint8 array; gzip members (.fastq.gz, magic 1f 8b) are inflated on the host first, as the
+        reference's readers do (fastq_set over flate2) - decompression is outside the accelerated path."""
+        if isinstance(fastq, (bytes, bytearray, memoryview)):
+            raw = bytes(fastq)
+            if raw[:2] == b"\x1f\x8b":
+                import gzip
+
+                raw = gzip.decompress(raw)
+            return np.frombuffer(raw, dtype=np.uint8)
+        a = np.ascontiguousarray(fastq, dtype=np.uint8)
+        if a.shape[0] >= 2 and a[0] == 0x1F and a[1] == 0x8B:
+            import gzip
+
+            return np.frombuffer(gzip.decompress(a.tobytes()), dtype=np.uint8)
+        return a
+
+    def _fastq_to_device(self, text: np.ndarray, read_len: int):
         cap = int(np.count_nonzero(text == 10) // 4 + 1)
         dev = []
         for _ in range(2):
             p = C.c_void_p()
-            check(self.L.crgpu_dev_alloc(self._ctx, C.c_uint64(cap * rl + 16), C.byref(p)), "crgpu_dev_alloc")
+            check(self.L.crgpu_dev_alloc(self._ctx, C.c_uint64(cap * read_len + 16), C.byref(p)), "crgpu_dev_alloc")
             dev.append(p.value)
         n_rec, n_short, n_bad = C.c_uint64(), C.c_uint64(), C.c_uint64()
-        check(self.L.crgpu_fastq_extract(self._ctx, ptr(text), C.c_uint64(text.shape[0]), 0, rl, C.c_void_p(dev[0]),
+        check(self.L.crgpu_fastq_extract(self._ctx, ptr(text), C.c_uint64(text.shape[0]), 0, read_len, C.c_void_p(dev[0]),
                                          C.c_void_p(dev[1]), C.c_uint64(cap), C.byref(n_rec), C.byref(n_short),
                                          C.byref(n_bad)), "crgpu_fastq_extract")
-        n = int(n_rec.value)
-        fdev = 0
-        if feature is not None:
+        return dev, int(n_rec.value), int(n_short.value), int(n_bad.value)
+
+    def add_fastq(self, library: int, r1_fastq, feature=None, read_len: Optional[int] = None, r2_fastq=None,
+                  select_key=None) -> dict:
+        """One chunk of R1 FASTQ text (bytes or uint8 array, whole 4-line records; plain or gzip) as a read batch:
+        crgpu_fastq_extract slices the first `read_len` bases / qualities of every record on the device
+        (RnaProcessor::process_read, cr_types/src/rna_read.rs:363-467). A gene-expression library gets `feature`
+        (uint32 per record, from the aligner) as in add_reads; a feature-barcode library gets `r2_fastq`, the R2
+        chunk of the same read pairs, whose first fb_offset + fb_length cycles hold the capture sequence
+        (FeatureExtractor::match_read, cr_types/src/reference/feature_extraction.rs:358-471).
+        Returns {batch, n_records, n_short, n_malformed, ...}."""
+        d = self._libs[library]
+        text = self._fastq_bytes(r1_fastq)
+        rl = int(read_len or max(d.bc_offset + d.bc_length, d.umi_offset + d.umi_length))
+        dev, n, n_short, n_bad = self._fastq_to_device(text, rl)
+        self._dev_owned.extend(dev)
+        info = {"n_records": n, "n_short": n_short, "n_malformed": n_bad, "read_len": rl, "dev_seq": dev[0],
+                "dev_qual": dev[1]}
+        fdev, r2_len, r2s, r2q = 0, 0, 0, 0
+        if d.is_feature_barcode:
+            if r2_fastq is None:
+                raise ValueError("a feature-barcode library needs the R2 FASTQ of the read pairs")
+            r2_len = int(d.fb_offset + d.fb_length)
+            dev2, n2, short2, bad2 = self._fastq_to_device(self._fastq_bytes(r2_fastq), r2_len)
+            self._dev_owned.extend(dev2)
+            if n2 != n:
+                raise ValueError(f"{n} R1 records but {n2} R2 records: the two files are not the same read pairs")
+            r2s, r2q = dev2
+            info.update(r2_len=r2_len, n_short_r2=short2, n_malformed_r2=bad2, dev_r2_seq=r2s, dev_r2_qual=r2q)
+        elif feature is not None:
             f = np.ascontiguousarray(feature, dtype=np.uint32)
             if f.shape[0] != n:
                 raise ValueError(f"{n} FASTQ records but {f.shape[0]} feature assignments")
@@ -371,11 +409,19 @@ class GemWell:
             check(self.L.crgpu_dev_alloc(self._ctx, C.c_uint64(max(n, 1) * 4), C.byref(p)), "crgpu_dev_alloc")
             check(self.L.crgpu_memcpy_h2d(self._ctx, p, ptr(f), C.c_uint64(f.nbytes)), "crgpu_memcpy_h2d")
             fdev = p.value
-            dev.append(fdev)
-        self._dev_owned.extend(dev)
-        batch = self.add_reads_device(library, n, rl, dev[0], dev[1], fdev)
-        return {"batch": batch, "n_records": n, "n_short": int(n_short.value), "n_malformed": int(n_bad.value),
-                "read_len": rl, "dev_seq": dev[0], "dev_qual": dev[1]}
+            self._dev_owned.append(fdev)
+        sdev = 0
+        if select_key is not None:
+            k = np.ascontiguousarray(select_key, dtype=np.uint64)
+            if k.shape[0] != n:
+                raise ValueError("select_key must have one entry per record")
+            p = C.c_void_p()
+            check(self.L.crgpu_dev_alloc(self._ctx, C.c_uint64(max(n, 1) * 8), C.byref(p)), "crgpu_dev_alloc")
+            check(self.L.crgpu_memcpy_h2d(self._ctx, p, ptr(k), C.c_uint64(k.nbytes)), "crgpu_memcpy_h2d")
+            sdev = p.value
+            self._dev_owned.append(sdev)
+        info["batch"] = self.add_reads_device(library, n, rl, dev[0], dev[1], fdev, r2_len, r2s, r2q, select_key=sdev)
+        return info
 
     def read_device(self, dev: int, shape, dtype=np.uint8) -> np.ndarray:
         """Copy a device array of this context to the host (inspection, tests)."""

@@ -610,6 +610,50 @@ def test_fastq_ingestion_matches_array_ingestion(trailing_newline):
     ref.close()
 
 
+def test_paired_fastq_gz_ingestion_of_a_feature_barcode_library():
+    """a GEX + Antibody Capture run fed from FASTQ text - R1 (gzip) of both libraries and the R2 of
+    the feature-barcode library (the capture sequence comes out of R2's first fb_offset + fb_length cycles on the
+    device) - gives the matrix, and the UmiCount rows, of the same reads handed over as arrays."""
+    import gzip
+
+    import cellranger_b200 as cb
+
+    prob = helpers.make_problem("cfg4", 60_000, n_whitelist=50_000, n_cells=50)
+    cfg, t = prob["cfg"], prob["tables"]
+    g, f = prob["gex"], prob["fb"]
+    ref = helpers.run_gpu(prob, annotate=False)
+    rng = np.random.default_rng(9)
+    gw = cb.GemWell()
+    wl = gw.add_whitelist(cb.Whitelist.plain(t.whitelist))
+    chem = cb.ChemistryDef(cfg.name, 0, cfg.bc_len, cfg.bc_len, cfg.umi_len)
+    lib = gw.add_library(wl, chem)
+    wl2 = gw.add_whitelist(cb.Whitelist.trans(t.trans, t.whitelist))
+    fb_lib = gw.add_library(wl2, chem, umi_correction=True, feature_type=1, fb_offset=cfg.fb_offset, fb_length=cfg.fb_len)
+    fr = cb.FeatureReference(cfg.n_genes)
+    for i in range(cfg.n_fb_features):
+        fr.add_feature_barcode(f"FB{i}", bytes(t.fb_seqs[i]).decode(), 1, "5P" + "N" * cfg.fb_offset + "(BC)")
+    gw.set_feature_reference(fr)
+    i1 = gw.add_fastq(lib, gzip.compress(_fastq_text(g["r1_seq"], g["r1_qual"], rng)), g["feature"])
+    # R2 as the sequencer writes it: longer than the capture region (90 cycles), the rest is cDNA
+    r2_full = np.concatenate([f["r2_seq"], np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=(prob["n_fb"], 65))]], axis=1)
+    q2_full = np.concatenate([f["r2_qual"], np.full((prob["n_fb"], 65), ord("F"), dtype=np.uint8)], axis=1)
+    i2 = gw.add_fastq(fb_lib, gzip.compress(_fastq_text(f["r1_seq"], f["r1_qual"], rng)),
+                      r2_fastq=_fastq_text(r2_full, q2_full, rng, trailing_newline=False))
+    assert (i1["n_records"], i2["n_records"]) == (prob["n_gex"], prob["n_fb"]) and i2["r2_len"] == cfg.fb_offset + cfg.fb_len
+    assert i2["n_short_r2"] == 0 and i2["n_malformed_r2"] == 0
+    assert np.array_equal(gw.read_device(i2["dev_r2_seq"], (prob["n_fb"], i2["r2_len"])), f["r2_seq"][:, :i2["r2_len"]])
+    gw.run()
+    m, m_ref = gw.count_matrix(), ref.count_matrix()
+    assert np.array_equal(m.barcode_rank, m_ref.barcode_rank) and np.array_equal(m.indptr, m_ref.indptr)
+    assert np.array_equal(m.indices, m_ref.indices) and np.array_equal(m.data, m_ref.data)
+    assert np.array_equal(gw.molecules(), ref.molecules())
+    assert int((m.indices >= cfg.n_genes).sum()) > 0  # feature-barcode rows are there
+    with pytest.raises(ValueError, match="R2 FASTQ"):
+        gw.add_fastq(fb_lib, _fastq_text(f["r1_seq"][:10], f["r1_qual"][:10], rng))
+    gw.close()
+    ref.close()
+
+
 def test_fastq_short_and_malformed_records():
     import cellranger_b200 as cb
 
