@@ -111,8 +111,9 @@ def setup_problem(gw, cfg, tables):
     return libs
 
 
-def cpu_oracle_rate(cfg, tables, sample_reads: int, threads: int, steps: int = 1, warmup: int = 0):
-    """reads/s of the CPU restatement (oracle/) on a bounded sample of the same workload."""
+def cpu_oracle_rate(cfg, tables, sample_reads: int, threads: int, steps: int = 1, warmup: int = 0, reads=None):
+    """reads/s of the CPU restatement (oracle/) on a bounded sample of the same workload: the first `sample_reads`
+    reads, handed in (`reads`, already generated) or generated here with the numpy generator."""
     from cellranger_b200 import synth
     from oracle import cro
 
@@ -120,7 +121,8 @@ def cpu_oracle_rate(cfg, tables, sample_reads: int, threads: int, steps: int = 1
     wl = o.add_whitelist(tables.whitelist)
     lib = o.add_library(wl, 0, cfg.bc_len, cfg.bc_len, cfg.umi_len)
     o.set_features(np.zeros(cfg.n_genes, dtype=np.int32))
-    reads = synth.generate_reads(tables, 0, sample_reads, "gex")
+    if reads is None:
+        reads = synth.generate_reads(tables, 0, sample_reads, "gex")
     times = []
     for it in range(warmup + steps):
         o.reset_reads()
@@ -300,7 +302,8 @@ def run_reference(args):
     cfg = synth.preset(name, n_total)
     tables = synth.make_tables(cfg, n_total)
     threads = os.cpu_count() or 1
-    sample = args.cpu_sample
+    # every step runs the whole sample again: bounded so that the driver's --steps 20 --warmup 5 stays within minutes
+    sample = min(args.cpu_sample, 4_000_000)
     rate, sec, st = cpu_oracle_rate(cfg, tables, sample, threads, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "reads/s", "n_gpus": args.gpus,
@@ -458,6 +461,7 @@ def run_ours(args):
 
     # ---------------- end to end through the public API with host buffers (e2e) ----------------
     e2e = None
+    cpu_reads = None
     if not args.no_e2e:
         gw.clear_reads()
         host = {}
@@ -488,6 +492,27 @@ def run_ours(args):
             return m
 
         step_e2e()  # warm-up (allocations of the H2D staging buffers)
+        # the ceiling of this number: the same pinned buffers copied to the device and nothing else, on every rank
+        # at once (PCIe link per GPU; at several GPUs also the host's memory and root complexes)
+        gw.clear_reads()
+        torch.cuda.empty_cache()
+        sinks = {k: torch.empty(a.nbytes, dtype=torch.uint8, device=dev) for k, a in host.items()}
+        srcs = {k: torch.from_numpy(a.reshape(-1).view(np.uint8)) for k, a in host.items()}
+        h2d_ms = []
+        for _ in range(2):
+            barrier()
+            t0 = time.perf_counter()
+            for k in sinks:
+                sinks[k].copy_(srcs[k], non_blocking=True)
+            torch.cuda.synchronize(dev)
+            h2d_ms.append((time.perf_counter() - t0) * 1e3)
+        h2d_only = min(h2d_ms)
+        if dist is not None:
+            t = torch.tensor([h2d_only], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            h2d_only = float(t.item())
+        del sinks, srcs
+        torch.cuda.empty_cache()
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
@@ -499,7 +524,14 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             sec = float(t.item())
         e2e = {"value": n_total / sec, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "steps": e2e_steps, "ms_per_step": sec * 1e3}
+               "steps": e2e_steps, "ms_per_step": sec * 1e3,
+               # the bare host-to-device copy of one step's inputs, all ranks at once, max over ranks: what PCIe and
+               # the host allow; the step overlaps pass 1 with the copy, pass 2 / count / D2H come after it
+               "h2d_only_ms": h2d_only, "h2d_gbs_per_gpu": h2d / h2d_only / 1e6,
+               "frac_of_h2d_ceiling": h2d_only / (sec * 1e3)}
+        if rank == 0 and world == 1 and not args.no_cpu:  # the CPU baseline's sample: the first reads of this very batch
+            ns = min(args.cpu_sample, n_per)
+            cpu_reads = {k: np.array(v[:ns]) for k, v in host.items()}
         for p in keep_ptrs:
             gw.L.crgpu_host_free_pinned(p)
 
@@ -547,9 +579,12 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        rate, sec, _ = cpu_oracle_rate(cfg, tables, args.cpu_sample, threads)
+        ns = args.cpu_sample if cpu_reads is not None else min(args.cpu_sample, 2_000_000)
+        rate, sec, _ = cpu_oracle_rate(cfg, tables, ns, threads, reads=cpu_reads)
         cpu = {"value": rate, "unit": "reads/s", "cores": threads, "kind": "port",
-               "sample": f"first {args.cpu_sample} reads of the workload, {sec:.1f} s on {threads} host threads"}
+               "sample": f"first {ns} reads of the workload, {sec:.1f} s on {threads} host threads",
+               "note": "C++ restatement of the reference's hash-map algorithm (oracle/cr_oracle.cpp), not the Rust "
+                       "crates (no cargo/rustc in this image) and not tuned: a reported baseline only"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
@@ -575,7 +610,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=FULL_READS_PER_GPU, help="reads per GPU (default: the full config)")
-    ap.add_argument("--cpu-sample", type=int, default=2_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=16_000_000,
+                    help="reads of the CPU baseline's sample (about 10-30 s of CPU work at the default)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
