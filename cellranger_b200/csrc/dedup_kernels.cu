@@ -672,6 +672,7 @@ constexpr int LF_THREADS = 512;
 constexpr int LF_TILE = 4096;
 constexpr int LF_MAX_SLOTS = 1 << 18;  // 2 bits each: 64 KB
 constexpr int LF_MIN_SLOTS = 1 << 12;
+constexpr int LF_SUPER = 32768;  // keys whose candidates are collected behind one global atomic
 
 __device__ __forceinline__ uint32_t lf_hash(unsigned long long key, const KeyLayout& kl, const FieldMasks& fm) {
   const unsigned long long umi = key & ((1ull << fm.ubits) - 1ull);
@@ -689,7 +690,8 @@ __global__ void __launch_bounds__(LF_THREADS) ls_filter_kernel(const unsigned lo
                                                                KeyLayout kl, unsigned long long* __restrict__ cand,
                                                                unsigned long long* __restrict__ n_cand) {
   extern __shared__ uint32_t lf_slots[];  // LF_MAX_SLOTS / 16 words
-  __shared__ unsigned long long s_lo, s_hi;
+  __shared__ unsigned long long s_lo, s_hi, s_base;
+  __shared__ uint32_t s_bits[LF_SUPER / 32], s_scan[LF_THREADS / 32 + 1], s_total;
   const FieldMasks fm = field_masks(kl);
   const int tid = threadIdx.x, lane = tid & 31;
   const uint64_t t_lo = (uint64_t)blockIdx.x * LF_TILE;
@@ -745,29 +747,56 @@ __global__ void __launch_bounds__(LF_THREADS) ls_filter_kernel(const unsigned lo
     if (old & bit) atomicOr(&lf_slots[h >> 4], bit << 1);
   }
   __syncthreads();
-  const uint64_t rounds = (range + LF_THREADS - 1) / LF_THREADS;  // warp-uniform trip count: ballots inside
-  for (uint64_t r = 0; r < rounds; r++) {
-    const uint64_t j = lo + r * LF_THREADS + tid;
-    bool hit = false;
-    unsigned long long k = 0ull;
-    if (j < hi) {
-      k = dkeys[j];
-      const uint32_t h = lf_hash(k, kl, fm) & (n_slots - 1u);
-      hit = (lf_slots[h >> 4] >> (2u * (h & 15u) + 1u)) & 1u;
+  // Collect, LF_SUPER keys at a time: hit flags into a bitmap, ONE global atomic for the block's candidates of the
+  // super-chunk (a global atomic per warp of candidates - 2.4 M on one address - was 45 % of this kernel's stalls),
+  // then every thread writes the candidates of its two bitmap words behind the block's prefix.
+  for (uint64_t sc_lo = lo; sc_lo < hi; sc_lo += LF_SUPER) {
+    const uint32_t sc_n = (uint32_t)((hi - sc_lo) < (uint64_t)LF_SUPER ? (hi - sc_lo) : (uint64_t)LF_SUPER);
+    if (tid == 0) s_total = 0u;
+    __syncthreads();
+    for (uint32_t r = 0; r < LF_SUPER / LF_THREADS; r++) {  // warp-uniform trip count: ballots inside
+      const uint32_t o = r * LF_THREADS + tid;
+      bool hit = false;
+      if (o < sc_n) {
+        const uint32_t h = lf_hash(dkeys[sc_lo + o], kl, fm) & (n_slots - 1u);
+        hit = (lf_slots[h >> 4] >> (2u * (h & 15u) + 1u)) & 1u;
+      }
+      const uint32_t mk = __ballot_sync(0xFFFFFFFFu, hit);
+      if (lane == 0) {
+        s_bits[o >> 5] = mk;
+        if (mk) atomicAdd(&s_total, (uint32_t)__popc(mk));
+      }
+      if ((r + 1u) * LF_THREADS >= sc_n) break;  // block-uniform: the rest of the super-chunk is past the range
     }
-    const uint32_t mk = __ballot_sync(0xFFFFFFFFu, hit);
-    if (mk) {
-      unsigned long long base = 0ull;
-      if (lane == 0) base = atomicAdd(n_cand, (unsigned long long)__popc(mk));
-      base = __shfl_sync(0xFFFFFFFFu, base, 0);
-      if (hit) {
-        const unsigned long long umi = k & ((1ull << fm.ubits) - 1ull);
-        const unsigned long long lib = (k >> kl.lib_shift) & ((1ull << fm.lbits) - 1ull);
-        const unsigned long long feat = (k >> kl.feature_shift) & ((1ull << fm.fbits) - 1ull);
-        const unsigned long long rank = k >> kl.rank_shift;
-        cand[base + __popc(mk & ((1u << lane) - 1u))] = (((rank << fm.lbits | lib) << fm.ubits | umi) << fm.fbits) | feat;
+    __syncthreads();
+    if (tid == 0) s_base = s_total ? atomicAdd(n_cand, (unsigned long long)s_total) : 0ull;
+    // exclusive prefix of the candidate counts per pair of bitmap words
+    constexpr int WPT = LF_SUPER / 32 / LF_THREADS;  // 2 words per thread
+    uint32_t wbits[WPT], cnt = 0;
+#pragma unroll
+    for (int k = 0; k < WPT; k++) {
+      const uint32_t w = tid * WPT + k;
+      wbits[k] = w * 32u < sc_n ? s_bits[w] : 0u;
+      cnt += (uint32_t)__popc(wbits[k]);
+    }
+    uint32_t tot;
+    uint32_t off = block_exclusive_scan<LF_THREADS>(cnt, &tot, s_scan);  // syncs: s_base is visible behind it
+    unsigned long long out = s_base + off;
+#pragma unroll
+    for (int k = 0; k < WPT; k++) {
+      uint32_t bits = wbits[k];
+      while (bits) {
+        const uint32_t b = (uint32_t)__ffs(bits) - 1u;
+        bits &= bits - 1u;
+        const unsigned long long key = dkeys[sc_lo + (uint64_t)(tid * WPT + k) * 32u + b];
+        const unsigned long long umi = key & ((1ull << fm.ubits) - 1ull);
+        const unsigned long long lib = (key >> kl.lib_shift) & ((1ull << fm.lbits) - 1ull);
+        const unsigned long long feat = (key >> kl.feature_shift) & ((1ull << fm.fbits) - 1ull);
+        const unsigned long long rank = key >> kl.rank_shift;
+        cand[out++] = (((rank << fm.lbits | lib) << fm.ubits | umi) << fm.fbits) | feat;
       }
     }
+    __syncthreads();
   }
 }
 
