@@ -560,16 +560,19 @@ def run_ours(args):
     if dom:
         k = kern[dom]
         achieved = k["alg_bytes_per_launch"] / (k["ms_per_launch"] * 1e-3) / 1e9
-        # dram__bytes_read+write per launch from the committed ncu --set full capture of the same workload
-        traffic = None
+        # dram__bytes_read+write per launch: ncu cannot run inside this process, so the figure comes from the
+        # committed `ncu --set full` capture of this very workload (same key count, checked) - see traffic_source
+        traffic, traffic_source = None, None
         try:
-            rec = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            rec = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
             if dom in rec and rec.get("_n_keys") == n_keys and world == 1:
                 traffic = rec[dom]["dram_bytes_per_launch"]
+                traffic_source = "profiles/r02_traffic.json <- " + rec.get("_source", "ncu --set full")
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
+                    "peak_source": peak_src,
                     "alg_bytes_per_launch": k["alg_bytes_per_launch"], "ms_per_launch": k["ms_per_launch"],
                     "launches_per_step": k["launches_per_step"],
                     "share_of_step": k["total_ms"] / max(sum(phases.values()), 1e-9)}
