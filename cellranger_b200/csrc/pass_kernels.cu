@@ -848,8 +848,15 @@ int launch_pass1(const Pass1Args& a, int n_sms, cudaStream_t st) {
 // One thread per invalid read: the neighbour mask comes from n_ord bucket scans, then the likelihoods are
 // accumulated strictly in the reference's (position ascending, base A,C,G,T) order with separate f64
 // multiply and add (no FMA), so every accept/reject decision is bit-identical.
+// The kernel is bound by memory latency times occupancy (about 17 L2 sectors per read, a third of them DRAM
+// misses): 32 registers = 8 blocks per SM run it in 2.37 ms where 34 registers = 7 blocks took 2.60 ms. Measured
+// and rejected on B200 (profiles/r02_pass2_sort_experiments.txt): reading the buckets as 16-byte windows or as
+// one 32-byte slot per ordering with a SWAR test and all orderings in flight (fewer loads and sectors, but 64
+// registers: 3.0-3.1 ms); one key-space atomic per warp instead of per block (3.2 ms: the counter's L2 slice
+// serialises a million returning atomics); the side list ordered by barcode prefix (2.99 -> 2.84 ms for four
+// bases: the scans are not the misses that matter).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pass2_kernel(const Pass2Args a) {
+__global__ void __launch_bounds__(256, 8) pass2_kernel(const Pass2Args a) {
   __shared__ uint32_t scan_a[9];
   __shared__ unsigned long long base_bcast;
   const uint64_t n_invalid = a.n_invalid_dev ? (*a.n_invalid_dev >> a.n_invalid_dev_shift) : a.n_invalid;
