@@ -848,15 +848,32 @@ int launch_pass1(const Pass1Args& a, int n_sms, cudaStream_t st) {
 // One thread per invalid read: the neighbour mask comes from n_ord bucket scans, then the likelihoods are
 // accumulated strictly in the reference's (position ascending, base A,C,G,T) order with separate f64
 // multiply and add (no FMA), so every accept/reject decision is bit-identical.
-// The kernel is bound by memory latency times occupancy (about 17 L2 sectors per read, a third of them DRAM
-// misses): 32 registers = 8 blocks per SM run it in 2.37 ms where 34 registers = 7 blocks took 2.60 ms. Measured
-// and rejected on B200 (profiles/r02_pass2_sort_experiments.txt): reading the buckets as 16-byte windows or as
-// one 32-byte slot per ordering with a SWAR test and all orderings in flight (fewer loads and sectors, but 64
-// registers: 3.0-3.1 ms); one key-space atomic per warp instead of per block (3.2 ms: the counter's L2 slice
-// serialises a million returning atomics); the side list ordered by barcode prefix (2.99 -> 2.84 ms for four
-// bases: the scans are not the misses that matter).
+// The kernel is bound by memory latency (about 17 L2 sectors per read, a third of them DRAM misses, 95 % of the
+// warp slots occupied at 32 registers). Measured on B200 and rejected (profiles/r02_pass2_sort_experiments.txt):
+// reading the buckets as 16-byte windows, or as one 32-byte slot per ordering, with a SWAR test and all
+// orderings in flight (fewer loads and sectors but 64 registers: 3.0-3.1 ms against 2.37); one key-space atomic
+// per warp instead of per block (3.2 ms: the counter's L2 slice serialises a million returning atomics); the
+// side list ordered by barcode prefix (2.99 -> 2.84 ms for four bases: locality of the scans is not the limit).
+// This form of the source (posterior state in a struct) also schedules better than the one it replaces
+// (2.37 against 2.60 ms at the same 32 registers).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 8) pass2_kernel(const Pass2Args a) {
+struct Posterior2 {
+  bool have_best = false;
+  double best = 0.0, total = 0.0;
+  uint32_t best_rank = 0;
+  __device__ __forceinline__ void add(uint32_t rank, uint32_t raw, uint32_t qv) {
+    if (qv > 66u) qv = 66u;  // BC_MAX_QV
+    const double lik = __dmul_rn(c_bc_prob[qv], (double)(1ull + (unsigned long long)raw));
+    if (!have_best || lik > best || (lik == best && rank >= best_rank)) {
+      have_best = true;
+      best = lik;
+      best_rank = rank;
+    }
+    total = __dadd_rn(total, lik);
+  }
+};
+
+__global__ void __launch_bounds__(256, 6) pass2_kernel(const Pass2Args a) {
   __shared__ uint32_t scan_a[9];
   __shared__ unsigned long long base_bcast;
   const uint64_t n_invalid = a.n_invalid_dev ? (*a.n_invalid_dev >> a.n_invalid_dev_shift) : a.n_invalid;
@@ -873,6 +890,8 @@ __global__ void __launch_bounds__(256, 8) pass2_kernel(const Pass2Args a) {
       const uint4 qq = __ldcs(a.inv_qual + e);
       const uint32_t qw[4] = {qq.x, qq.y, qq.z, qq.w};
       const int L = a.wl.L;
+      uint32_t uw = 0u, feat_raw = NO_FEATURE;
+      Posterior2 post;
       unsigned long long m;
       if (nmask == 0u) {
         m = wl_neighbor_mask(a.wl, q);
@@ -883,9 +902,6 @@ __global__ void __launch_bounds__(256, 8) pass2_kernel(const Pass2Args a) {
       } else {
         m = 0ull;  // every trial still holds a non-ACGT base
       }
-      bool have_best = false;
-      double best = 0.0, total = 0.0;
-      uint32_t best_rank = 0;
       while (m) {
         int bit = __ffsll((long long)m) - 1;
         m &= m - 1ull;
@@ -898,17 +914,10 @@ __global__ void __launch_bounds__(256, 8) pass2_kernel(const Pass2Args a) {
         uint32_t rank = wl_rank_of(a.wl, widx);
         uint32_t raw = __ldg(a.prior + rank);
         uint32_t qv = a.have_qual ? ((qw[pos >> 2] >> (8 * (pos & 3))) & 0xFFu) : 66u;
-        if (qv > 66u) qv = 66u;  // BC_MAX_QV
-        double lik = __dmul_rn(c_bc_prob[qv], (double)(1ull + (unsigned long long)raw));
-        if (!have_best || lik > best || (lik == best && rank >= best_rank)) {
-          have_best = true;
-          best = lik;
-          best_rank = rank;
-        }
-        total = __dadd_rn(total, lik);
+        post.add(rank, raw, qv);
       }
       bool accept = false;
-      if (have_best) {
+      if (post.have_best) {
         bool ee_ok = true;
         if (a.check_expected_errors) {
           double ee = 0.0;
@@ -916,14 +925,16 @@ __global__ void __launch_bounds__(256, 8) pass2_kernel(const Pass2Args a) {
             for (int i = 0; i < L; i++) ee = __dadd_rn(ee, c_bc_prob[(qw[i >> 2] >> (8 * (i & 3))) & 0xFFu]);
           ee_ok = ee < a.max_expected_errors;
         }
-        accept = ee_ok && (__ddiv_rn(best, total) >= a.threshold);
+        accept = ee_ok && (__ddiv_rn(post.best, post.total) >= a.threshold);
       }
       if (accept) {
+        const uint32_t best_rank = post.best_rank;
         __stcs(a.bc_out + idx, (ST_VALID_AFTER << BC_STATE_SHIFT) | best_rank);
         if (a.corrected) atomicAdd(a.corrected + best_rank, 1u);
         if (a.emit_keys) {
-          uint32_t uw = __ldcs(a.umi_out + idx);
-          uint32_t feature = a.feature ? checked_feature(__ldcs(a.feature + idx), a.n_features, nullptr) : NO_FEATURE;
+          uw = __ldcs(a.umi_out + idx);
+          if (a.feature) feat_raw = __ldcs(a.feature + idx);
+          const uint32_t feature = a.feature ? checked_feature(feat_raw, a.n_features, nullptr) : NO_FEATURE;
           if ((uw & UMI_VALID_BIT) && feature != NO_FEATURE) {
             emit = true;
             key = make_key(a.kl, best_rank, feature, a.lib, uw & UMI_SEQ_MASK);
@@ -931,7 +942,7 @@ __global__ void __launch_bounds__(256, 8) pass2_kernel(const Pass2Args a) {
         }
       }
     }
-    if (a.emit_keys) {
+    if (a.emit_keys) {  // one atomic per block (per warp: 3.2 ms, the counter's L2 slice serialises them)
       uint32_t tot;
       uint32_t off = block_exclusive_scan<256>(emit ? 1u : 0u, &tot, scan_a);
       if (threadIdx.x == 0) base_bcast = tot ? atomicAdd(a.counters, (unsigned long long)tot) : 0ull;
