@@ -421,6 +421,8 @@ def run_ours(args):
     # per-phase device times of one more step (phase_times() synchronises, so outside the timed loop)
     step_device()
     phases = gw.phase_times()
+    if os.environ.get("CRGPU_BENCH_PHASES_EARLY") and rank == 0:  # timing experiments whose results are not valid
+        print(json.dumps({"ms_per_step": ms, "phases_ms": phases}), file=sys.stderr, flush=True)
     n_keys, n_distinct = stats["keys"], stats["distinct_keys"]
 
     # ---------------- what was computed: fingerprint, and single values checked against the oracle ----------------

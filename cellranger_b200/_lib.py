@@ -14,7 +14,7 @@ from . import build as _build
 
 STAT_NAMES = ["reads", "valid_before", "corrected", "invalid", "keys", "distinct_keys", "umi_corrected_keys",
               "low_support_keys", "molecules", "nnz", "barcodes", "kernel_launches", "umi_corrected_reads",
-              "low_support_reads", "sort_violations", "rle_violations"]
+              "low_support_reads", "sort_violations", "rle_violations", "filtered_target_umis"]
 NO_FEATURE = 0xFFFFFFFF
 NO_RANK = 0x3FFFFFFF
 

@@ -291,6 +291,14 @@ class GemWell:
         check(self.L.crgpu_features_set(self._ctx, fr.n_features, ptr(ft), ptr(seqs), stride), "crgpu_features_set")
         self.feature_reference = fr
 
+    def set_target_filter(self, on_target, targeted_umi_min_read_count: Optional[int]):
+        """DupBuilder::build(filter_umis, umi_correction, targeted_umi_min_read_count) with the feature
+        reference's target set (tx_annotation/src/mark_dups.rs:156-170,311-320): on_target = bool per feature;
+        None / 0 switches the filter off."""
+        t = np.ascontiguousarray(on_target, dtype=np.uint8)
+        check(self.L.crgpu_set_target_filter(self._ctx, ptr(t), C.c_int32(t.shape[0]),
+                                             C.c_uint64(int(targeted_umi_min_read_count or 0))), "crgpu_set_target_filter")
+
     def add_reads(self, library: int, r1_seq, r1_qual, feature=None, r2_seq=None, r2_qual=None, select_key=None) -> int:
         """Host arrays: r1_seq/r1_qual (n, r1_len) uint8, feature uint32[n] (GEX) or r2_* (feature barcode);
         select_key: optional uint64[n], UmiSelectKey{utype, qname} per read as one order-preserving word (bit 63
@@ -596,7 +604,7 @@ class GemWell:
 
     # ---- results ----
     def stats(self) -> dict:
-        out = (C.c_uint64 * 16)()
+        out = (C.c_uint64 * len(_lib.STAT_NAMES))()
         check(self.L.crgpu_stats(self._ctx, out))
         return {k: int(v) for k, v in zip(_lib.STAT_NAMES, out) if not k.startswith("_")}
 

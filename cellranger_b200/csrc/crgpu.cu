@@ -240,7 +240,7 @@ void crgpu_ctx_destroy(crgpu_ctx* c) {
                    &c->keys_alt, &c->sort_temp, &c->counters, &c->dkeys, &c->c0, &c->best, &c->inc, &c->low, &c->key2,
                    &c->key2_alt, &c->lb_desc, &c->tickets, &c->scalars, &c->ent_rank, &c->ent_feature, &c->ent_count,
                    &c->mol, &c->col_of_rank, &c->barcode_rank, &c->indptr, &c->mol_rows, &c->min_read, &c->rep_raw, &c->summary, &c->fastq_text, &c->fastq_tmp,
-                   &c->ls_slots, &c->mol_idx, &c->mol_sort, &c->mol_sort_alt};
+                   &c->ls_slots, &c->mol_idx, &c->mol_sort, &c->mol_sort_alt, &c->on_target};
   for (auto* b : all) b->release();
   for (auto& p : c->phases) {
     cudaEventDestroy(p.second.first);
@@ -274,6 +274,22 @@ int crgpu_set_params(crgpu_ctx* c, double thr, double max_ee, int filter_umis) {
   c->threshold = thr;
   c->max_expected_errors = max_ee;
   c->filter_umis = filter_umis;
+  return CRGPU_OK;
+}
+
+int crgpu_set_target_filter(crgpu_ctx* c, const uint8_t* on_target, int32_t n, uint64_t min_reads) {
+  if (!c) return fail(CRGPU_E_INVALID, "ctx is NULL");
+  if (n < 0) return fail(CRGPU_E_INVALID, "n_features < 0");
+  CU(cudaSetDevice(c->device));
+  c->n_on_target = 0;
+  c->target_min_reads = 0;
+  if (!on_target || n == 0 || min_reads == 0) return CRGPU_OK;
+  int rc;
+  if ((rc = c->on_target.ensure((size_t)n))) return rc;
+  CU(cudaMemcpyAsync(c->on_target.p, on_target, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));  // on_target is the caller's
+  c->n_on_target = (uint32_t)n;
+  c->target_min_reads = min_reads;
   return CRGPU_OK;
 }
 
@@ -1291,6 +1307,9 @@ int crgpu_count(crgpu_ctx* c) {
   for (size_t l = 0; l < c->libs.size(); l++)
     if (c->libs[l]->def.umi_correction) b.umi_correction_mask |= 1u << l;
   b.filter_umis = c->filter_umis;
+  b.on_target = c->target_min_reads ? c->on_target.as<uint8_t>() : nullptr;
+  b.n_on_target = c->n_on_target;
+  b.target_min_reads = c->target_min_reads;
   b.verify = getenv("CRGPU_VERIFY") != nullptr;
   b.mark = [](void* user, const char* name) {
     crgpu_ctx* cc = static_cast<crgpu_ctx*>(user);
@@ -1337,6 +1356,7 @@ int crgpu_count(crgpu_ctx* c) {
   CU(cudaMemcpyAsync(hs, c->scalars.p, 16 * 8, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   c->n_mol = m ? hs[2] : 0;
+  const unsigned long long hs_dedup12 = hs[12];
   const uint32_t nc = (uint32_t)c->content.size();
   if ((rc = c->col_of_rank.ensure((size_t)(nc + 1) * 4))) return rc;
   if ((rc = c->barcode_rank.ensure((size_t)(nc + 1) * 4))) return rc;
@@ -1382,6 +1402,7 @@ int crgpu_count(crgpu_ctx* c) {
   c->stats[CRGPU_STAT_SORT_VIOLATIONS] = m ? hs[10] : 0;
   c->stats[CRGPU_STAT_RLE_VIOLATIONS] = m ? hs[11] : 0;
   c->stats[CRGPU_STAT_NNZ] = c->nnz;
+  c->stats[CRGPU_STAT_FILTERED_TARGET_UMIS] = m ? hs_dedup12 : 0;
   c->stats[CRGPU_STAT_BARCODES] = c->n_barcodes;
   c->stage = 3;
   c->annotated = false;

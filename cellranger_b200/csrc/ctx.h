@@ -113,6 +113,9 @@ struct crgpu_ctx {
   double threshold = 0.975;
   double max_expected_errors = 1.7976931348623157e308;
   int filter_umis = 1;
+  DevBuf on_target;  // u8[n_on_target]: the panel's target set (crgpu_set_target_filter)
+  uint32_t n_on_target = 0;
+  uint64_t target_min_reads = 0;
 
   // content space
   int L = 0;

@@ -858,6 +858,34 @@ __global__ void __launch_bounds__(256) low_support_kernel(const unsigned long lo
 }
 
 // ---------------------------------------------------------------------------
+// Targeted-panel filter (BarcodeDupMarker::process, mark_dups.rs:311-320): a correction target on a feature of the
+// target set with read_count (c2) below the threshold, and not low support, is no UMI count. Bit 1 of low[].
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) target_filter_kernel(const unsigned long long* __restrict__ dkeys,
+                                                            const uint32_t* __restrict__ c0,
+                                                            const uint32_t* __restrict__ best,
+                                                            const unsigned long long* __restrict__ inc, uint64_t m,
+                                                            KeyLayout kl, const uint8_t* __restrict__ on_target,
+                                                            uint32_t n_on_target, unsigned long long min_reads,
+                                                            uint8_t* __restrict__ low, unsigned long long* n_filtered) {
+  const FieldMasks fm = field_masks(kl);
+  unsigned long long mine = 0;
+  for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < m; j += (uint64_t)gridDim.x * blockDim.x) {
+    const bool self = best[j] == (uint32_t)j;
+    const unsigned long long in = inc[j];
+    if (!(self || (in >> 40) != 0ull) || (low[j] & 1)) continue;
+    const uint32_t feature = (uint32_t)((dkeys[j] >> kl.feature_shift) & ((1ull << fm.fbits) - 1ull));
+    const unsigned long long reads = (self ? c0[j] : 0u) + (in & INC_READS_MASK);
+    if (feature < n_on_target && on_target[feature] && reads < min_reads) {
+      low[j] |= 2;
+      mine++;
+    }
+  }
+  for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_filtered, mine);
+}
+
+// ---------------------------------------------------------------------------
 // molecules (UmiCount rows) and matrix entries
 // ---------------------------------------------------------------------------
 // molecules = correction targets that are not low support: key + read count (c2), compacted in order
@@ -909,7 +937,7 @@ __global__ void __launch_bounds__(CP_THREADS) molecules_compact_kernel(
     const bool is_target = self || (in[i] >> 40) != 0ull;
     f[i] = j < m && is_target && !lw[i];
     cnt += f[i];
-    if (j < m && (self ? lw[i] != 0 : low[b[i]] != 0)) low_reads += c0[j];
+    if (j < m && (self ? (lw[i] & 1) != 0 : (low[b[i]] & 1) != 0)) low_reads += c0[j];
   }
   for (int d = 16; d > 0; d >>= 1) low_reads += __shfl_xor_sync(0xFFFFFFFFu, low_reads, d);
   if ((threadIdx.x & 31) == 0 && low_reads) atomicAdd(low_reads_out, low_reads);
@@ -1201,15 +1229,26 @@ __device__ __forceinline__ uint32_t match_owner(uint32_t own) {
   return peers;
 }
 
-// One pass of a 16-way partition per chunk, built like a radix pass (sort.cu): every key is ranked among the keys
-// of its owner inside its warp (ballots, warp-private counters), the counters are scanned over the warps and the
-// owners, the chunk is ordered by owner in shared memory and every owner's run leaves as coalesced peer stores
-// behind one remote claim per owner and chunk, whose round trip runs under the ordering of the chunk. 1.70 ms
-// for 168 M keys at 2 GPUs, where the former kernel (two match.any rounds per key, owner_scatter_peers_body)
-// took 2.62 ms. Measured and dropped: addresses planned ahead (a counting pass, a scan, an all-gather of the
-// G x G counts, no atomics at all): 2.59 ms - the claims were never the bottleneck; chunks of 2048 keys at five
-// blocks per SM: 1.78 ms.
-template <int FS_ITEMS, int FS_MINB>
+// A 16-way partition built like a radix pass (sort.cu). Every block owns a contiguous range of chunks. It first
+// counts its keys per owner (a streaming read with per-thread packed counters) and claims its whole space in
+// every owner's receive buffer with ONE remote atomic per owner; then, chunk by chunk, every key is ranked among
+// the keys of its owner inside its warp (ballots, warp-private counters), the counters are scanned over the warps
+// and the owners, the chunk is ordered by owner in shared memory and every owner's run leaves as coalesced peer
+// stores at the block's running offset. Measured on B200 (168 M keys per GPU): the former kernel (two match.any
+// rounds per key and a claim per owner and chunk, owner_scatter_peers_body) 2.62 ms at 2 GPUs; this ranking with
+// a claim per owner and CHUNK 1.70 ms at 2 GPUs but 3.13 ms at 8 - 330 k atomics on one cursor word serialise at
+// its L2 slice, most of them arriving over NVLink; the claim per owner and BLOCK costs a second read of the keys
+// and removes that limit. Also measured: addresses planned ahead by a separate counting kernel, a scan and an
+// all-gather of the G x G counts (2.59 ms at 2 GPUs); chunks of 2048 keys at five blocks per SM (1.78 ms).
+// owner of a rank = number of inner bounds at or below it (the bounds ascend): n_parts - 1 compares, not 15
+__device__ __forceinline__ uint32_t owner_of_n(const OwnerBounds& ob, int n_parts, uint32_t rank) {
+  uint32_t p = 0;
+  for (int i = 1; i < n_parts; i++) p += rank >= ob.b[i] ? 1u : 0u;
+  return p;
+}
+
+// BLOCK_CLAIM = false: no counting phase, one claim per owner and chunk (the faster form at two GPUs)
+template <int FS_ITEMS, int FS_MINB, bool BLOCK_CLAIM>
 __global__ void __launch_bounds__(PL_THREADS, FS_MINB) owner_scatter_fast_kernel(
     const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ begin_dev,
     const unsigned long long* __restrict__ end_dev, int rank_shift, const uint32_t* __restrict__ bounds_dev, int n_parts,
@@ -1220,18 +1259,79 @@ __global__ void __launch_bounds__(PL_THREADS, FS_MINB) owner_scatter_fast_kernel
   __shared__ uint8_t s_own[FS_CHUNK];
   __shared__ uint32_t s_warp_hist[WARPS * (P + 1)];
   __shared__ uint32_t s_cnt[P], s_off[P + 1];
-  __shared__ unsigned long long s_run[P];  // where this chunk's run of every owner goes (~0: nowhere)
+  __shared__ unsigned long long s_tot[P];  // keys of this block per owner
+  __shared__ unsigned long long s_run[P];  // where the next run of every owner goes (~0: nowhere)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid <= P) ob.b[tid] = tid <= n_parts ? bounds_dev[tid] : 0xFFFFFFFFu;
   if (tid == 0) ob.n = n_parts;
+  if (tid < P) s_tot[tid] = 0ull;
+  __syncthreads();
   const unsigned long long first_key = begin_dev ? *begin_dev : 0ull;
   const unsigned long long last_key = *end_dev;
   const uint64_t n = last_key > first_key ? last_key - first_key : 0ull;
   keys += first_key;
+  // the chunks of this block: [c_lo, c_hi)
   const uint64_t n_chunks = (n + FS_CHUNK - 1) / FS_CHUNK;
+  const uint64_t per = (n_chunks + gridDim.x - 1) / gridDim.x;
+  const uint64_t c_lo = (uint64_t)blockIdx.x * per < n_chunks ? (uint64_t)blockIdx.x * per : n_chunks;
+  const uint64_t c_hi = c_lo + per < n_chunks ? c_lo + per : n_chunks;
+  if (c_lo == c_hi) return;  // block-uniform
+  // ---- phase A: keys per owner over the whole range. Two owners per 64-bit counter word; eight loads in flight ----
+  if (BLOCK_CLAIM) {
+    unsigned long long c[P / 2];
+#pragma unroll
+    for (int i = 0; i < P / 2; i++) c[i] = 0ull;
+    const uint64_t k_lo = c_lo * FS_CHUNK, k_hi = c_hi * FS_CHUNK < n ? c_hi * FS_CHUNK : n;
+    for (uint64_t g0 = k_lo + tid; g0 < k_hi; g0 += (uint64_t)PL_THREADS * 8) {
+      unsigned long long v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const uint64_t g = g0 + (uint64_t)u * PL_THREADS;
+        v[u] = g < k_hi ? __ldg(keys + g) : ~0ull;  // the keys come back in phase B: keep them in L2 if it can
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const uint64_t g = g0 + (uint64_t)u * PL_THREADS;
+        if (g < k_hi) {
+          const int own = (int)owner_of_n(ob, n_parts, (uint32_t)(v[u] >> rank_shift));
+          const unsigned long long inc = 1ull << (32 * (own & 1));
+#pragma unroll
+          for (int i = 0; i < P / 2; i++)
+            if (2 * i < n_parts) c[i] += (own >> 1) == i ? inc : 0ull;  // block-uniform guard
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < P / 2; i++) {
+      if (2 * i < n_parts) {  // block-uniform
+        unsigned long long v = c[i];
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+        if (lane == 0) {
+          atomicAdd(&s_tot[2 * i], v & 0xFFFFFFFFull);
+          atomicAdd(&s_tot[2 * i + 1], v >> 32);
+        }
+      }
+    }
+    __syncthreads();
+    // one claim per owner for the whole block
+    if (tid < P) {
+      unsigned long long base = ~0ull;
+      const unsigned long long tot = s_tot[tid];
+      if (tid < n_parts && tot) {
+        base = atomicAdd(pt.cursor[tid], tot);
+        if (base + tot > pt.capacity) {
+          atomicExch(pt.cursor[tid] + 1, 1ull);  // the receiver reports the overflow
+          base = ~0ull;
+        }
+        atomicAdd(sent + tid, tot);
+      }
+      s_run[tid] = base;
+    }
+  }
+  // ---- phase B: chunk by chunk ----
   uint32_t* my_hist = s_warp_hist + warp * (P + 1);
   const uint32_t lt_mask = (1u << lane) - 1u;
-  for (uint64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+  for (uint64_t chunk = c_lo; chunk < c_hi; chunk++) {
     for (int i = tid; i < WARPS * (P + 1); i += PL_THREADS) s_warp_hist[i] = 0u;
     __syncthreads();
     const uint64_t first = chunk * FS_CHUNK;
@@ -1246,7 +1346,7 @@ __global__ void __launch_bounds__(PL_THREADS, FS_MINB) owner_scatter_fast_kernel
 #pragma unroll
     for (int i = 0; i < FS_ITEMS; i++) {
       const uint64_t g = first + warp_first + i * 32 + lane;
-      const uint32_t own = g < n ? (uint32_t)owner_of(ob, (uint32_t)(k[i] >> rank_shift)) : (uint32_t)P;
+      const uint32_t own = g < n ? owner_of_n(ob, n_parts, (uint32_t)(k[i] >> rank_shift)) : (uint32_t)P;
       const uint32_t peers = match_owner(own);
       const int leader = __ffs(peers) - 1;
       uint32_t base = 0;
@@ -1259,36 +1359,36 @@ __global__ void __launch_bounds__(PL_THREADS, FS_MINB) owner_scatter_fast_kernel
       dr[i] = own | ((base + (uint32_t)__popc(peers & lt_mask)) << 8);
     }
     __syncthreads();
-    if (tid < P) {  // exclusive scan of this owner's counts over the warps
+    if (warp == 0) {  // per owner: exclusive scan of its counts over the warps, then over the owners (shuffles)
       uint32_t run = 0;
+      if (lane < P) {
 #pragma unroll
-      for (int w = 0; w < WARPS; w++) {
-        const uint32_t c = s_warp_hist[w * (P + 1) + tid];
-        s_warp_hist[w * (P + 1) + tid] = run;
-        run += c;
+        for (int w = 0; w < WARPS; w++) {
+          const uint32_t c = s_warp_hist[w * (P + 1) + lane];
+          s_warp_hist[w * (P + 1) + lane] = run;
+          run += c;
+        }
+        s_cnt[lane] = run;
       }
-      s_cnt[tid] = run;
+      uint32_t inc = run;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d) inc += t;
+      }
+      if (lane <= P) s_off[lane] = inc - run;  // lane P: the chunk's total
     }
     __syncthreads();
-    if (tid == 0) {
-      uint32_t run = 0;
-      for (int p = 0; p < P; p++) {
-        s_off[p] = run;
-        run += s_cnt[p];
-      }
-      s_off[P] = run;
-    }
-    // one remote claim per owner and chunk; its round trip runs under the ordering of the chunk in shared memory
+    // per-chunk claims: the round trip runs under the ordering of the chunk in shared memory
     unsigned long long claim = ~0ull;
     uint32_t claim_cnt = 0u;
-    if (tid < n_parts) {
+    if (!BLOCK_CLAIM && tid < n_parts) {
       claim_cnt = s_cnt[tid];
       if (claim_cnt) {
         claim = atomicAdd(pt.cursor[tid], (unsigned long long)claim_cnt);
         atomicAdd(sent + tid, (unsigned long long)claim_cnt);
       }
     }
-    __syncthreads();
 #pragma unroll
     for (int i = 0; i < FS_ITEMS; i++) {
       const uint32_t own = dr[i] & 0xFFu;
@@ -1298,7 +1398,7 @@ __global__ void __launch_bounds__(PL_THREADS, FS_MINB) owner_scatter_fast_kernel
         s_own[pos] = (uint8_t)own;
       }
     }
-    if (tid < n_parts) {
+    if (!BLOCK_CLAIM && tid < P) {
       if (claim != ~0ull && claim + claim_cnt > pt.capacity) {
         atomicExch(pt.cursor[tid] + 1, 1ull);  // the receiver reports the overflow
         claim = ~0ull;
@@ -1315,6 +1415,7 @@ __global__ void __launch_bounds__(PL_THREADS, FS_MINB) owner_scatter_fast_kernel
       if (b != ~0ull) pt.buf[o][b + (p - s_off[o])] = s_keys[p];
     }
     __syncthreads();
+    if (BLOCK_CLAIM && tid < P && s_run[tid] != ~0ull) s_run[tid] += s_cnt[tid];
   }
   __threadfence_system();  // as in owner_scatter_peers_body
 }
@@ -1341,8 +1442,15 @@ int run_owner_scatter_peers_dev(const unsigned long long* keys, const unsigned l
   }
   const uint64_t chunks = (n_max + PL_CHUNK - 1) / PL_CHUNK;
   const int grid = (int)std::min<uint64_t>(chunks, (uint64_t)sm_count() * 3);
-  owner_scatter_fast_kernel<PL_ITEMS, 3><<<grid, PL_THREADS, 0, st>>>(keys, begin_dev, end_dev, rank_shift, bounds_dev,
-                                                                     n_parts, pt, d_sent);
+  // two ranks: a claim per chunk is cheaper than the counting phase (1.70 against 2.35 ms); from three ranks on the
+  // claims of all senders on one cursor word become the limit (3.13 ms at eight)
+  const int mode = getenv("CRGPU_SCATTER_CFG") ? atoi(getenv("CRGPU_SCATTER_CFG")) : 0;
+  if ((n_parts <= 2 && mode != 3) || mode == 2)
+    owner_scatter_fast_kernel<PL_ITEMS, 3, false><<<grid, PL_THREADS, 0, st>>>(keys, begin_dev, end_dev, rank_shift,
+                                                                              bounds_dev, n_parts, pt, d_sent);
+  else
+    owner_scatter_fast_kernel<PL_ITEMS, 3, true><<<grid, PL_THREADS, 0, st>>>(keys, begin_dev, end_dev, rank_shift,
+                                                                             bounds_dev, n_parts, pt, d_sent);
   return 1;
 }
 
@@ -1599,6 +1707,11 @@ int run_dedup(DedupBuffers& b, uint64_t* n_distinct_host, cudaStream_t st) {
     }
   }
   mark("count.dedup.molecules");
+  if (b.on_target && b.target_min_reads) {
+    target_filter_kernel<<<grid_for(m, 256, 16), 256, 0, st>>>(b.dkeys, b.c0, b.best, b.inc, m, b.kl, b.on_target,
+                                                                   b.n_on_target, b.target_min_reads, b.low, b.scalars + 12);
+    launches++;
+  }
   // 4. molecules = correction targets that are not low support (key2 now holds their keys)
   {
     uint64_t tiles = (m + CP_TILE - 1) / CP_TILE;
@@ -1831,7 +1944,7 @@ __global__ void __launch_bounds__(256) summary_keys_kernel(const unsigned long l
         rank = (uint32_t)(k >> kl.rank_shift);
         const uint32_t t = best[j];
         const uint32_t n = c0[j];
-        if (!low[t]) cand = n;
+        if (!(low[t] & 1)) cand = n;  // candidate_dup_reads: not low support (aligner.rs:56-58)
         if (t != (uint32_t)j) corr = n;
         const bool is_target = t == (uint32_t)j || (inc[j] >> 40) != 0ull;
         umis = is_target && !low[j];
@@ -1976,13 +2089,15 @@ __global__ void annotate_final_kernel(const unsigned long long* __restrict__ dke
       uint64_t j = lower_bound_u64(dkeys, m, key);
       uint32_t d = best[j];
       bool corrected = d != (uint32_t)j;
-      bool is_low = low[d] != 0;
+      bool is_low = (low[d] & 1) != 0;
+      bool is_filtered = (low[d] & 2) != 0;  // is_filtered_target_umi, mark_dups.rs:311-320
       uint32_t rep = rep_raw[d] == 0xFFFFFFFFu ? d : rep_raw[d];
       // is_min_qname: the read's header equals the qname of the corrected key's UmiSelectKey (mark_dups.rs:300-303);
       // the key's select key is the one of raw key `rep` (:248-268), and only its own reads can carry that qname
       const unsigned long long q63 = 0x7FFFFFFFFFFFFFFFull;
       bool is_rep = rep == (uint32_t)j && (min_key[j] & q63) == (select_word(a, i) & q63);
-      fl |= 2u | (corrected ? 4u : 0u) | (is_low ? 8u : 0u) | ((!is_low && is_rep) ? 16u : 0u);
+      fl |= 2u | (corrected ? 4u : 0u) | (is_low ? 8u : 0u) | ((!is_low && !is_filtered && is_rep) ? 16u : 0u) |
+            (is_filtered ? 32u : 0u);
       uw = (uw & ~UMI_SEQ_MASK) | (uint32_t)(dkeys[d] & umask);
     }
     a.umi_proc[i] = uw;

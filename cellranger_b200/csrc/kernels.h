@@ -136,17 +136,23 @@ struct DedupBuffers {
   KeyLayout kl;
   uint32_t umi_correction_mask;  // bit lib set: UMI correction enabled for that library
   int filter_umis;
+  // targeted-panel filter (mark_dups.rs:311-320): on_target[feature] != 0 and fewer than target_min_reads reads
+  // (0 = no filter) and not low support: not a UMI count. Sets bit 1 of low[].
+  const uint8_t* on_target;
+  uint32_t n_on_target;
+  unsigned long long target_min_reads;
   // work / outputs (device)
   unsigned long long* dkeys;  // [cap] distinct keys
   uint32_t* c0;               // [cap] raw read counts
   uint32_t* best;             // [cap] index of the correction target (self if uncorrected)
   unsigned long long* inc;    // [cap] incoming: count << 40 | reads
-  uint8_t* low;               // [cap] low-support flag
+  uint8_t* low;               // [cap] bit 0: low support, bit 1: filtered target UMI
   unsigned long long* key2;   // [cap] (rank, lib, umi, feature) order for the low-support grouping
   unsigned long long* key2_alt;
   unsigned long long* lb_desc;  // look-back descriptors
   uint32_t* tickets;            // atomic tickets (several)
   unsigned long long* scalars;  // device scalars: [0] n_distinct [1] nnz [2] n_molecules [3] corrected keys [4] low keys
+                                // [12] filtered target UMIs
   void* sort_temp;
   size_t sort_temp_bytes;
   void (*mark)(void* user, const char* phase);  // optional: called at the start of each sub-phase

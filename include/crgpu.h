@@ -64,6 +64,12 @@ void crgpu_ctx_destroy(crgpu_ctx* ctx);
  * filter_umis — cr_lib/src/aligner.rs:270. Defaults: 0.975, f64::MAX, 1. */
 int crgpu_set_params(crgpu_ctx* ctx, double bc_confidence_threshold, double max_expected_barcode_errors,
                      int filter_umis);
+/* Targeted-panel UMI filter: DupBuilder::build(.., targeted_umi_min_read_count) with FeatureReference::target_set
+ * (tx_annotation/src/mark_dups.rs:156-170,189-191,311-320; cr_lib/src/aligner.rs:319). A molecule whose feature
+ * is on target (on_target[feature] != 0), whose read count after UMI correction is below min_read_count and
+ * that is not low support is no UMI count: it enters neither the matrix nor the UmiCount rows, and its reads
+ * carry flag bit 5 (is_filtered_target_umi). on_target NULL or min_read_count 0 (the default): no filter. */
+int crgpu_set_target_filter(crgpu_ctx* ctx, const uint8_t* on_target, int32_t n_features, uint64_t min_read_count);
 
 /* ---- Whitelist — barcode/src/whitelist.rs:452-525 (Whitelist::{Plain,Trans}) ----
  * seqs: n*L ASCII. translated: NULL for a plain whitelist, else n*L ASCII (raw -> translated).
@@ -285,7 +291,8 @@ enum {
   CRGPU_STAT_LOW_SUPPORT_READS = 13,
   CRGPU_STAT_SORT_VIOLATIONS = 14, /* with CRGPU_VERIFY=1 in the environment: order violations found after */
   CRGPU_STAT_RLE_VIOLATIONS = 15,  /* the radix sort and after the run-length encoding (must be 0) */
-  CRGPU_STAT_COUNT = 16
+  CRGPU_STAT_FILTERED_TARGET_UMIS = 16, /* molecules dropped by crgpu_set_target_filter */
+  CRGPU_STAT_COUNT = 17
 };
 int crgpu_stats(crgpu_ctx* ctx, uint64_t out[CRGPU_STAT_COUNT]);
 

@@ -442,7 +442,7 @@ const uint32_t NO_FEATURE = 0xFFFFFFFFu;
 struct ReadOut {
   uint8_t bc_state = NOT_CHECKED;
   uint8_t umi_valid = 0;
-  uint8_t has_dup = 0, is_corrected = 0, is_low_support = 0, is_umi_count = 0;
+  uint8_t has_dup = 0, is_corrected = 0, is_low_support = 0, is_umi_count = 0, is_filtered_target = 0;
   uint32_t feature = NO_FEATURE;
   uint32_t read_count = 0;
 };
@@ -465,6 +465,9 @@ struct Ctx {
   double threshold = 0.975;
   double max_expected_errors = 1.7976931348623157e308;  // f64::MAX, corrector.rs:104-106
   bool filter_umis = true;                              // lib/rust/cr_lib/src/aligner.rs:270
+  // targeted_umi_min_read_count (None = 0) and the panel's target set (mark_dups.rs:189-191,311-320)
+  uint64_t target_min_reads = 0;
+  std::vector<uint8_t> on_target;
 
   // outputs
   std::vector<ReadOut> out;
@@ -643,7 +646,11 @@ static void process_barcode(Ctx& c, const std::vector<uint64_t>& reads, const st
     const uint64_t sk = select_key(g);
     bool is_min = (m.min_key.at(ck) & 0x7FFFFFFFFFFFFFFFull) == (sk & 0x7FFFFFFFFFFFFFFFull);
     uint64_t rc = m.counts.at(ck);
-    bool is_umi_count = !low && is_min;
+    // is_filtered_target_umi (mark_dups.rs:311-320): on-target feature, fewer reads than the threshold, not low support
+    bool filtered = c.target_min_reads != 0 && raw.gene < c.on_target.size() && c.on_target[raw.gene] &&
+                    rc < c.target_min_reads && !low;
+    bool is_umi_count = !low && is_min && !filtered;  // sampling_factor is always true (stages/stubs.rs:6-8)
+    o.is_filtered_target = filtered;
     o.has_dup = 1;
     o.is_corrected = is_corrected;
     o.is_low_support = low;
@@ -724,6 +731,13 @@ double cro_probability(uint8_t q) { return probability(q); }
 
 void* cro_ctx_new() { return new Ctx(); }
 void cro_ctx_free(void* p) { delete (Ctx*)p; }
+
+// DupBuilder::build(.., targeted_umi_min_read_count) + FeatureReference::target_set; min_reads = 0: None
+void cro_set_target_filter(void* p, const uint8_t* on_target, int32_t n, uint64_t min_reads) {
+  Ctx& c = *(Ctx*)p;
+  c.on_target.assign(on_target, on_target + (on_target ? n : 0));
+  c.target_min_reads = on_target ? min_reads : 0;
+}
 
 void cro_set_params(void* p, double threshold, double max_expected_errors, int filter_umis) {
   Ctx& c = *(Ctx*)p;
@@ -855,7 +869,8 @@ void cro_get_feat_dist(void* p, double* out) {
 uint64_t cro_n_reads(void* p) { return ((Ctx*)p)->n_reads; }
 
 // Per-read outputs. bc: n*bc_len ASCII content; umi: n*umi_len ASCII processed UMI.
-// flags bit0 umi_valid, bit1 has_dup, bit2 is_corrected, bit3 is_low_support, bit4 is_umi_count
+// flags bit0 umi_valid, bit1 has_dup, bit2 is_corrected, bit3 is_low_support, bit4 is_umi_count,
+// bit5 is_filtered_target_umi
 void cro_get_reads(void* p, int bc_len, int umi_len, uint8_t* bc, uint8_t* state, uint8_t* umi, uint8_t* flags,
                    uint32_t* feature, uint32_t* read_count) {
   Ctx& c = *(Ctx*)p;
@@ -866,7 +881,7 @@ void cro_get_reads(void* p, int bc_len, int umi_len, uint8_t* bc, uint8_t* state
     if (umi) memcpy(umi + g * umi_len, c.umi_out[g].data(), std::min((size_t)umi_len, c.umi_out[g].size()));
     if (flags)
       flags[g] = (uint8_t)(o.umi_valid | (o.has_dup << 1) | (o.is_corrected << 2) | (o.is_low_support << 3) |
-                           (o.is_umi_count << 4));
+                           (o.is_umi_count << 4) | (o.is_filtered_target << 5));
     if (feature) feature[g] = o.feature;
     if (read_count) read_count[g] = o.read_count;
   }

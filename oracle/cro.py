@@ -88,6 +88,11 @@ class Oracle:
         except Exception:
             pass
 
+    def set_target_filter(self, on_target, min_read_count: int):
+        """DupBuilder::build(.., targeted_umi_min_read_count) with the panel's target set (mark_dups.rs:311-320)."""
+        t = np.ascontiguousarray(on_target, dtype=np.uint8)
+        self.L.cro_set_target_filter(self.ctx, _p(t), C.c_int32(t.shape[0]), C.c_uint64(int(min_read_count)))
+
     def add_whitelist(self, seqs, trans=None) -> int:
         s = ascii_mat(seqs)
         t = ascii_mat(trans) if trans is not None else None

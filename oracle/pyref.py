@@ -124,7 +124,7 @@ def match_feature(fb_lookup: dict, dist, seq: bytes, qual: bytes, threshold=0.97
     return best_f if best / total >= threshold else None
 
 
-def dedup_count(keys, key_fields, umi_correction, filter_umis=True):
+def dedup_count(keys, key_fields, umi_correction, filter_umis=True, on_target=None, target_min_reads=0):
     """keys: iterable of (rank, lib, feature, umi) tuples, one per read entering dedup (any order).
     umi_correction: {lib: bool}. Returns dict with
       table   {(rank, lib, feature, umi): dict(c0, dest, low, c2)}
@@ -167,7 +167,13 @@ def dedup_count(keys, key_fields, umi_correction, filter_umis=True):
             for f, c in lst:
                 low[(r, l, f, u)] = tied or c < m
     targets = {(k[0], k[1], k[2], d) for k, d in dest.items()}
-    mols = sorted((r, l, f, u, c2[(r, l, f, u)]) for (r, l, f, u) in targets if not low[(r, l, f, u)])
+
+    def filtered(r, l, f, u):  # is_filtered_target_umi, mark_dups.rs:311-320
+        return bool(target_min_reads) and on_target is not None and f < len(on_target) and bool(on_target[f]) and \
+            c2[(r, l, f, u)] < target_min_reads and not low[(r, l, f, u)]
+
+    mols = sorted((r, l, f, u, c2[(r, l, f, u)]) for (r, l, f, u) in targets
+                  if not low[(r, l, f, u)] and not filtered(r, l, f, u))
     ent = defaultdict(int)
     for r, l, f, u, _ in mols:
         ent[(r, f)] += 1

@@ -88,7 +88,7 @@ def test_header_is_plain_c(tmp_path):
     src = tmp_path / "use_header.c"
     src.write_text('#include "crgpu.h"\n'
                    "int main(void) { crgpu_library_def d; crgpu_read_batch b; (void)d; (void)b;\n"
-                   "  return sizeof(d) == 40 && CRGPU_STAT_COUNT == 16 ? 0 : 1; }\n")
+                   "  return sizeof(d) == 40 && CRGPU_STAT_COUNT == 17 ? 0 : 1; }\n")
     res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I" + os.path.join(root, "include"),
                           "-fsyntax-only", str(src)], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
