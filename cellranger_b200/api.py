@@ -291,6 +291,20 @@ class GemWell:
         check(self.L.crgpu_features_set(self._ctx, fr.n_features, ptr(ft), ptr(seqs), stride), "crgpu_features_set")
         self.feature_reference = fr
 
+    def total_barcode_counts(self, min_reads_to_report_bc: int = 1):
+        """total_barcode_counts of BARCODE_CORRECTION (cr_lib/src/stages/barcode_correction.rs:327-362): the reads
+        that were not valid before correction, by barcode after correction -> (seqs (n, L) ASCII, valid, counts),
+        invalid sequences first. Needs barcode_correction()."""
+        n = C.c_uint64()
+        check(self.L.crgpu_total_barcode_counts(self._ctx, C.c_uint64(int(min_reads_to_report_bc)), C.byref(n)),
+              "crgpu_total_barcode_counts")
+        seqs = np.zeros((n.value, self.bc_length or 0), dtype=np.uint8)
+        valid = np.zeros(n.value, dtype=np.uint8)
+        counts = np.zeros(n.value, dtype=np.uint64)
+        check(self.L.crgpu_total_barcode_counts_get(self._ctx, ptr(seqs), ptr(valid), ptr(counts)),
+              "crgpu_total_barcode_counts_get")
+        return seqs, valid, counts
+
     def set_target_filter(self, on_target, targeted_umi_min_read_count: Optional[int]):
         """DupBuilder::build(filter_umis, umi_correction, targeted_umi_min_read_count) with the feature
         reference's target set (tx_annotation/src/mark_dups.rs:156-170,311-320): on_target = bool per feature;

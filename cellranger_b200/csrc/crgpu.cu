@@ -466,6 +466,104 @@ int crgpu_barcode_seqs(crgpu_ctx* c, const uint32_t* ranks, uint64_t n, uint8_t*
   return CRGPU_OK;
 }
 
+// BarcodeCorrection::main, bc_counts_total (cr_lib/src/stages/barcode_correction.rs:327-362): every read the stage
+// sees (the reads that were not valid before correction) is observed under its barcode after correction - a
+// whitelist barcode when the correction succeeded, else the raw sequence with valid = false - and the entries seen
+// fewer than min_reads_to_report_bc times are dropped. One histogram over all library types; the whole read set
+// counts as one chunk (the reference's per-chunk `retain` makes its own output depend on the chunking).
+int crgpu_total_barcode_counts(crgpu_ctx* c, uint64_t min_reads, uint64_t* out_n) {
+  if (!c || !out_n) return fail(CRGPU_E_INVALID, "NULL argument");
+  if (c->stage < 2) return fail(CRGPU_E_INVALID, "crgpu_pass2 must run first");
+  CU(cudaSetDevice(c->device));
+  const int L = c->L;
+  const uint64_t W = c->content.size();
+  c->tbc_seqs.clear();
+  c->tbc_valid.clear();
+  c->tbc_counts.clear();
+  int rc;
+  // (1) still-invalid reads by raw sequence: collect, sort, count runs
+  uint64_t n_side = 0;
+  for (auto* b : c->batches) n_side += b->n;
+  DevBuf keys, alt, temp, ctr_buf;
+  if ((rc = keys.ensure(std::max<uint64_t>(n_side, 1) * 8))) return rc;
+  if ((rc = alt.ensure(std::max<uint64_t>(n_side, 1) * 8))) return rc;
+  if ((rc = ctr_buf.ensure(8))) return rc;
+  auto release = [&]() { keys.release(); alt.release(); temp.release(); ctr_buf.release(); };
+  CU(cudaMemsetAsync(ctr_buf.p, 0, 8, c->stream));
+  unsigned long long* ctr = c->counters.as<unsigned long long>();
+  for (size_t bi = 0; bi < c->batches.size(); bi++) {
+    Batch* b = c->batches[bi];
+    if (!b->n) continue;
+    c->launches += launch_collect_invalid(b->inv_idx.as<uint32_t>(), b->inv_bc.as<uint32_t>(), b->inv_nmask.as<uint32_t>(),
+                                          ctr + 2 + bi, b->n, c->bc_out.as<uint32_t>() + b->base,
+                                          keys.as<unsigned long long>(), ctr_buf.as<unsigned long long>(), c->stream);
+  }
+  unsigned long long n_inv = 0;
+  CU(cudaMemcpyAsync(&n_inv, ctr_buf.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  std::vector<unsigned long long> sorted_h(n_inv);
+  if (n_inv) {
+    if ((rc = temp.ensure(sort_temp_bytes(n_inv)))) { release(); return rc; }
+    unsigned long long* sorted = nullptr;
+    c->launches += sort_keys(keys.as<unsigned long long>(), alt.as<unsigned long long>(), n_inv, 48, temp.p, temp.cap,
+                             &sorted, c->stream, 0);
+    CU(cudaMemcpyAsync(sorted_h.data(), sorted, n_inv * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  release();
+  static const char B[4] = {'A', 'C', 'G', 'T'};
+  struct Entry {
+    std::string seq;
+    uint8_t valid;
+    uint64_t count;
+  };
+  std::vector<Entry> ent;
+  for (uint64_t i = 0; i < n_inv;) {
+    uint64_t j = i;
+    while (j < n_inv && sorted_h[j] == sorted_h[i]) j++;
+    if (j - i >= min_reads) {
+      const uint32_t k = (uint32_t)sorted_h[i], nm = (uint32_t)(sorted_h[i] >> 32);
+      std::string s((size_t)L, 'N');
+      for (int p = 0; p < L; p++)
+        if (!((nm >> p) & 1u)) s[p] = B[(k >> (2 * (L - 1 - p))) & 3u];
+      ent.push_back(Entry{s, 0, j - i});
+    }
+    i = j;
+  }
+  std::sort(ent.begin(), ent.end(), [](const Entry& a, const Entry& b) { return a.seq < b.seq; });
+  // (2) corrected reads by whitelist barcode, summed over the library types
+  std::vector<uint64_t> corr(W, 0);
+  std::vector<uint32_t> h(W);
+  for (auto* l : c->libs) {
+    if (!W) break;
+    CU(cudaMemcpyAsync(h.data(), l->corrected.p, W * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (uint64_t r = 0; r < W; r++) corr[r] += h[r];
+  }
+  for (uint64_t r = 0; r < W; r++)  // content ranks ascend with the sequence
+    if (corr[r] && corr[r] >= min_reads) {
+      const uint32_t k = c->content[r];
+      std::string s((size_t)L, 'A');
+      for (int p = 0; p < L; p++) s[p] = B[(k >> (2 * (L - 1 - p))) & 3u];
+      ent.push_back(Entry{s, 1, corr[r]});
+    }
+  for (const auto& e : ent) {
+    c->tbc_seqs.insert(c->tbc_seqs.end(), e.seq.begin(), e.seq.end());
+    c->tbc_valid.push_back(e.valid);
+    c->tbc_counts.push_back(e.count);
+  }
+  *out_n = ent.size();
+  return CRGPU_OK;
+}
+
+int crgpu_total_barcode_counts_get(crgpu_ctx* c, uint8_t* seqs, uint8_t* valid, uint64_t* counts) {
+  if (!c) return fail(CRGPU_E_INVALID, "ctx is NULL");
+  if (seqs && !c->tbc_seqs.empty()) memcpy(seqs, c->tbc_seqs.data(), c->tbc_seqs.size());
+  if (valid && !c->tbc_valid.empty()) memcpy(valid, c->tbc_valid.data(), c->tbc_valid.size());
+  if (counts && !c->tbc_counts.empty()) memcpy(counts, c->tbc_counts.data(), c->tbc_counts.size() * 8);
+  return CRGPU_OK;
+}
+
 int crgpu_library_add(crgpu_ctx* c, const crgpu_library_def* def, int* out_lib) {
   if (!c || !def || !out_lib) return fail(CRGPU_E_INVALID, "NULL argument");
   if (def->whitelist < 0 || def->whitelist >= (int)c->wls.size()) return fail(CRGPU_E_INVALID, "unknown whitelist");

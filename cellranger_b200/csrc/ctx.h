@@ -116,6 +116,9 @@ struct crgpu_ctx {
   DevBuf on_target;  // u8[n_on_target]: the panel's target set (crgpu_set_target_filter)
   uint32_t n_on_target = 0;
   uint64_t target_min_reads = 0;
+  // crgpu_total_barcode_counts: the last result, host side
+  std::vector<uint8_t> tbc_seqs, tbc_valid;
+  std::vector<uint64_t> tbc_counts;
 
   // content space
   int L = 0;

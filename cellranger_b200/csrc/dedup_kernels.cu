@@ -1229,17 +1229,16 @@ __device__ __forceinline__ uint32_t match_owner(uint32_t own) {
   return peers;
 }
 
-// A 16-way partition built like a radix pass (sort.cu). Every block owns a contiguous range of chunks. It first
-// counts its keys per owner (a streaming read with per-thread packed counters) and claims its whole space in
-// every owner's receive buffer with ONE remote atomic per owner; then, chunk by chunk, every key is ranked among
-// the keys of its owner inside its warp (ballots, warp-private counters), the counters are scanned over the warps
-// and the owners, the chunk is ordered by owner in shared memory and every owner's run leaves as coalesced peer
-// stores at the block's running offset. Measured on B200 (168 M keys per GPU): the former kernel (two match.any
-// rounds per key and a claim per owner and chunk, owner_scatter_peers_body) 2.62 ms at 2 GPUs; this ranking with
-// a claim per owner and CHUNK 1.70 ms at 2 GPUs but 3.13 ms at 8 - 330 k atomics on one cursor word serialise at
-// its L2 slice, most of them arriving over NVLink; the claim per owner and BLOCK costs a second read of the keys
-// and removes that limit. Also measured: addresses planned ahead by a separate counting kernel, a scan and an
-// all-gather of the G x G counts (2.59 ms at 2 GPUs); chunks of 2048 keys at five blocks per SM (1.78 ms).
+// A 16-way partition per chunk, built like a radix pass (sort.cu): every key is ranked among the keys of its
+// owner inside its warp (ballots, warp-private counters), the counters are scanned over the warps and the owners,
+// the chunk is ordered by owner in shared memory and every owner's run leaves as coalesced peer stores behind one
+// remote claim per owner and chunk, whose round trip runs under the ordering of the chunk. Measured on B200, 168 M
+// keys per GPU (profiles/r02_bench_{2,8}gpu*.json): 1.61 ms at 2 GPUs, where the former kernel (two match.any
+// rounds per key, owner_scatter_peers_body) took 2.62 ms; 3.13 ms at 8 GPUs (1.18 GB out and in per GPU). At 2
+// GPUs the kernel is bound by its own instructions (the same time with every store kept local). Measured and
+// dropped: a counting phase and one claim per owner and BLOCK (2.35 ms at 2 GPUs, 3.46 ms at 8: the claims are not
+// what limits it); addresses planned ahead by a counting kernel, a scan and an all-gather of the G x G counts
+// (2.59 ms at 2 GPUs); chunks of 2048 keys at five blocks per SM (1.78 ms).
 // owner of a rank = number of inner bounds at or below it (the bounds ascend): n_parts - 1 compares, not 15
 __device__ __forceinline__ uint32_t owner_of_n(const OwnerBounds& ob, int n_parts, uint32_t rank) {
   uint32_t p = 0;
@@ -1247,8 +1246,7 @@ __device__ __forceinline__ uint32_t owner_of_n(const OwnerBounds& ob, int n_part
   return p;
 }
 
-// BLOCK_CLAIM = false: no counting phase, one claim per owner and chunk (the faster form at two GPUs)
-template <int FS_ITEMS, int FS_MINB, bool BLOCK_CLAIM>
+template <int FS_ITEMS, int FS_MINB>
 __global__ void __launch_bounds__(PL_THREADS, FS_MINB) owner_scatter_fast_kernel(
     const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ begin_dev,
     const unsigned long long* __restrict__ end_dev, int rank_shift, const uint32_t* __restrict__ bounds_dev, int n_parts,
@@ -1259,12 +1257,10 @@ __global__ void __launch_bounds__(PL_THREADS, FS_MINB) owner_scatter_fast_kernel
   __shared__ uint8_t s_own[FS_CHUNK];
   __shared__ uint32_t s_warp_hist[WARPS * (P + 1)];
   __shared__ uint32_t s_cnt[P], s_off[P + 1];
-  __shared__ unsigned long long s_tot[P];  // keys of this block per owner
-  __shared__ unsigned long long s_run[P];  // where the next run of every owner goes (~0: nowhere)
+  __shared__ unsigned long long s_run[P];  // where this chunk's run of every owner goes (~0: nowhere)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid <= P) ob.b[tid] = tid <= n_parts ? bounds_dev[tid] : 0xFFFFFFFFu;
   if (tid == 0) ob.n = n_parts;
-  if (tid < P) s_tot[tid] = 0ull;
   __syncthreads();
   const unsigned long long first_key = begin_dev ? *begin_dev : 0ull;
   const unsigned long long last_key = *end_dev;
@@ -1276,59 +1272,6 @@ __global__ void __launch_bounds__(PL_THREADS, FS_MINB) owner_scatter_fast_kernel
   const uint64_t c_lo = (uint64_t)blockIdx.x * per < n_chunks ? (uint64_t)blockIdx.x * per : n_chunks;
   const uint64_t c_hi = c_lo + per < n_chunks ? c_lo + per : n_chunks;
   if (c_lo == c_hi) return;  // block-uniform
-  // ---- phase A: keys per owner over the whole range. Two owners per 64-bit counter word; eight loads in flight ----
-  if (BLOCK_CLAIM) {
-    unsigned long long c[P / 2];
-#pragma unroll
-    for (int i = 0; i < P / 2; i++) c[i] = 0ull;
-    const uint64_t k_lo = c_lo * FS_CHUNK, k_hi = c_hi * FS_CHUNK < n ? c_hi * FS_CHUNK : n;
-    for (uint64_t g0 = k_lo + tid; g0 < k_hi; g0 += (uint64_t)PL_THREADS * 8) {
-      unsigned long long v[8];
-#pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const uint64_t g = g0 + (uint64_t)u * PL_THREADS;
-        v[u] = g < k_hi ? __ldg(keys + g) : ~0ull;  // the keys come back in phase B: keep them in L2 if it can
-      }
-#pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const uint64_t g = g0 + (uint64_t)u * PL_THREADS;
-        if (g < k_hi) {
-          const int own = (int)owner_of_n(ob, n_parts, (uint32_t)(v[u] >> rank_shift));
-          const unsigned long long inc = 1ull << (32 * (own & 1));
-#pragma unroll
-          for (int i = 0; i < P / 2; i++)
-            if (2 * i < n_parts) c[i] += (own >> 1) == i ? inc : 0ull;  // block-uniform guard
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < P / 2; i++) {
-      if (2 * i < n_parts) {  // block-uniform
-        unsigned long long v = c[i];
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
-        if (lane == 0) {
-          atomicAdd(&s_tot[2 * i], v & 0xFFFFFFFFull);
-          atomicAdd(&s_tot[2 * i + 1], v >> 32);
-        }
-      }
-    }
-    __syncthreads();
-    // one claim per owner for the whole block
-    if (tid < P) {
-      unsigned long long base = ~0ull;
-      const unsigned long long tot = s_tot[tid];
-      if (tid < n_parts && tot) {
-        base = atomicAdd(pt.cursor[tid], tot);
-        if (base + tot > pt.capacity) {
-          atomicExch(pt.cursor[tid] + 1, 1ull);  // the receiver reports the overflow
-          base = ~0ull;
-        }
-        atomicAdd(sent + tid, tot);
-      }
-      s_run[tid] = base;
-    }
-  }
-  // ---- phase B: chunk by chunk ----
   uint32_t* my_hist = s_warp_hist + warp * (P + 1);
   const uint32_t lt_mask = (1u << lane) - 1u;
   for (uint64_t chunk = c_lo; chunk < c_hi; chunk++) {
@@ -1382,7 +1325,7 @@ __global__ void __launch_bounds__(PL_THREADS, FS_MINB) owner_scatter_fast_kernel
     // per-chunk claims: the round trip runs under the ordering of the chunk in shared memory
     unsigned long long claim = ~0ull;
     uint32_t claim_cnt = 0u;
-    if (!BLOCK_CLAIM && tid < n_parts) {
+    if (tid < n_parts) {
       claim_cnt = s_cnt[tid];
       if (claim_cnt) {
         claim = atomicAdd(pt.cursor[tid], (unsigned long long)claim_cnt);
@@ -1398,7 +1341,7 @@ __global__ void __launch_bounds__(PL_THREADS, FS_MINB) owner_scatter_fast_kernel
         s_own[pos] = (uint8_t)own;
       }
     }
-    if (!BLOCK_CLAIM && tid < P) {
+    if (tid < P) {
       if (claim != ~0ull && claim + claim_cnt > pt.capacity) {
         atomicExch(pt.cursor[tid] + 1, 1ull);  // the receiver reports the overflow
         claim = ~0ull;
@@ -1415,7 +1358,6 @@ __global__ void __launch_bounds__(PL_THREADS, FS_MINB) owner_scatter_fast_kernel
       if (b != ~0ull) pt.buf[o][b + (p - s_off[o])] = s_keys[p];
     }
     __syncthreads();
-    if (BLOCK_CLAIM && tid < P && s_run[tid] != ~0ull) s_run[tid] += s_cnt[tid];
   }
   __threadfence_system();  // as in owner_scatter_peers_body
 }
@@ -1442,15 +1384,8 @@ int run_owner_scatter_peers_dev(const unsigned long long* keys, const unsigned l
   }
   const uint64_t chunks = (n_max + PL_CHUNK - 1) / PL_CHUNK;
   const int grid = (int)std::min<uint64_t>(chunks, (uint64_t)sm_count() * 3);
-  // two ranks: a claim per chunk is cheaper than the counting phase (1.70 against 2.35 ms); from three ranks on the
-  // claims of all senders on one cursor word become the limit (3.13 ms at eight)
-  const int mode = getenv("CRGPU_SCATTER_CFG") ? atoi(getenv("CRGPU_SCATTER_CFG")) : 0;
-  if ((n_parts <= 2 && mode != 3) || mode == 2)
-    owner_scatter_fast_kernel<PL_ITEMS, 3, false><<<grid, PL_THREADS, 0, st>>>(keys, begin_dev, end_dev, rank_shift,
-                                                                              bounds_dev, n_parts, pt, d_sent);
-  else
-    owner_scatter_fast_kernel<PL_ITEMS, 3, true><<<grid, PL_THREADS, 0, st>>>(keys, begin_dev, end_dev, rank_shift,
-                                                                             bounds_dev, n_parts, pt, d_sent);
+  owner_scatter_fast_kernel<PL_ITEMS, 3><<<grid, PL_THREADS, 0, st>>>(keys, begin_dev, end_dev, rank_shift, bounds_dev,
+                                                                     n_parts, pt, d_sent);
   return 1;
 }
 

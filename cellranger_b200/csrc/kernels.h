@@ -88,6 +88,9 @@ int launch_pass1(const Pass1Args& a, int n_sms, cudaStream_t st);  // returns #k
 int launch_pass2(const Pass2Args& a, cudaStream_t st);
 int launch_fb(const FbArgs& a, cudaStream_t st);
 int launch_emit_keys(const EmitArgs& a, cudaStream_t st);
+int launch_collect_invalid(const uint32_t* inv_idx, const uint32_t* inv_bc, const uint32_t* inv_nmask,
+                           const unsigned long long* n_invalid_dev, uint64_t n_max, const uint32_t* bc_out,
+                           unsigned long long* out, unsigned long long* counter, cudaStream_t st);
 int launch_valid_counts(const uint32_t* prior, const uint32_t* corrected, uint32_t* out, uint64_t n, cudaStream_t st);
 
 // ---- FASTQ text -> fixed-stride read arrays (fastq.cu) ----

@@ -962,6 +962,48 @@ int launch_pass2(const Pass2Args& a, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------
+// total_barcode_counts (barcode_correction.rs:327-362): the reads of the side list that pass 2 left invalid, as
+// keys (non-ACGT mask << 32 | packed sequence) for a sort + run-length count.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) collect_invalid_kernel(const uint32_t* __restrict__ inv_idx,
+                                                              const uint32_t* __restrict__ inv_bc,
+                                                              const uint32_t* __restrict__ inv_nmask,
+                                                              const unsigned long long* __restrict__ n_invalid_dev,
+                                                              const uint32_t* __restrict__ bc_out,
+                                                              unsigned long long* __restrict__ out,
+                                                              unsigned long long* __restrict__ counter) {
+  const uint64_t n = *n_invalid_dev;
+  const int lane = threadIdx.x & 31;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t rounds = (n + stride - 1) / stride;  // warp-uniform trip count: ballots inside
+  for (uint64_t r = 0; r < rounds; r++) {
+    const uint64_t e = r * stride + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    bool take = false;
+    unsigned long long key = 0ull;
+    if (e < n) {
+      take = (bc_out[inv_idx[e]] >> BC_STATE_SHIFT) == ST_INVALID;
+      key = ((unsigned long long)(inv_nmask[e] & 0xFFFFu) << 32) | inv_bc[e];
+    }
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, take);
+    if (m) {
+      unsigned long long base = 0ull;
+      if (lane == 0) base = atomicAdd(counter, (unsigned long long)__popc(m));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (take) out[base + __popc(m & ((1u << lane) - 1u))] = key;
+    }
+  }
+}
+
+int launch_collect_invalid(const uint32_t* inv_idx, const uint32_t* inv_bc, const uint32_t* inv_nmask,
+                           const unsigned long long* n_invalid_dev, uint64_t n_max, const uint32_t* bc_out,
+                           unsigned long long* out, unsigned long long* counter, cudaStream_t st) {
+  if (!n_max) return 0;
+  const int grid = (int)std::min<uint64_t>((n_max + 255) / 256, (uint64_t)sm_count() * 16);
+  collect_invalid_kernel<<<grid, 256, 0, st>>>(inv_idx, inv_bc, inv_nmask, n_invalid_dev, bc_out, out, counter);
+  return 1;
+}
+
+// ---------------------------------------------------------------------------
 // Feature-barcode libraries: tethered fixed-offset capture R2[fb_off : fb_off+fb_len].
 // exact_counts != nullptr: MAKE_SHARD pre-count of exact captures (make_shard_metrics.rs:337-345).
 // feat_dist   != nullptr: ALIGN_AND_COUNT extraction with Hamming-1 posterior correction

@@ -302,6 +302,16 @@ int crgpu_stats(crgpu_ctx* ctx, uint64_t out[CRGPU_STAT_COUNT]);
 int crgpu_reads_get(crgpu_ctx* ctx, int batch, uint32_t* bc_rank, uint8_t* bc_state, uint32_t* umi,
                     uint8_t* flags, uint32_t* feature);
 
+/* total_barcode_counts of BARCODE_CORRECTION (cr_lib/src/stages/barcode_correction.rs:327-362,401-407): the reads
+ * that were not valid before correction, counted under their barcode after correction - a whitelist barcode
+ * (valid = 1) or, when the correction failed, the raw sequence (valid = 0, non-ACGT bases as 'N') - without the
+ * entries seen fewer than min_reads_to_report_bc times. One histogram over all library types, the whole read set
+ * as one chunk. Needs crgpu_pass2. Entries in Barcode order: the invalid sequences first, each group ascending.
+ * crgpu_total_barcode_counts computes and returns the number of entries; _get copies them out
+ * (seqs: n * L bytes). */
+int crgpu_total_barcode_counts(crgpu_ctx* ctx, uint64_t min_reads_to_report_bc, uint64_t* out_n);
+int crgpu_total_barcode_counts_get(crgpu_ctx* ctx, uint8_t* seqs, uint8_t* valid, uint64_t* counts);
+
 /* which: 0 = prior (reads valid before correction), 1 = corrected reads; n = content size */
 int crgpu_bc_counts_get(crgpu_ctx* ctx, int library, int which, uint32_t* out, uint64_t n);
 int crgpu_fb_counts_get(crgpu_ctx* ctx, int64_t* out, int32_t n);

@@ -140,6 +140,13 @@ class GemWell {
 
   crgpu_ctx* ctx() { return ctx_; }
 
+  // DupBuilder::build(filter_umis, umi_correction, targeted_umi_min_read_count) with the panel's target set
+  // (tx_annotation/src/mark_dups.rs:156-170,311-320); min_read_count 0 = None
+  void set_target_filter(const std::vector<uint8_t>& on_target, uint64_t targeted_umi_min_read_count) {
+    check(crgpu_set_target_filter(ctx_, on_target.data(), (int32_t)on_target.size(), targeted_umi_min_read_count),
+          "crgpu_set_target_filter");
+  }
+
   int add_whitelist(const Whitelist& w) {
     int id = -1;
     check(crgpu_whitelist_add(ctx_, w.seqs.data(), w.size(), w.length,

@@ -910,6 +910,29 @@ void cro_matrix_get(void* p, int bc_len, uint8_t* barcodes, int64_t* indptr, uin
     memcpy(data, c.data.data(), c.data.size() * sizeof(int32_t));
   }
 }
+// bc_counts_total of BarcodeCorrection::main (cr_lib/src/stages/barcode_correction.rs:327-362): every read of the
+// invalid shard observed under its barcode after correction, entries below min_reads_to_report_bc dropped; the
+// whole read set as one chunk. Entries in Barcode order (derive(Ord): valid = false first, then the sequence).
+// Returns the number of entries; a second call with buffers copies them out.
+uint64_t cro_total_barcode_counts(void* p, uint64_t min_reads, int bc_len, uint8_t* seqs, uint8_t* valid, uint64_t* counts) {
+  Ctx& c = *(Ctx*)p;
+  std::map<std::pair<bool, Seq>, uint64_t> hist;
+  for (uint64_t g = 0; g < c.n_reads; g++) {
+    const uint8_t st = c.out[g].bc_state;
+    if (st == VALID_BEFORE_CORRECTION) continue;  // never reaches BARCODE_CORRECTION's reader
+    hist[{st == VALID_AFTER_CORRECTION, c.bc_content[g]}] += 1;  // bc_counts_total.observe_owned(bc), :344
+  }
+  uint64_t n = 0;
+  for (const auto& kv : hist) {
+    if (kv.second < min_reads) continue;  // retain(|_, v| min_reads_to_report_bc <= v.count()), :357
+    if (seqs) memcpy(seqs + n * bc_len, kv.first.second.data(), std::min((size_t)bc_len, kv.first.second.size()));
+    if (valid) valid[n] = kv.first.first ? 1 : 0;
+    if (counts) counts[n] = kv.second;
+    n++;
+  }
+  return n;
+}
+
 uint64_t cro_n_molecules(void* p) { return ((Ctx*)p)->molecules.size(); }
 // rows in the order ALIGN_AND_COUNT emits them: by barcode, then umi_counts.sort() (align_and_count.rs:314)
 void cro_molecules_get(void* p, uint32_t* out6) {

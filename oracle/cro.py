@@ -39,6 +39,7 @@ def lib():
         L.cro_matrix_n_barcodes.restype = C.c_uint64
         L.cro_matrix_nnz.restype = C.c_uint64
         L.cro_n_molecules.restype = C.c_uint64
+        L.cro_total_barcode_counts.restype = C.c_uint64
         L.cro_kat_encode_2bit.restype = C.c_uint32
         _lib = L
     return _lib
@@ -87,6 +88,16 @@ class Oracle:
             self.close()
         except Exception:
             pass
+
+    def total_barcode_counts(self, min_reads_to_report_bc: int = 1):
+        """bc_counts_total of BARCODE_CORRECTION (barcode_correction.rs:327-362) -> (seqs (n, L), valid, counts)."""
+        n = int(self.L.cro_total_barcode_counts(self.ctx, C.c_uint64(min_reads_to_report_bc), self.bc_len, None, None, None))
+        seqs = np.zeros((n, self.bc_len), dtype=np.uint8)
+        valid = np.zeros(n, dtype=np.uint8)
+        counts = np.zeros(n, dtype=np.uint64)
+        self.L.cro_total_barcode_counts(self.ctx, C.c_uint64(min_reads_to_report_bc), self.bc_len, _p(seqs), _p(valid),
+                                        _p(counts))
+        return seqs, valid, counts
 
     def set_target_filter(self, on_target, min_read_count: int):
         """DupBuilder::build(.., targeted_umi_min_read_count) with the panel's target set (mark_dups.rs:311-320)."""
