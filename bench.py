@@ -303,7 +303,7 @@ def run_reference(args):
     tables = synth.make_tables(cfg, n_total)
     threads = os.cpu_count() or 1
     # every step runs the whole sample again: bounded so that the driver's --steps 20 --warmup 5 stays within minutes
-    sample = min(args.cpu_sample, 4_000_000)
+    sample = min(args.cpu_sample, 8_000_000)
     rate, sec, st = cpu_oracle_rate(cfg, tables, sample, threads, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "reads/s", "n_gpus": args.gpus,
@@ -588,8 +588,9 @@ def run_ours(args):
         rate, sec, _ = cpu_oracle_rate(cfg, tables, ns, threads, reads=cpu_reads)
         cpu = {"value": rate, "unit": "reads/s", "cores": threads, "kind": "port",
                "sample": f"first {ns} reads of the workload, {sec:.1f} s on {threads} host threads",
-               "note": "C++ restatement of the reference's hash-map algorithm (oracle/cr_oracle.cpp), not the Rust "
-                       "crates (no cargo/rustc in this image) and not tuned: a reported baseline only"}
+               "note": "C++ restatement of the reference's hash-map algorithm (oracle/cr_oracle.cpp: inline "
+                       "fixed-capacity sequences and open-addressing maps like the reference's SSeqGen / hashbrown), "
+                       "not the Rust crates (no cargo/rustc in this image): a reported baseline only"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
@@ -615,7 +616,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=FULL_READS_PER_GPU, help="reads per GPU (default: the full config)")
-    ap.add_argument("--cpu-sample", type=int, default=16_000_000,
+    ap.add_argument("--cpu-sample", type=int, default=32_000_000,
                     help="reads of the CPU baseline's sample (about 10-30 s of CPU work at the default)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")

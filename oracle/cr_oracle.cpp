@@ -36,7 +36,172 @@
 
 namespace {
 
-typedef std::string Seq;
+// BcSegSeq / UmiSeq / feature-barcode sequences as the reference holds them: SSeqGen<N> of fastq_set 0.5.3 - a
+// fixed-capacity array of ASCII bytes plus a length byte, stored inline (no heap), Ord = byte-lexicographic,
+// Hash over the bytes (lib/rust/barcode/src/lib.rs:33-52, lib/rust/umi/src/lib.rs:12-14). Unused bytes stay zero,
+// so equality and hashing run over the whole 32-byte value.
+struct Seq {
+  static const size_t CAP = 31;
+  char b[CAP] = {0};
+  uint8_t n = 0;
+  Seq() {}
+  Seq(const char* p, size_t len) {
+    if (len > CAP) {
+      fprintf(stderr, "cr_oracle: sequence of %zu bytes exceeds the %zu-byte capacity\n", len, CAP);
+      abort();
+    }
+    n = (uint8_t)len;
+    memcpy(b, p, len);
+  }
+  size_t size() const { return n; }
+  const char* data() const { return b; }
+  char& operator[](size_t i) { return b[i]; }
+  char operator[](size_t i) const { return b[i]; }
+  bool operator==(const Seq& o) const { return memcmp(this, &o, sizeof(Seq)) == 0; }
+  bool operator!=(const Seq& o) const { return !(*this == o); }
+  bool operator<(const Seq& o) const {  // lexicographic over unsigned bytes, the shorter first on a tie
+    const int c = memcmp(b, o.b, n < o.n ? n : o.n);
+    return c < 0 || (c == 0 && n < o.n);
+  }
+  bool operator>(const Seq& o) const { return o < *this; }
+  bool operator>=(const Seq& o) const { return !(*this < o); }
+  bool operator<=(const Seq& o) const { return !(o < *this); }
+  const char* begin() const { return b; }
+  const char* end() const { return b + n; }
+  static const size_t npos = (size_t)-1;
+  size_t find(char c) const {
+    for (size_t i = 0; i < n; i++)
+      if (b[i] == c) return i;
+    return npos;
+  }
+};
+static_assert(sizeof(Seq) == 32, "Seq is hashed and compared as 32 bytes");
+struct SeqHash {
+  size_t operator()(const Seq& s) const {
+    uint64_t w[4];
+    memcpy(w, &s, 32);
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (int i = 0; i < 4; i++) {
+      h ^= w[i];
+      h *= 0xFF51AFD7ED558CCDull;
+      h ^= h >> 32;
+    }
+    return (size_t)h;
+  }
+};
+
+// The reference's HashMap / HashSet (TxHashMap = hashbrown behind std, lib/rust/metric/src/lib.rs:61-111): an
+// open-addressing table with the entries stored inline - one probe is one cache line, not the two pointer hops of
+// std::unordered_map's node lists. The subset of the std interface this file uses; iteration order is arbitrary,
+// as it is for the reference's maps.
+template <typename K, typename V, typename H>
+class FlatMap {
+ public:
+  struct Entry {
+    K first;
+    V second;
+  };
+
+ private:
+  std::vector<Entry> slots_;
+  std::vector<uint8_t> used_;
+  size_t size_ = 0, mask_ = 0;
+  H hash_;
+
+  size_t probe(const K& k) const {  // slot of k, or the free slot where it would go (capacity > 0)
+    size_t i = hash_(k) & mask_;
+    while (used_[i] && !(slots_[i].first == k)) i = (i + 1) & mask_;
+    return i;
+  }
+  void grow() {
+    const size_t cap = slots_.empty() ? 16 : slots_.size() * 2;
+    std::vector<Entry> old;
+    std::vector<uint8_t> old_used;
+    old.swap(slots_);
+    old_used.swap(used_);
+    slots_.resize(cap);
+    used_.assign(cap, 0);
+    mask_ = cap - 1;
+    for (size_t i = 0; i < old.size(); i++)
+      if (old_used[i]) {
+        const size_t j = probe(old[i].first);
+        slots_[j] = old[i];
+        used_[j] = 1;
+      }
+  }
+
+ public:
+  template <bool CONST>
+  class Iter {
+    typedef typename std::conditional<CONST, const FlatMap, FlatMap>::type Map;
+    typedef typename std::conditional<CONST, const Entry, Entry>::type E;
+    Map* m_;
+    size_t i_;
+    void skip() {
+      while (i_ < m_->slots_.size() && !m_->used_[i_]) i_++;
+    }
+
+   public:
+    Iter(Map* m, size_t i) : m_(m), i_(i) { skip(); }
+    E& operator*() const { return m_->slots_[i_]; }
+    E* operator->() const { return &m_->slots_[i_]; }
+    Iter& operator++() {
+      i_++;
+      skip();
+      return *this;
+    }
+    bool operator==(const Iter& o) const { return i_ == o.i_; }
+    bool operator!=(const Iter& o) const { return i_ != o.i_; }
+  };
+  typedef Iter<false> iterator;
+  typedef Iter<true> const_iterator;
+  iterator begin() { return iterator(this, 0); }
+  iterator end() { return iterator(this, slots_.size()); }
+  const_iterator begin() const { return const_iterator(this, 0); }
+  const_iterator end() const { return const_iterator(this, slots_.size()); }
+  size_t size() const { return size_; }
+  bool empty() const { return size_ == 0; }
+  void clear() {
+    slots_.clear();
+    used_.clear();
+    size_ = mask_ = 0;
+  }
+  void reserve(size_t n) {
+    while (slots_.size() < 2 * n + 16) grow();
+  }
+  iterator find(const K& k) {
+    if (slots_.empty()) return end();
+    const size_t i = probe(k);
+    return used_[i] ? iterator(this, i) : end();
+  }
+  const_iterator find(const K& k) const {
+    if (slots_.empty()) return end();
+    const size_t i = probe(k);
+    return used_[i] ? const_iterator(this, i) : end();
+  }
+  size_t count(const K& k) const { return find(k) != end() ? 1 : 0; }
+  std::pair<iterator, bool> emplace(const K& k, const V& v) {
+    if (2 * (size_ + 1) > slots_.size()) grow();
+    const size_t i = probe(k);
+    if (used_[i]) return {iterator(this, i), false};
+    slots_[i].first = k;
+    slots_[i].second = v;
+    used_[i] = 1;
+    size_++;
+    return {iterator(this, i), true};
+  }
+  void insert(const K& k) { emplace(k, V()); }
+  V& operator[](const K& k) { return emplace(k, V()).first->second; }
+  V& at(const K& k) {
+    auto it = find(k);
+    if (it == end()) {
+      fprintf(stderr, "cr_oracle: FlatMap::at on a missing key\n");
+      abort();
+    }
+    return it->second;
+  }
+  const V& at(const K& k) const { return const_cast<FlatMap*>(this)->at(k); }
+};
 
 // ---------------------------------------------------------------------------
 // Barcode segment state — lib/rust/barcode/src/lib.rs:270-310
@@ -66,8 +231,8 @@ static inline uint8_t state_change(uint8_t s, bool in_wl) {
 struct Whitelist {
   int L = 0;
   bool is_trans = false;
-  std::unordered_set<Seq> plain;
-  std::unordered_map<Seq, Seq> trans;
+  FlatMap<Seq, char, SeqHash> plain;  // HashSet
+  FlatMap<Seq, Seq, SeqHash> trans;
 
   // check_and_update: membership; a translation whitelist replaces the content
   // by the translated sequence (whitelist.rs:494-516).
@@ -90,7 +255,7 @@ struct Whitelist {
 };
 
 // SimpleHistogram<K>::get → 0 when absent — lib/rust/metric/src/histogram.rs:26-145
-typedef std::unordered_map<Seq, int64_t> Hist;
+typedef FlatMap<Seq, int64_t, SeqHash> Hist;
 static inline int64_t hist_get(const Hist& h, const Seq& k) {
   auto it = h.find(k);
   return it == h.end() ? 0 : it->second;
@@ -199,11 +364,12 @@ struct UG {
 };
 struct UGHash {
   size_t operator()(const UG& k) const {
-    return std::hash<Seq>()(k.umi) * 1000003u ^ (size_t)k.gene * 0x9E3779B97F4A7C15ull;
+    return SeqHash()(k.umi) * 1000003u ^ (size_t)k.gene * 0x9E3779B97F4A7C15ull;
   }
 };
-typedef std::unordered_map<UG, uint64_t, UGHash> UGCounts;
-typedef std::unordered_map<UG, Seq, UGHash> UGCorr;
+typedef FlatMap<UG, uint64_t, UGHash> UGCounts;
+typedef FlatMap<UG, Seq, UGHash> UGCorr;
+typedef FlatMap<UG, char, UGHash> UGSet;
 
 // correct_umis — mark_dups.rs:19-59
 static UGCorr correct_umis(const UGCounts& counts) {
@@ -234,8 +400,8 @@ static UGCorr correct_umis(const UGCounts& counts) {
 }
 
 // determine_low_support_umigenes — mark_dups.rs:87-108
-static std::unordered_set<UG, UGHash> determine_low_support(const UGCounts& counts) {
-  std::unordered_set<UG, UGHash> low;
+static UGSet determine_low_support(const UGCounts& counts) {
+  UGSet low;
   struct Row {
     Seq umi;
     uint32_t gene;
@@ -267,12 +433,12 @@ static std::unordered_set<UG, UGHash> determine_low_support(const UGCounts& coun
 
 // UmiSelectKey{utype, qname} (mark_dups.rs:110-152) as the order-preserving word Ctx::select_key holds per read
 // (without caller-supplied keys: every read Txomic, the qname ordered like the global read index).
-typedef std::unordered_map<UG, uint64_t, UGHash> UGMinKey;
+typedef FlatMap<UG, uint64_t, UGHash> UGMinKey;
 
 // BarcodeDupMarker — mark_dups.rs:183-364
 struct DupMarker {
   UGCounts counts;
-  std::unordered_set<UG, UGHash> low_support;
+  UGSet low_support;
   UGCorr corrections;
   UGMinKey min_key;
 
@@ -328,7 +494,7 @@ const double FEATURE_CONF_THRESHOLD = 0.975;
 struct FeaturePattern {
   int offset = 0;  // capture starts at R2[offset]
   int len = 0;
-  std::unordered_map<Seq, int> features;  // sequence → feature index
+  FlatMap<Seq, int, SeqHash> features;  // sequence → feature index
 };
 
 static bool correct_feature_barcode(const FeaturePattern& pat, const std::vector<double>& feat_dist,
@@ -672,17 +838,32 @@ static void process_barcode(Ctx& c, const std::vector<uint64_t>& reads, const st
 static void count_stage(Ctx& c, int threads) {
   // Barcode index: sorted unique union over library types of raw-valid and
   // corrected barcodes — barcode_correction.rs:401-407, cr_types/src/barcode_index.rs:39-53
-  std::map<Seq, std::vector<uint64_t>> by_bc;  // ordered = shardio sort by Barcode
+  // The reads of a barcode are brought together (shardio's sort by Barcode in the reference, which hands
+  // ALIGN_AND_COUNT one barcode at a time in ascending order): grouped through a hash map in read order, then the
+  // distinct barcodes sorted.
   std::vector<int> lib_of(c.n_reads);
   for (auto& b : c.batches)
     for (uint64_t i = 0; i < b.n; i++) lib_of[b.base + i] = b.lib;
+  FlatMap<Seq, uint32_t, SeqHash> group_of;
+  std::vector<Seq> group_bc;
+  std::vector<std::vector<uint64_t>> members;
   for (uint64_t g = 0; g < c.n_reads; g++)
-    if (state_is_valid(c.out[g].bc_state)) by_bc[c.bc_content[g]].push_back(g);
+    if (state_is_valid(c.out[g].bc_state)) {
+      auto r = group_of.emplace(c.bc_content[g], (uint32_t)group_bc.size());
+      if (r.second) {
+        group_bc.push_back(c.bc_content[g]);
+        members.emplace_back();
+      }
+      members[r.first->second].push_back(g);
+    }
+  std::vector<uint32_t> order(group_bc.size());
+  for (size_t i = 0; i < order.size(); i++) order[i] = (uint32_t)i;
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return group_bc[a] < group_bc[b]; });
   c.barcodes.clear();
   std::vector<const std::vector<uint64_t>*> groups;
-  for (auto& kv : by_bc) {
-    c.barcodes.push_back(kv.first);
-    groups.push_back(&kv.second);
+  for (uint32_t i : order) {
+    c.barcodes.push_back(group_bc[i]);
+    groups.push_back(&members[i]);
   }
   size_t nb = groups.size();
   std::vector<BcResult> results(nb);
