@@ -164,7 +164,12 @@ int crgpu_pass2(crgpu_ctx* ctx);
 /* Corrector plugin seam, batch form of trait CorrectBarcode (barcode/src/corrector.rs:73-81):
  * n segments of the library's bc_length (ASCII) with qualities (or NULL = no qualities) against the
  * library's whitelist and its CURRENT priors. out_rank[i] = content rank or CRGPU_NO_RANK;
- * out_state[i] = ValidBeforeCorrection (exact hit), ValidAfterCorrection or Invalid. */
+ * out_state[i] = ValidBeforeCorrection (exact hit), ValidAfterCorrection or Invalid.
+ * Divergence from the trait: Posterior::correct_barcode asserts that the caller only hands over segments in state
+ * Invalid (corrector.rs:120) and never re-checks membership; the batch form has no state on its input, so a
+ * segment that IS on the whitelist comes back as an exact hit (ValidBeforeCorrection) instead of being treated
+ * as Invalid. A caller that follows the reference (correct_barcode_in_read, barcode_correction.rs:95-97: invalid
+ * segments only) never sees the difference. */
 int crgpu_correct_barcodes(crgpu_ctx* ctx, int library, const uint8_t* bc_ascii, const uint8_t* qual,
                            uint64_t n, uint32_t* out_rank, uint8_t* out_state);
 
