@@ -888,3 +888,39 @@ class BarcodeCorrector:
 
     def close(self):
         self.gw.close()
+
+
+class SegmentedBarcodeCorrector:
+    """BarcodeConstruct<BarcodeCorrector> over a segmented barcode (GelBeadAndProbe, Segmented;
+    barcode/src/lib.rs:510-514): every segment has its own whitelist, its own segment counts
+    (valid_bc_segment_counts, cr_lib/src/make_shard_metrics.rs:171-188) and is checked and corrected on its own,
+    exactly as correct_barcode_in_read walks the segments (cr_lib/src/stages/barcode_correction.rs:88-99); the
+    barcode is valid when every segment is (SegmentedBarcode::is_valid, barcode/src/lib.rs:818-823). One
+    BarcodeCorrector - one resident whitelist table - per segment."""
+
+    def __init__(self, whitelists: Sequence[Whitelist], segment_counts: Optional[Sequence[Optional[dict]]] = None,
+                 strategy: Optional[Posterior] = None, device: int = 0):
+        counts = list(segment_counts) if segment_counts is not None else [None] * len(whitelists)
+        if len(counts) != len(whitelists):
+            raise ValueError("one count histogram (or None) per segment")
+        self.segments = [BarcodeCorrector(w, c, strategy, device) for w, c in zip(whitelists, counts)]
+
+    def correct_barcodes(self, segment_seqs: Sequence, segment_quals: Optional[Sequence] = None):
+        """segment_seqs[k]: the n sequences of segment k (with segment_quals[k] or None). Returns
+        (corrected sequences per segment, states per segment, barcode_valid bool[n])."""
+        if len(segment_seqs) != len(self.segments):
+            raise ValueError("one array of sequences per segment")
+        outs, states = [], []
+        for k, seg in enumerate(self.segments):
+            q = None if segment_quals is None else segment_quals[k]
+            o, st = seg.correct_barcodes(segment_seqs[k], q)
+            outs.append(o)
+            states.append(st)
+        valid = np.ones(states[0].shape[0], dtype=bool)
+        for st in states:
+            valid &= (st == VALID_BEFORE_CORRECTION) | (st == VALID_AFTER_CORRECTION)
+        return outs, states, valid
+
+    def close(self):
+        for seg in self.segments:
+            seg.close()

@@ -734,3 +734,49 @@ def test_bench_parity_at_scale_check_works_and_detects_a_wrong_count():
     gw.count_matrix = real
     reads.close()
     gw.close()
+
+
+def test_segmented_barcode_corrector_matches_oracle_per_segment():
+    """GelBeadAndProbe: a 16-base gel-bead segment and an 8-base probe segment, each checked and corrected against
+    its own whitelist with its own segment counts (correct_barcode_in_read walks the segments,
+    barcode_correction.rs:88-99); the barcode is valid when both segments are (barcode/src/lib.rs:818-823)."""
+    import cellranger_b200 as cb
+    from oracle import cro
+
+    rng = np.random.default_rng(23)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    wls, counts = [], []
+    for L, W in ((16, 4000), (8, 16)):
+        wl = acgt[np.unique(rng.integers(0, 4, size=(W, L)), axis=0)]
+        wls.append(wl)
+        counts.append({bytes(s): int(c) for s, c in zip(wl, rng.integers(1, 400, size=len(wl)))})
+    n = 2500
+    seqs, quals = [], []
+    for wl in wls:
+        L = wl.shape[1]
+        src = wl[rng.integers(0, len(wl), size=n)].copy()
+        for i in range(n):
+            if rng.random() < 0.6:  # 40 % of the segments arrive exact
+                for _ in range(rng.integers(1, 3)):
+                    src[i, rng.integers(0, L)] = acgt[rng.integers(0, 4)]
+        seqs.append(src)
+        quals.append(rng.integers(33 + 2, 33 + 41, size=(n, L)).astype(np.uint8))
+    corr = cb.SegmentedBarcodeCorrector([cb.Whitelist.plain(w) for w in wls], counts)
+    outs, states, valid = corr.correct_barcodes(seqs, quals)
+    exp_valid = np.ones(n, dtype=bool)
+    for k, wl in enumerate(wls):
+        members = {bytes(s) for s in wl}
+        for i in range(n):
+            s = bytes(seqs[k][i])
+            if s in members:
+                assert states[k][i] == cb.api.VALID_BEFORE_CORRECTION and bytes(outs[k][i]) == s
+                continue
+            exp = cro.kat_correct_barcode(wl, counts[k], s, bytes(quals[k][i]), F64_MAX, 0.975)
+            if exp is None:
+                assert states[k][i] == cb.api.INVALID, (k, i)
+                exp_valid[i] = False
+            else:
+                assert states[k][i] == cb.api.VALID_AFTER_CORRECTION and bytes(outs[k][i]) == exp, (k, i)
+    assert np.array_equal(valid, exp_valid)
+    assert 0 < int(valid.sum()) < n
+    corr.close()
