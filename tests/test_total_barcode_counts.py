@@ -92,3 +92,39 @@ def test_gpu_hand_case_and_random_problem():
             assert _as_list(gw.total_barcode_counts(m)) == _as_list(o.total_barcode_counts(m)), (name, m)
         gw.close()
         o.close()
+
+
+def test_oracle_recount_with_many_non_acgt_bases():
+    """Barcodes with one or several N (and exact hits, one- and two-base substitutions) over a tiny whitelist: the
+    histogram equals the recount, its order is (valid, sequence) with N between G and T, and the thresholds nest."""
+    rng = np.random.default_rng(17)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    wl = acgt[np.unique(rng.integers(0, 4, size=(40, 16)), axis=0)]
+    n = 6000
+    src = wl[rng.integers(0, len(wl), size=n)].copy()
+    for i in range(n):
+        r = rng.random()
+        if r < 0.5:
+            for _ in range(rng.integers(1, 3)):
+                src[i, rng.integers(0, 16)] = acgt[rng.integers(0, 4)]
+        if r > 0.7:
+            for _ in range(rng.integers(1, 3)):
+                src[i, rng.integers(0, 16)] = ord("N")
+    r1 = np.concatenate([src, np.tile(np.frombuffer(b"ACGTTGCAAC", dtype=np.uint8), (n, 1))], axis=1)
+    q1 = np.full((n, 26), ord("I"), dtype=np.uint8)
+    o = cro.Oracle()
+    lib = o.add_library(o.add_whitelist(wl), 0, 16, 16, 10)
+    o.set_features(np.zeros(4, dtype=np.int32))
+    o.add_reads(lib, r1, q1, np.zeros(n, dtype=np.uint32))
+    o.run()
+    prev = None
+    for m in (1, 2, 3, 10):
+        got = _as_list(o.total_barcode_counts(m))
+        assert got == _recount(o, m)
+        keys = [(v, s) for s, v, _ in got]
+        assert keys == sorted(keys)
+        if prev is not None:
+            assert set(got) <= set(prev)
+        prev = got
+    assert any("N" in s for s, v, _ in _as_list(o.total_barcode_counts(1)) if v == 0)
+    o.close()
