@@ -780,3 +780,29 @@ def test_segmented_barcode_corrector_matches_oracle_per_segment():
     assert np.array_equal(valid, exp_valid)
     assert 0 < int(valid.sum()) < n
     corr.close()
+
+
+def test_barcode_diversity_against_reference_python_vectors(kats):
+    """effective_barcode_diversity on read sets whose valid-barcode histogram is a given count vector, against the
+    values the reference's Python effective_diversity() gives for that vector (tests/golden, generated)."""
+    import cellranger_b200 as cb
+
+    rng = np.random.default_rng(3)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for case in kats["effective_diversity"]["cases"]:
+        counts = case["counts"]
+        wl = acgt[np.unique(rng.integers(0, 4, size=(len(counts) + 5, 16)), axis=0)]
+        assert len(wl) >= len(counts)
+        rows = np.repeat(np.arange(len(counts)), counts)
+        n = len(rows)
+        r1 = np.concatenate([wl[rows], np.tile(np.frombuffer(b"ACGTTGCAAC", dtype=np.uint8), (n, 1))], axis=1)
+        q1 = np.full((n, 26), ord("I"), dtype=np.uint8)
+        gw = cb.GemWell()
+        lib = gw.add_library(gw.add_whitelist(cb.Whitelist.plain(wl)), cb.ChemistryDef.SC3Pv2())
+        gw.set_feature_reference(cb.FeatureReference(4))
+        gw.add_reads(lib, r1, q1, np.zeros(n, dtype=np.uint32))
+        gw.run()
+        d = gw.barcode_diversity(0)
+        assert d["barcodes_detected"] == len(counts)
+        assert d["effective_barcode_diversity"] == case["expect"], case
+        gw.close()

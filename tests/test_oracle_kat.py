@@ -124,3 +124,14 @@ def test_low_support_rule():
     low = cro.kat_low_support([("AAAA", 0, 5), ("AAAA", 1, 2), ("CCCC", 0, 3), ("CCCC", 1, 3), ("GGGG", 2, 1),
                                ("TTTT", 0, 0), ("TTTT", 1, 0)])
     assert low.tolist() == [False, True, True, True, False, True, True]
+
+
+def test_effective_diversity_formula_against_the_reference_python(kats):
+    """SimpleHistogram::effective_diversity (metric/src/histogram.rs:161-171) restated as the loop the GPU test uses,
+    against values GENERATED by the reference's own Python twin (cellranger/stats.py:17-21)."""
+    for case in kats["effective_diversity"]["cases"]:
+        s, s2 = 0.0, 0.0
+        for x in case["counts"]:
+            s += float(x)
+            s2 += float(x) ** 2
+        assert s ** 2 / s2 == case["expect"], case
