@@ -697,6 +697,20 @@ def test_write_mex_matches_matrix(tmp_path):
     assert bcs[:-1] == m.barcode_strings(1) and bcs[-1] == ""
     feats = gzip.open(out / "features.tsv.gz", "rt").read().split("\n")
     assert len(feats) - 1 == m.n_features and feats[0].split("\t")[2] == "Gene Expression"
+    # read back the way the reference's own loader does (lib/python/cellranger/mtx_to_matrix_converter.py:70-92,
+    # from_v3_mtx: pandas for the two TSVs, scipy.io.mmread for the matrix): the same CSC comes out
+    import pandas as pd
+    import scipy.io as sp_io
+    import scipy.sparse as sp_sparse
+
+    barcodes = pd.read_csv(str(out / "barcodes.tsv.gz"), delimiter="\t", header=None, usecols=[0], dtype=bytes).values.squeeze()
+    features = pd.read_csv(str(out / "features.tsv.gz"), delimiter="\t", header=None)
+    mat = sp_sparse.csc_matrix(sp_io.mmread(str(out / "matrix.mtx.gz")))
+    mat.sort_indices()
+    assert mat.shape == (m.n_features, len(m.barcode_rank)) and len(features) == m.n_features
+    assert [b.decode() if isinstance(b, bytes) else b for b in barcodes.tolist()] == m.barcode_strings(1)
+    assert np.array_equal(mat.indptr, m.indptr) and np.array_equal(mat.indices, m.indices)
+    assert np.array_equal(mat.data, m.data)
     gw.close()
 
 
