@@ -107,3 +107,24 @@ def test_csc_fingerprint_adds_up_over_column_blocks():
     for other in (cm([3, 9, 12], [0, 2, 3, 3], [0, 5, 2], [1, 4, 8]), cm([3, 9, 12], [0, 2, 3, 3], [0, 6, 2], [1, 4, 7]),
                   cm([3, 9, 13], [0, 2, 3, 3], [0, 5, 2], [1, 4, 7]), cm([3, 9, 12], [0, 1, 3, 3], [0, 5, 2], [1, 4, 7])):
         assert bench.combine_fingerprints([bench.csc_fingerprint(other, 5)])["csc_hash"] != whole["csc_hash"]
+
+
+def test_tethered_offset_against_the_reference_pattern_compiler(kats):
+    """tethered_offset() against vectors GENERATED by the reference's own Python compile_pattern
+    (lib/python/cellranger/rna/feature_ref.py:426-465, the twin of feature_extraction.rs:306-342): the capture of its
+    regex on a probe read starts where tethered_offset says; a pattern with bases behind (BC) is refused."""
+    import pytest
+
+    from cellranger_b200.api import tethered_offset
+
+    seen = 0
+    for c in kats["tethered_patterns"]["cases"]:
+        if c["pattern"].endswith("(BC)"):
+            off = tethered_offset(c["pattern"])
+            assert off == c["capture_start"], c
+            assert c["probe"][off:off + c["length"]] == c["capture"]
+            seen += 1
+        else:
+            with pytest.raises(ValueError):
+                tethered_offset(c["pattern"])
+    assert seen >= 10
