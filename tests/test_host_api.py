@@ -128,3 +128,17 @@ def test_tethered_offset_against_the_reference_pattern_compiler(kats):
             with pytest.raises(ValueError):
                 tethered_offset(c["pattern"])
     assert seen >= 10
+
+
+def test_barcode_strings_against_the_reference_formatter(kats):
+    """CountMatrix.barcode_strings (what barcodes.tsv holds) against vectors GENERATED by the reference's own
+    format_barcode_seq (lib/python/cellranger/utils.py:44-47)."""
+    import numpy as np
+
+    from cellranger_b200.api import CountMatrix
+
+    for c in kats["format_barcode_seq"]["cases"]:
+        bcs = np.frombuffer(c["barcode"].encode(), dtype=np.uint8).reshape(1, -1)
+        m = CountMatrix(np.zeros(1, dtype=np.uint32), np.zeros(2, dtype=np.int64), np.zeros(0, dtype=np.uint32),
+                        np.zeros(0, dtype=np.int32), 1, barcodes=bcs)
+        assert m.barcode_strings(c["gem_group"]) == [c["expect"]]
