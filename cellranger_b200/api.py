@@ -745,6 +745,22 @@ class GemWell:
         return out
 
 
+# molecule_info.h5 column set: names, order and dtypes of MOLECULE_INFO_COLUMNS
+# (lib/python/cellranger/molecule_counter.py:90-103; written by cr_h5/src/molecule_info.rs:28-47,972-1033)
+MOLECULE_INFO_COLUMNS = (("gem_group", np.uint16), ("barcode_idx", np.uint64), ("feature_idx", np.uint32),
+                         ("library_idx", np.uint16), ("umi", np.uint32), ("count", np.uint32), ("umi_type", np.uint32))
+UMI_TYPE_TXOMIC = 1  # molecule_counter.py:86; a non-transcriptomic UMI carries 0
+
+
+def molecule_info_columns(rows: np.ndarray, gem_group: int = 1) -> dict:
+    """The UmiCount rows of GemWell.molecules() as the datasets of molecule_info.h5: one array per column of
+    MOLECULE_INFO_COLUMNS, in row order (barcode_idx = column of the barcode in the barcode index)."""
+    rows = np.asarray(rows)
+    src = {"gem_group": np.full(rows.shape[0], gem_group), "barcode_idx": rows[:, 0], "library_idx": rows[:, 1],
+           "feature_idx": rows[:, 2], "umi": rows[:, 3], "count": rows[:, 4], "umi_type": rows[:, 5]}
+    return {name: src[name].astype(dt) for name, dt in MOLECULE_INFO_COLUMNS}
+
+
 MAX_READS_BARCODE_COMPATIBILITY = 1_000_000   # check_barcodes_compatibility.rs:79
 MIN_BARCODE_SIMILARITY = 0.1                  # lib/bin/parameters.toml
 

@@ -142,3 +142,25 @@ def test_barcode_strings_against_the_reference_formatter(kats):
         m = CountMatrix(np.zeros(1, dtype=np.uint32), np.zeros(2, dtype=np.int64), np.zeros(0, dtype=np.uint32),
                         np.zeros(0, dtype=np.int32), 1, barcodes=bcs)
         assert m.barcode_strings(c["gem_group"]) == [c["expect"]]
+
+
+def test_molecule_info_columns_against_the_reference_module(kats):
+    """molecule_info_columns(): names, order and dtypes of molecule_info.h5's datasets and the Txomic code, against
+    MOLECULE_INFO_COLUMNS / UMI_TYPE_TXOMIC evaluated from the reference's own module
+    (lib/python/cellranger/molecule_counter.py:74-103)."""
+    import numpy as np
+
+    from cellranger_b200 import api
+
+    k = kats["molecule_info_columns"]
+    assert [[n, np.dtype(d).name] for n, d in api.MOLECULE_INFO_COLUMNS] == k["columns"]
+    assert api.UMI_TYPE_TXOMIC == k["umi_type_txomic"]
+    rows = np.array([[0, 0, 7, 0x2C, 3, 1], [0, 1, 9, 0x1B, 1, 0], [4, 0, 7, 0x2C, 2, 1]], dtype=np.uint32)
+    cols = api.molecule_info_columns(rows, gem_group=2)
+    assert list(cols) == [n for n, _ in k["columns"]]
+    for n, d in k["columns"]:
+        assert cols[n].dtype == np.dtype(d) and cols[n].shape == (3,)
+    assert cols["gem_group"].tolist() == [2, 2, 2] and cols["barcode_idx"].tolist() == [0, 0, 4]
+    assert cols["library_idx"].tolist() == [0, 1, 0] and cols["feature_idx"].tolist() == [7, 9, 7]
+    assert cols["umi"].tolist() == [0x2C, 0x1B, 0x2C] and cols["count"].tolist() == [3, 1, 2]
+    assert cols["umi_type"].tolist() == [1, 0, 1]
