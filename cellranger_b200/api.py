@@ -125,6 +125,16 @@ class ChemistryDef:
     def SC3Pv3() -> "ChemistryDef":
         return ChemistryDef("SC3Pv3", 0, 16, 16, 12)
 
+    @staticmethod
+    def from_chemistry_defs_entry(name: str, entry: dict) -> "ChemistryDef":
+        """From one entry of the reference's chemistry_defs.json (lib/python/cellranger/chemistry_defs.json): the
+        layouts this path handles keep one gel-bead barcode segment and the UMI on R1."""
+        bcs, umis = entry["barcode"], entry["umi"]
+        if len(bcs) != 1 or len(umis) != 1 or bcs[0]["read_type"] != "R1" or umis[0]["read_type"] != "R1":
+            raise ValueError(f"chemistry {name}: only a single R1 barcode segment with the UMI on R1 is supported here")
+        return ChemistryDef(name, int(bcs[0]["offset"]), int(bcs[0]["length"]), int(umis[0]["offset"]),
+                            int(umis[0]["length"]))
+
 
 _PATTERN_RE = re.compile(r"^(?:5[Pp]?[-_]?|\^)?([ACGTN]*)\(BC\)([ACGTN]*)(?:[-_]?3[Pp]?|\$)?$")
 

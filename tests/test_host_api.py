@@ -164,3 +164,17 @@ def test_molecule_info_columns_against_the_reference_module(kats):
     assert cols["library_idx"].tolist() == [0, 1, 0] and cols["feature_idx"].tolist() == [7, 9, 7]
     assert cols["umi"].tolist() == [0x2C, 0x1B, 0x2C] and cols["count"].tolist() == [3, 1, 2]
     assert cols["umi_type"].tolist() == [1, 0, 1]
+
+
+def test_chemistry_presets_against_the_reference_chemistry_defs(kats):
+    """ChemistryDef.SC3Pv2 / SC3Pv3 (and the generic constructor) against the entries of the reference's
+    chemistry_defs.json: barcode R1[0:16], UMI R1[16:26] (v2) / R1[16:28] (v3)."""
+    from cellranger_b200.api import ChemistryDef
+
+    e = kats["chemistry_defs"]["entries"]
+    assert ChemistryDef.from_chemistry_defs_entry("SC3Pv2", e["SC3Pv2"]) == ChemistryDef.SC3Pv2()
+    assert ChemistryDef.from_chemistry_defs_entry("SC3Pv3", e["SC3Pv3"]) == ChemistryDef.SC3Pv3()
+    lt = ChemistryDef.from_chemistry_defs_entry("SC3Pv3LT", e["SC3Pv3LT"])
+    assert (lt.bc_offset, lt.bc_length, lt.umi_offset, lt.umi_length) == (0, 16, 16, 12)
+    assert e["SC3Pv2"]["barcode"][0]["whitelist"]["name"] == "737K-august-2016"
+    assert e["SC3Pv3"]["barcode"][0]["whitelist"]["name"] == "3M-february-2018"
