@@ -139,17 +139,32 @@ class ChemistryDef:
 _PATTERN_RE = re.compile(r"^(?:5[Pp]?[-_]?|\^)?([ACGTN]*)\(BC\)([ACGTN]*)(?:[-_]?3[Pp]?|\$)?$")
 
 
-def tethered_offset(pattern: str) -> int:
-    """Offset of the (BC) capture of a 5'-tethered pattern such as `5PNNNNNNNNNN(BC)` or `^(BC)`
-    (FeatureExtractor::compile_pattern, cr_types/src/reference/feature_extraction.rs:306-342).
-    Only wildcard (N) bases may precede the capture; anything else is outside this path."""
+def _tethered_parts(pattern: str):
     m = _PATTERN_RE.match(pattern)
     if not m or not (pattern.startswith("5") or pattern.startswith("^")):
         raise ValueError(f"unsupported feature pattern {pattern!r}: need a 5'-tethered pattern with one (BC)")
     pre, post = m.group(1), m.group(2)
-    if set(pre) - {"N"} or post:
-        raise ValueError(f"unsupported feature pattern {pattern!r}: only N wildcards before (BC) are supported")
-    return len(pre)
+    if set(pre) - {"N"} or set(post) - {"N"}:
+        raise ValueError(f"unsupported feature pattern {pattern!r}: only N wildcards around (BC) are supported")
+    if re.search(r"(?:[-_]?3[Pp]?|\$)$", pattern):
+        raise ValueError(f"unsupported feature pattern {pattern!r}: anchored at both ends (the read length itself "
+                         "would decide the match)")
+    return len(pre), len(post)
+
+
+def tethered_offset(pattern: str) -> int:
+    """Offset of the (BC) capture of a 5'-tethered pattern such as `5PNNNNNNNNNN(BC)`, `^(BC)` or TotalSeq-B's
+    `5PNNNNNNNNNN(BC)NNNNNNNNN` (FeatureExtractor::compile_pattern, cr_types/src/reference/feature_extraction.rs:
+    306-342; Python twin: lib/python/cellranger/rna/feature_ref.py:426-465). Only wildcard (N) bases may surround
+    the capture; anything else is outside this path."""
+    return _tethered_parts(pattern)[0]
+
+
+def tethered_min_read_length(pattern: str, fb_length: int) -> int:
+    """Cycles a read needs before the reference's anchored regex can match it at all: the wildcards before the
+    capture, the capture, and the wildcards behind it. Hand it to add_library(fb_min_read_length=...)."""
+    pre, post = _tethered_parts(pattern)
+    return pre + int(fb_length) + post
 
 
 FEATURE_TYPE_NAMES = {1: "Antibody Capture", 2: "CRISPR Guide Capture", 3: "Multiplexing Capture", 4: "Custom"}
@@ -279,15 +294,19 @@ class GemWell:
         return out.value
 
     def add_library(self, whitelist: int, chemistry: ChemistryDef, umi_correction: bool = True,
-                    feature_type: int = 0, fb_offset: int = 0, fb_length: int = 0) -> int:
+                    feature_type: int = 0, fb_offset: int = 0, fb_length: int = 0, fb_min_read_length: int = 0) -> int:
         """A library type. feature_type 0 = Gene Expression (features come with the reads);
-        otherwise a feature-barcode library whose features carry that feature_type."""
+        otherwise a feature-barcode library whose features carry that feature_type. fb_min_read_length
+        (tethered_min_read_length): a pattern with wildcards behind (BC) only matches reads that long - batches
+        with a shorter R2 stride are refused, since the reference would match none of their reads."""
         d = LibraryDef(whitelist, chemistry.bc_offset, chemistry.bc_length, chemistry.umi_offset,
                        chemistry.umi_length, int(umi_correction), int(feature_type != 0), feature_type,
                        fb_offset, fb_length)
         out = C.c_int(-1)
         check(self.L.crgpu_library_add(self._ctx, C.byref(d), C.byref(out)), "crgpu_library_add")
         self._libs.append(d)
+        self._fb_min_read_length = getattr(self, "_fb_min_read_length", {})
+        self._fb_min_read_length[out.value] = max(int(fb_min_read_length), int(fb_offset + fb_length))
         self.umi_length = chemistry.umi_length
         return out.value
 
@@ -346,6 +365,10 @@ class GemWell:
             r2_seq = np.ascontiguousarray(r2_seq, dtype=np.uint8)
             r2_qual = np.ascontiguousarray(r2_qual, dtype=np.uint8)
             rb.r2_len = r2_seq.shape[1]
+            need = getattr(self, "_fb_min_read_length", {}).get(library, 0)
+            if self._libs[library].is_feature_barcode and rb.r2_len < need:
+                raise ValueError(f"R2 of {rb.r2_len} cycles is shorter than the {need} cycles the feature pattern "
+                                 "needs: no read could match")
             rb.r2_seq, rb.r2_qual = r2_seq.ctypes.data, r2_qual.ctypes.data
             keep += [r2_seq, r2_qual]
         if select_key is not None:

@@ -110,24 +110,27 @@ def test_csc_fingerprint_adds_up_over_column_blocks():
 
 
 def test_tethered_offset_against_the_reference_pattern_compiler(kats):
-    """tethered_offset() against vectors GENERATED by the reference's own Python compile_pattern
-    (lib/python/cellranger/rna/feature_ref.py:426-465, the twin of feature_extraction.rs:306-342): the capture of its
-    regex on a probe read starts where tethered_offset says; a pattern with bases behind (BC) is refused."""
+    """tethered_offset() / tethered_min_read_length() against vectors GENERATED by the reference's own Python
+    compile_pattern (lib/python/cellranger/rna/feature_ref.py:426-465, the twin of feature_extraction.rs:306-342):
+    the capture of its regex on a probe read starts where tethered_offset says, wildcards behind (BC) included
+    (TotalSeq-B), and its regex stops matching exactly below tethered_min_read_length cycles."""
+    import re
+
     import pytest
 
-    from cellranger_b200.api import tethered_offset
+    from cellranger_b200.api import tethered_min_read_length, tethered_offset
 
-    seen = 0
     for c in kats["tethered_patterns"]["cases"]:
-        if c["pattern"].endswith("(BC)"):
-            off = tethered_offset(c["pattern"])
-            assert off == c["capture_start"], c
-            assert c["probe"][off:off + c["length"]] == c["capture"]
-            seen += 1
-        else:
-            with pytest.raises(ValueError):
-                tethered_offset(c["pattern"])
-    assert seen >= 10
+        off = tethered_offset(c["pattern"])
+        assert off == c["capture_start"], c
+        assert c["probe"][off:off + c["length"]] == c["capture"]
+        need = tethered_min_read_length(c["pattern"], c["length"])
+        rx = re.compile(c["regex"])
+        assert rx.search(c["probe"][:need]) is not None and rx.search(c["probe"][:need - 1]) is None, c
+    assert len(kats["tethered_patterns"]["cases"]) >= 16
+    for bad in ("(BC)", "NN(BC)", "5PACGT(BC)", "5PNN(BC)ACGT", "5P(BC)(BC)", "5PNN(BC)3P", "^(BC)$"):
+        with pytest.raises(ValueError):
+            tethered_offset(bad)
 
 
 def test_barcode_strings_against_the_reference_formatter(kats):
