@@ -77,24 +77,30 @@ class Whitelist:
         return Whitelist(r, t)
 
     @staticmethod
-    def from_txt(path: str) -> "Whitelist":
-        """A whitelist .txt[.gz]: one sequence per line, or `raw translated` pairs
-        (WhitelistSource::iter, barcode/src/whitelist.rs:255-281)."""
+    def from_txt(path: str, translation: Optional[bool] = None) -> "Whitelist":
+        """A whitelist .txt[.gz] as WhitelistSource reads it (barcode/src/whitelist.rs:242-337): every line is split
+        on whitespace, the first column is the sequence, the second (when present) its translation. The file is a
+        translation whitelist exactly when its parent directory is called `translation` (is_translation, :242-253;
+        `translation=` overrides that); then every line needs both columns (as_translation, :299-309), otherwise
+        only the first column counts (as_set, :288-290)."""
         import gzip
+        import os
 
+        if translation is None:
+            translation = os.path.basename(os.path.dirname(os.path.abspath(path))) == "translation"
         op = gzip.open if path.endswith(".gz") else open
         raw, tr = [], []
         with op(path, "rt") as f:
             for line in f:
                 parts = line.split()
                 if not parts:
-                    continue
+                    raise ValueError(f"{path}: empty line in a whitelist")  # iter.next().unwrap() in the reference
                 raw.append(parts[0])
-                if len(parts) > 1:
+                if translation:
+                    if len(parts) < 2:
+                        raise ValueError(f"not a translation whitelist: {path}")
                     tr.append(parts[1])
-        if tr and len(tr) != len(raw):
-            raise ValueError("not a translation whitelist: some lines have one column")
-        return Whitelist.trans(raw, tr) if tr else Whitelist.plain(raw)
+        return Whitelist.trans(raw, tr) if translation else Whitelist.plain(raw)
 
     @property
     def length(self) -> int:

@@ -23,7 +23,8 @@ def test_whitelist_from_txt_plain_and_translation(tmp_path):
     p.write_text("ACGT\nTTTT\n")
     wl = api.Whitelist.from_txt(str(p))
     assert wl.translated is None and wl.length == 4 and wl.seqs.shape == (2, 4)
-    g = tmp_path / "tr.txt.gz"
+    (tmp_path / "translation").mkdir()  # what makes a file a translation whitelist in the reference
+    g = tmp_path / "translation" / "tr.txt.gz"
     with gzip.open(g, "wt") as f:
         f.write("ACGT\tAAAA\nTTTT\tCCCC\n")
     tr = api.Whitelist.from_txt(str(g))
@@ -181,3 +182,32 @@ def test_chemistry_presets_against_the_reference_chemistry_defs(kats):
     assert (lt.bc_offset, lt.bc_length, lt.umi_offset, lt.umi_length) == (0, 16, 16, 12)
     assert e["SC3Pv2"]["barcode"][0]["whitelist"]["name"] == "737K-august-2016"
     assert e["SC3Pv3"]["barcode"][0]["whitelist"]["name"] == "3M-february-2018"
+
+
+def test_whitelist_from_txt_follows_the_reference_reader(tmp_path):
+    """WhitelistSource::{iter, is_translation, as_set, as_translation} (barcode/src/whitelist.rs:242-337): first
+    column = sequence; a translation whitelist is one that lives in a directory called `translation`, and then
+    every line carries the translated sequence too."""
+    import gzip
+
+    import pytest
+
+    from cellranger_b200.api import Whitelist
+
+    plain_dir, trans_dir = tmp_path / "barcodes", tmp_path / "barcodes" / "translation"
+    trans_dir.mkdir(parents=True)
+    (plain_dir / "wl.txt").write_text("AAAACCCCGGGGTTTT\nACGTACGTACGTACGT\n")
+    w = Whitelist.from_txt(str(plain_dir / "wl.txt"))
+    assert w.translated is None and [bytes(s) for s in w.seqs] == [b"AAAACCCCGGGGTTTT", b"ACGTACGTACGTACGT"]
+    # extra columns outside a translation directory are ignored (as_set takes the left column only)
+    (plain_dir / "wl_ids.txt").write_text("AAAACCCCGGGGTTTT\tTTTTGGGGCCCCAAAA\tBC001\nACGTACGTACGTACGT\tTGCATGCATGCATGCA\tBC002\n")
+    w = Whitelist.from_txt(str(plain_dir / "wl_ids.txt"))
+    assert w.translated is None and w.seqs.shape == (2, 16)
+    with gzip.open(trans_dir / "wl.txt.gz", "wt") as f:
+        f.write("AAAACCCCGGGGTTTT TTTTGGGGCCCCAAAA\nACGTACGTACGTACGT TGCATGCATGCATGCA\n")
+    w = Whitelist.from_txt(str(trans_dir / "wl.txt.gz"))
+    assert [bytes(s) for s in w.translated] == [b"TTTTGGGGCCCCAAAA", b"TGCATGCATGCATGCA"]
+    (trans_dir / "broken.txt").write_text("AAAACCCCGGGGTTTT TTTTGGGGCCCCAAAA\nACGTACGTACGTACGT\n")
+    with pytest.raises(ValueError, match="not a translation whitelist"):
+        Whitelist.from_txt(str(trans_dir / "broken.txt"))
+    assert Whitelist.from_txt(str(plain_dir / "wl_ids.txt"), translation=True).translated is not None
